@@ -1,0 +1,421 @@
+"""Batch API: PyTorch tensors in, PyTorch tensors out, CUDA through the C ABI (include/faop.h).
+
+PyTorch is plumbing here — device memory, streams, torch.distributed — and nothing else: every
+number is produced by a hand-written sm_100a kernel in csrc/.  All functions take 1-D structure-of-
+arrays inputs (anything torch.as_tensor accepts; moved to the current CUDA device as float64) and
+return CUDA tensors.  They raise if CUDA or libfaop.so is unavailable; there is no CPU path.
+"""
+import ctypes
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+from numpy.polynomial.legendre import leggauss
+
+from . import _lib
+from ._lib import FaopCfg, FaopSurface, check
+
+
+@dataclass(frozen=True)
+class AloConfig:
+    """Solver knobs; field names follow the reference's attributes
+    (FastAmericanOptionSolverBase.py:19-23, 46-47): collocation_num, quadrature_num, integration_num."""
+    solver: str = "A"
+    n: int = 12            # collocation_num
+    l: int = 24            # quadrature_num
+    m: int = 48            # integration_num (frozen at 2*24 in the reference constructor)
+    iter_tol: float = 1e-5
+    max_iters: int = 200
+    use_derivative: bool = False
+    eta: float = 0.5
+    kernel: int = 0        # 0 = auto (specialised kernel when available), 1 = generic kernel
+
+    def c(self):
+        return FaopCfg(0 if self.solver == "A" else 1, int(bool(self.use_derivative)), int(self.n), int(self.l),
+                       int(self.m), int(self.max_iters), float(self.iter_tol), float(self.eta), int(self.kernel), 0)
+
+
+def _device(device=None):
+    if not torch.cuda.is_available():
+        raise _lib.FaopError("CUDA device required: fastamericanoptionpricing_b200 has no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+
+
+def _f64(x, dev, N=None):
+    t = torch.as_tensor(x, dtype=torch.float64)
+    if t.device != dev:
+        t = t.to(dev, non_blocking=True)
+    t = t.reshape(-1) if t.dim() != 1 else t
+    if N is not None and t.numel() == 1 and N != 1:
+        t = t.expand(N)
+    return t.contiguous()
+
+
+def _u8(x, dev, N=None):
+    t = torch.as_tensor(x)
+    t = t.to(device=dev, dtype=torch.uint8, non_blocking=True).reshape(-1)
+    if N is not None and t.numel() == 1 and N != 1:
+        t = t.expand(N)
+    return t.contiguous()
+
+
+def _ptr(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _stream(dev):
+    return ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+_TABLES = {}
+
+
+def gauss_legendre(num):
+    """The reference's quadrature rule: numpy.polynomial.legendre.leggauss (FastAmericanOptionSolverBase.py:175)."""
+    y, w = leggauss(int(num))
+    return np.ascontiguousarray(y, dtype=np.float64), np.ascontiguousarray(w, dtype=np.float64)
+
+
+def tables_for(cfg: AloConfig, dev):
+    """Device table blob for (n, l, m), built once per device by faop_tables_build."""
+    key = (cfg.n, cfg.l, cfg.m, str(dev))
+    t = _TABLES.get(key)
+    if t is None:
+        lib = _lib.load()
+        c = cfg.c()
+        nbytes = ctypes.c_size_t()
+        check(lib.faop_tables_bytes(ctypes.byref(c), ctypes.byref(nbytes)), "faop_tables_bytes")
+        host = np.empty(nbytes.value // 8, dtype=np.float64)
+        yl, wl = gauss_legendre(cfg.l)
+        ym, wm = gauss_legendre(cfg.m)
+        check(lib.faop_tables_build(ctypes.byref(c), yl.ctypes.data, wl.ctypes.data, ym.ctypes.data, wm.ctypes.data,
+                                    host.ctypes.data), "faop_tables_build")
+        t = torch.from_numpy(host).to(dev)
+        _TABLES[key] = t
+    return t
+
+
+def price_batch(r, q, sigma, K, T, S, is_put, t=None, cfg: AloConfig = AloConfig(), B0=None,
+                want_boundary=True, device=None):
+    """FastAmericanOptionSolver{A,B}.solve(t, s0) for a batch (FastAmericanOptionSolverBase.py:49-76).
+
+    Returns dict(price, european, iters, err[, B, B0, tau]); B/B0/tau are N x (n+1) (node i at
+    tau_i = T (1 + cos(i pi/n))^2 / 4).  B0 (optional, N x (n+1)) borrows a seed boundary instead of the QD seed.
+    """
+    lib = _lib.load()
+    dev = _device(device)
+    with torch.cuda.device(dev):
+        r = _f64(r, dev)
+        N = r.numel()
+        q, sigma, K, T, S = (_f64(x, dev, N) for x in (q, sigma, K, T, S))
+        is_put = _u8(is_put, dev, N)
+        tt = None if t is None else _f64(t, dev, N)
+        for x in (q, sigma, K, T, S, is_put):
+            if x.numel() != N:
+                raise ValueError("all option arrays must have the same length")
+        nn = cfg.n + 1
+        tab = tables_for(cfg, dev)
+        price = torch.empty(N, dtype=torch.float64, device=dev)
+        eur = torch.empty(N, dtype=torch.float64, device=dev)
+        iters = torch.empty(N, dtype=torch.int32, device=dev)
+        err = torch.empty(N, dtype=torch.float64, device=dev)
+        B = torch.empty((N, nn), dtype=torch.float64, device=dev) if want_boundary else None
+        B0_in = None
+        if B0 is not None:
+            B0_in = torch.as_tensor(B0, dtype=torch.float64).to(dev).reshape(N, nn).contiguous()
+            B0_out = None
+            ws = None
+        elif want_boundary:
+            B0_out = torch.empty((N, nn), dtype=torch.float64, device=dev)
+            ws = None
+        else:
+            B0_out = None
+            c = cfg.c()
+            nb = ctypes.c_size_t()
+            check(lib.faop_workspace_bytes(ctypes.byref(c), N, ctypes.byref(nb)), "faop_workspace_bytes")
+            ws = torch.empty(nb.value, dtype=torch.uint8, device=dev)
+        c = cfg.c()
+        check(lib.faop_alo_price_batch(ctypes.byref(c), N, _ptr(r), _ptr(q), _ptr(sigma), _ptr(K), _ptr(T), _ptr(tt),
+                                       _ptr(S), _ptr(is_put), _ptr(tab), _ptr(B0_in), _ptr(price), _ptr(eur), _ptr(B),
+                                       _ptr(B0_out), _ptr(iters), _ptr(err), _ptr(ws), _stream(dev)),
+              "faop_alo_price_batch")
+        out = dict(price=price, european=eur, iters=iters, err=err)
+        if want_boundary:
+            out["B"] = B
+            out["B0"] = B0_in if B0_in is not None else B0_out
+            out["tau"] = collocation_tau(T, cfg.n)
+        return out
+
+
+def collocation_tau(T, n):
+    """set_collocation_points (FastAmericanOptionSolverBase.py:221-223): tau_i = (cos(i pi/n) + 1)^2 T / 4."""
+    c = torch.as_tensor(np.cos(np.arange(n + 1) * np.pi / n), dtype=torch.float64, device=T.device)
+    return (c + 1).square()[None, :] * T[:, None] / 4
+
+
+def eval_nodes_batch(B, r, q, sigma, K, T, is_put, cfg: AloConfig = AloConfig(), device=None):
+    """N_func, D_func, Nprime_func, Dprime_func, compute_f_and_fprime on a given boundary (N x (n+1)).
+    Returns dict(N, D, Nprime, Dprime, f, fprime), each N x n (active nodes)."""
+    lib = _lib.load()
+    dev = _device(device)
+    with torch.cuda.device(dev):
+        r = _f64(r, dev)
+        N = r.numel()
+        q, sigma, K, T = (_f64(x, dev, N) for x in (q, sigma, K, T))
+        is_put = _u8(is_put, dev, N)
+        Bd = torch.as_tensor(B, dtype=torch.float64).to(dev).reshape(N, cfg.n + 1).contiguous()
+        outs = [torch.empty((N, cfg.n), dtype=torch.float64, device=dev) for _ in range(6)]
+        tab = tables_for(cfg, dev)
+        c = cfg.c()
+        check(lib.faop_alo_eval_nodes_batch(ctypes.byref(c), N, _ptr(r), _ptr(q), _ptr(sigma), _ptr(K), _ptr(T),
+                                            _ptr(is_put), _ptr(tab), _ptr(Bd), *[_ptr(o) for o in outs], _stream(dev)),
+              "faop_alo_eval_nodes_batch")
+        return dict(zip(("N", "D", "Nprime", "Dprime", "f", "fprime"), outs))
+
+
+def price_known_boundary_batch(B, r, q, sigma, K, T, S, is_put, t=None, cfg: AloConfig = AloConfig(), device=None):
+    """american_value_with_known_boundary (FastAmericanOptionSolverBase.py:92-103). Returns (price, european)."""
+    lib = _lib.load()
+    dev = _device(device)
+    with torch.cuda.device(dev):
+        r = _f64(r, dev)
+        N = r.numel()
+        q, sigma, K, T, S = (_f64(x, dev, N) for x in (q, sigma, K, T, S))
+        is_put = _u8(is_put, dev, N)
+        tt = None if t is None else _f64(t, dev, N)
+        Bd = torch.as_tensor(B, dtype=torch.float64).to(dev).reshape(N, cfg.n + 1).contiguous()
+        price = torch.empty(N, dtype=torch.float64, device=dev)
+        eur = torch.empty(N, dtype=torch.float64, device=dev)
+        tab = tables_for(cfg, dev)
+        c = cfg.c()
+        check(lib.faop_alo_price_known_boundary_batch(ctypes.byref(c), N, _ptr(r), _ptr(q), _ptr(sigma), _ptr(K), _ptr(T),
+                                                      _ptr(tt), _ptr(S), _ptr(is_put), _ptr(tab), _ptr(Bd), _ptr(price),
+                                                      _ptr(eur), _stream(dev)), "faop_alo_price_known_boundary_batch")
+        return price, eur
+
+
+def surface_batch(surface: dict, first, count, cfg: AloConfig, want_iters=False, device=None, workspace_mb=512):
+    """Config-5 implied-surface sweep; options are decoded from the flat index on the device
+    (workloads.c5_surface defines the index order).  Returns price (and iters)."""
+    lib = _lib.load()
+    dev = _device(device)
+    with torch.cuda.device(dev):
+        s = FaopSurface(surface["K0"], surface["K1"], surface["T0"], surface["T1"], surface["V0"], surface["V1"],
+                        surface["S"], surface["r"], surface["q"], surface["nK"], surface["nT"], surface["nV"],
+                        int(surface.get("is_put", 1)))
+        price = torch.empty(count, dtype=torch.float64, device=dev)
+        iters = torch.empty(count, dtype=torch.int32, device=dev) if want_iters else None
+        ws = torch.empty(workspace_mb << 20, dtype=torch.uint8, device=dev)
+        tab = tables_for(cfg, dev)
+        c = cfg.c()
+        check(lib.faop_alo_surface_batch(ctypes.byref(c), ctypes.byref(s), int(first), int(count), _ptr(tab), _ptr(price),
+                                         _ptr(iters), _ptr(ws), ws.numel(), _stream(dev)), "faop_alo_surface_batch")
+        return (price, iters) if want_iters else price
+
+
+# ------------------------------------------------------------------------------------------ leaf kernels
+def _common(arrs, device):
+    dev = _device(device)
+    first = _f64(arrs[0], dev)
+    N = first.numel()
+    rest = [_f64(x, dev, N) for x in arrs[1:]]
+    N = max([N] + [x.numel() for x in rest])
+    allv = [first.expand(N).contiguous() if first.numel() == 1 and N != 1 else first] + \
+           [x.expand(N).contiguous() if x.numel() == 1 and N != 1 else x for x in rest]
+    return dev, N, allv
+
+
+def qd_boundary_batch(tau, r, q, sigma, K, is_put, device=None):
+    """QDplus.compute_exercise_boundary (QDplusAmericanOptionSolver.py:69-76) per element."""
+    lib = _lib.load()
+    dev, N, (tau, r, q, sigma, K) = _common([tau, r, q, sigma, K], device)
+    with torch.cuda.device(dev):
+        ip = _u8(is_put, dev, N)
+        B = torch.empty(N, dtype=torch.float64, device=dev)
+        check(lib.faop_qd_boundary_batch(N, _ptr(r), _ptr(q), _ptr(sigma), _ptr(K), _ptr(tau), _ptr(ip), _ptr(B), _stream(dev)),
+              "faop_qd_boundary_batch")
+        return B
+
+
+def qd_residual_batch(S, tau, r, q, sigma, K, is_put, device=None):
+    """QDplus.exercise_boundary_func(S, tau) (QDplusAmericanOptionSolver.py:110-125) per element."""
+    lib = _lib.load()
+    dev, N, (S, tau, r, q, sigma, K) = _common([S, tau, r, q, sigma, K], device)
+    with torch.cuda.device(dev):
+        ip = _u8(is_put, dev, N)
+        F = torch.empty(N, dtype=torch.float64, device=dev)
+        check(lib.faop_qd_residual_batch(N, _ptr(r), _ptr(q), _ptr(sigma), _ptr(K), _ptr(tau), _ptr(S), _ptr(ip), _ptr(F),
+                                         _stream(dev)), "faop_qd_residual_batch")
+        return F
+
+
+def qd_price_batch(tau, S, r, q, sigma, K, is_put, device=None):
+    """QDplus.price(tau, S) (QDplusAmericanOptionSolver.py:44-67). Returns (price, exercise_boundary)."""
+    lib = _lib.load()
+    dev, N, (tau, S, r, q, sigma, K) = _common([tau, S, r, q, sigma, K], device)
+    with torch.cuda.device(dev):
+        ip = _u8(is_put, dev, N)
+        P = torch.empty(N, dtype=torch.float64, device=dev)
+        Bd = torch.empty(N, dtype=torch.float64, device=dev)
+        check(lib.faop_qd_price_batch(N, _ptr(r), _ptr(q), _ptr(sigma), _ptr(K), _ptr(tau), _ptr(S), _ptr(ip), _ptr(P),
+                                      _ptr(Bd), _stream(dev)), "faop_qd_price_batch")
+        return P, Bd
+
+
+def european_batch(tau, S, r, q, sigma, K, is_put, device=None):
+    """EuropeanOption.european_put_value / european_call_value (EuropeanOptionSolver.py:7-22)."""
+    lib = _lib.load()
+    dev, N, (tau, S, r, q, sigma, K) = _common([tau, S, r, q, sigma, K], device)
+    with torch.cuda.device(dev):
+        ip = _u8(is_put, dev, N)
+        P = torch.empty(N, dtype=torch.float64, device=dev)
+        check(lib.faop_european_batch(N, _ptr(tau), _ptr(S), _ptr(r), _ptr(q), _ptr(sigma), _ptr(K), _ptr(ip), _ptr(P),
+                                      _stream(dev)), "faop_european_batch")
+        return P
+
+
+def european_greeks_batch(tau, S, r, q, sigma, K, device=None):
+    """european_option_theta, d1, d2 (EuropeanOptionSolver.py:25-40). Returns (theta, d1, d2)."""
+    lib = _lib.load()
+    dev, N, (tau, S, r, q, sigma, K) = _common([tau, S, r, q, sigma, K], device)
+    with torch.cuda.device(dev):
+        th, d1, d2 = (torch.empty(N, dtype=torch.float64, device=dev) for _ in range(3))
+        check(lib.faop_european_greeks_batch(N, _ptr(tau), _ptr(S), _ptr(r), _ptr(q), _ptr(sigma), _ptr(K), _ptr(th),
+                                             _ptr(d1), _ptr(d2), _stream(dev)), "faop_european_greeks_batch")
+        return th, d1, d2
+
+
+def cheb_fit_batch(y, device=None):
+    """ChebyshevInterpolation coefficient fit (ChebyshevInterpolation.py:43-51); y is N x (n+1)."""
+    lib = _lib.load()
+    dev = _device(device)
+    with torch.cuda.device(dev):
+        y = torch.as_tensor(y, dtype=torch.float64).to(dev)
+        y = y.reshape(1, -1) if y.dim() == 1 else y.contiguous()
+        N, nn = y.shape
+        a = torch.empty_like(y)
+        check(lib.faop_cheb_fit_batch(N, nn - 1, _ptr(y), _ptr(a), _stream(dev)), "faop_cheb_fit_batch")
+        return a
+
+
+def cheb_eval_batch(a, z, device=None):
+    """Clenshaw evaluation (ChebyshevInterpolation.py:31-41); a is N x (n+1), z is N x npts in [-1, 1]."""
+    lib = _lib.load()
+    dev = _device(device)
+    with torch.cuda.device(dev):
+        a = torch.as_tensor(a, dtype=torch.float64).to(dev)
+        a = a.reshape(1, -1) if a.dim() == 1 else a.contiguous()
+        z = torch.as_tensor(z, dtype=torch.float64).to(dev)
+        z = z.reshape(1, -1) if z.dim() == 1 else z.contiguous()
+        N, nn = a.shape
+        out = torch.empty_like(z)
+        check(lib.faop_cheb_eval_batch(N, nn - 1, z.shape[1], _ptr(a), _ptr(z), _ptr(out), _stream(dev)), "faop_cheb_eval_batch")
+        return out
+
+
+# ------------------------------------------------------------------------------------------ Crank-Nicolson
+def cn_dt_schedule(T, max_dt):
+    """CNOptionSolver.solvePDE's float countdown (CrankNicolsonOptionSolver.py:36-45), host-side control logic."""
+    out = []
+    t = float(T)
+    max_dt = float(max_dt)
+    while t > 0:
+        dt = min(t, max_dt)
+        out.append(dt)
+        t -= dt
+    return out
+
+
+CN_MODE_DIRECT, CN_MODE_SOR, CN_MODE_PROJECTED = 0, 1, 2
+
+
+def cn_put_batch(r, q, sigma, K, T, S0, n_space=200, max_dt=1 / 12.0, mode=CN_MODE_PROJECTED, omega=1.2, tol=1e-5,
+                 max_iter=200, want_grid=False, device=None):
+    """CNOptionSolver(r,q,sigma,K,T).solve(S0) for a batch of American puts (CrankNicolsonOptionSolver.py:27-107).
+    mode 0 = the reference default (dense solve, no projection), 1 = the reference's SOR+project loop,
+    2 = projected tridiagonal sweep.  Returns price (and the final grid values X, N x n_space)."""
+    lib = _lib.load()
+    dev, N, (r, q, sigma, K, T, S0) = _common([r, q, sigma, K, T, S0], device)
+    with torch.cuda.device(dev):
+        Th = T.cpu().numpy()
+        mdt = np.broadcast_to(np.asarray(max_dt, dtype=np.float64), (N,))
+        if np.all(Th == Th[0]) and np.all(mdt == mdt[0]):
+            s0 = cn_dt_schedule(Th[0], mdt[0])
+            dts = np.tile(np.asarray(s0), (N, 1))
+            ns = np.full(N, len(s0), dtype=np.int32)
+        else:
+            sched = [cn_dt_schedule(Th[i], mdt[i]) for i in range(N)]
+            ms = max(len(s) for s in sched)
+            dts = np.zeros((N, ms))
+            ns = np.zeros(N, dtype=np.int32)
+            for i, s in enumerate(sched):
+                dts[i, :len(s)] = s
+                ns[i] = len(s)
+        dts_d = torch.from_numpy(np.ascontiguousarray(dts)).to(dev)
+        ns_d = torch.from_numpy(ns).to(dev)
+        price = torch.empty(N, dtype=torch.float64, device=dev)
+        X = torch.empty((N, n_space), dtype=torch.float64, device=dev) if want_grid else None
+        nb = ctypes.c_size_t()
+        check(lib.faop_cn_workspace_bytes(N, n_space, mode, ctypes.byref(nb)), "faop_cn_workspace_bytes")
+        ws = torch.empty(max(nb.value, 1), dtype=torch.uint8, device=dev)
+        check(lib.faop_cn_put_batch(N, n_space, mode, _ptr(r), _ptr(q), _ptr(sigma), _ptr(K), _ptr(S0), _ptr(dts_d),
+                                    _ptr(ns_d), dts.shape[1], float(omega), float(tol), int(max_iter), _ptr(price), _ptr(X),
+                                    _ptr(ws), _stream(dev)), "faop_cn_put_batch")
+        return (price, X) if want_grid else price
+
+
+# ------------------------------------------------------------------------------------------ misc
+def launch_count():
+    return int(_lib.load().faop_launch_count())
+
+
+def measure_fp64_peak(launches=20, device=None):
+    """DFMA-pipe peak of this GPU in TFLOP/s (the roofline denominator): returns (tflops, ms_per_launch)."""
+    lib = _lib.load()
+    dev = _device(device)
+    with torch.cuda.device(dev):
+        tf, ms = ctypes.c_double(), ctypes.c_double()
+        check(lib.faop_measure_fp64_peak(int(launches), ctypes.byref(tf), ctypes.byref(ms), _stream(dev)),
+              "faop_measure_fp64_peak")
+        return tf.value, ms.value
+
+
+class HostContext:
+    """faop_ctx wrapper: the host-buffer entry point (numpy / pinned host arrays in and out), used by the
+    e2e leg of bench.py and by callers that do not hold device memory."""
+
+    def __init__(self, device=0):
+        self._lib = _lib.load()
+        self._h = ctypes.c_void_p()
+        check(self._lib.faop_ctx_create(int(device), ctypes.byref(self._h)), "faop_ctx_create")
+
+    def close(self):
+        if self._h:
+            self._lib.faop_ctx_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def price_batch(self, r, q, sigma, K, T, S, is_put, t=None, cfg: AloConfig = AloConfig(), out=None, want_boundary=False):
+        """Host arrays (numpy float64 / uint8; pinned memory makes the copies asynchronous) -> dict of numpy arrays."""
+        def hp(a):
+            return None if a is None else ctypes.c_void_p(a.ctypes.data if isinstance(a, np.ndarray) else a.data_ptr())
+        N = len(r)
+        nn = cfg.n + 1
+        if out is None:
+            out = dict(price=np.empty(N), european=np.empty(N), iters=np.empty(N, dtype=np.int32), err=np.empty(N))
+            if want_boundary:
+                out["B"] = np.empty((N, nn))
+                out["B0"] = np.empty((N, nn))
+        yl, wl = gauss_legendre(cfg.l)
+        ym, wm = gauss_legendre(cfg.m)
+        c = cfg.c()
+        check(self._lib.faop_alo_price_batch_host(self._h, ctypes.byref(c), N, hp(r), hp(q), hp(sigma), hp(K), hp(T), hp(t),
+                                                  hp(S), hp(is_put), hp(yl), hp(wl), hp(ym), hp(wm), None, hp(out["price"]),
+                                                  hp(out.get("european")), hp(out.get("B")), hp(out.get("B0")),
+                                                  hp(out.get("iters")), hp(out.get("err"))), "faop_alo_price_batch_host")
+        return out

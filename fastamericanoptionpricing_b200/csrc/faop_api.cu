@@ -1,0 +1,367 @@
+// faop_api.cu — the C ABI of libfaop.so (include/faop.h): argument checks, table construction,
+// kernel dispatch, and the host-buffer convenience path.  No compute happens on the host except the
+// one-time construction of the (option-independent) quadrature/collocation tables.
+#include <stdlib.h>
+#include <string.h>
+
+#include <new>
+#include <vector>
+
+#include "faop_kernels.h"
+
+namespace faop {
+unsigned long long g_launches = 0;
+
+static int check_cfg(const faop_cfg* cfg) {
+    if (!cfg) return FAOP_EINVAL;
+    if (cfg->solver < 0 || cfg->solver > 1) return FAOP_EINVAL;
+    if (cfg->n_colloc < 2 || cfg->n_colloc > FAOP_MAX_COLLOC) return FAOP_ERANGE;
+    if (cfg->n_quad < 1 || cfg->n_quad > FAOP_MAX_QUAD) return FAOP_ERANGE;
+    if (cfg->n_price_quad < 1 || cfg->n_price_quad > FAOP_MAX_QUAD) return FAOP_ERANGE;
+    if (cfg->max_iters < 0) return FAOP_EINVAL;
+    return 0;
+}
+
+static void fill_rule(double* w, double* h, double* rh, double* sg, const double* y, const double* wt, int cnt, int padded) {
+    for (int k = 0; k < padded; ++k) {
+        double yk = k < cnt ? y[k] : 0.0;
+        double hk = (1.0 + yk) * 0.5;
+        w[k] = k < cnt ? wt[k] : 0.0;
+        h[k] = hk;
+        rh[k] = 1.0 / hk;
+        sg[k] = sqrt(0.5 * (1.0 - yk) * (1.0 + hk));  // sqrt(1 - h^2) without cancellation near y = 1
+    }
+}
+}  // namespace faop
+
+using namespace faop;
+
+extern "C" {
+
+int faop_version(void) { return FAOP_VERSION; }
+int64_t faop_launch_count(void) { return (int64_t)__atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
+
+int faop_tables_bytes(const faop_cfg* cfg, size_t* bytes) {
+    int rc = check_cfg(cfg);
+    if (rc) return rc;
+    if (!bytes) return FAOP_EINVAL;
+    TableLayout tl = table_layout(cfg->n_colloc, cfg->n_quad, cfg->n_price_quad);
+    *bytes = sizeof(double) * (size_t)tl.total;
+    return 0;
+}
+
+int faop_tables_build(const faop_cfg* cfg, const double* y_l, const double* w_l, const double* y_m, const double* w_m,
+                      void* host_out) {
+    int rc = check_cfg(cfg);
+    if (rc) return rc;
+    if (!y_l || !w_l || !y_m || !w_m || !host_out) return FAOP_EINVAL;
+    const int n = cfg->n_colloc;
+    TableLayout tl = table_layout(n, cfg->n_quad, cfg->n_price_quad);
+    double* t = (double*)host_out;
+    memset(t, 0, sizeof(double) * (size_t)tl.total);
+    fill_rule(t + tl.off_wl, t + tl.off_hl, t + tl.off_rhl, t + tl.off_sgl, y_l, w_l, tl.l, tl.LP);
+    fill_rule(t + tl.off_wm, t + tl.off_hm, t + tl.off_rhm, t + tl.off_sgm, y_m, w_m, tl.m, tl.MP);
+    for (int i = 0; i <= n; ++i) t[tl.off_c + i] = cos(i * M_PI / n);  // ChebyshevInterpolation.py:15-17
+    for (int j = 0; j < 2 * n; ++j) t[tl.off_cos + j] = cos(j * M_PI / n);
+    t[tl.off_cos + n] = -1.0;
+    if (tl.has_matrix) {
+        // M[i][j][k] = value at z_ik = (1+c_i) sqrt(g_k) - 1 of the Chebyshev interpolant of the unit vector e_j
+        // (DCT-I fit ChebyshevInterpolation.py:43-51 followed by Clenshaw :31-41), in long double.
+        std::vector<long double> a(n + 1);
+        for (int j = 0; j <= n; ++j) {
+            for (int kk = 0; kk <= n; ++kk) {
+                long double v = cosl((long double)((j * kk) % (2 * n)) * (long double)M_PIl / n);
+                if (j == 0 || j == n) v *= 0.5L;
+                a[kk] = v * (2.0L / n);
+            }
+            for (int i = 0; i < n; ++i) {
+                for (int k = 0; k < tl.LP; ++k) {
+                    long double z = (1.0L + (long double)t[tl.off_c + i]) * (long double)t[tl.off_sgl + k] - 1.0L;
+                    long double b0 = a[n] * 0.5L, b1 = 0, b2 = 0;
+                    for (int kk = n - 1; kk >= 0; --kk) {
+                        b2 = b1;
+                        b1 = b0;
+                        b0 = a[kk] + 2 * z * b1 - b2;
+                    }
+                    t[tl.off_M + ((size_t)i * (n + 1) + j) * tl.LP + k] = (double)(0.5L * (b0 - b2));
+                }
+            }
+        }
+    }
+    return 0;
+}
+
+int faop_workspace_bytes(const faop_cfg* cfg, int64_t N, size_t* bytes) {
+    int rc = check_cfg(cfg);
+    if (rc) return rc;
+    if (!bytes || N < 0) return FAOP_EINVAL;
+    size_t b = sizeof(double) * (size_t)N * (size_t)(cfg->n_colloc + 1);
+    *bytes = (b + 255) & ~(size_t)255;
+    return 0;
+}
+
+static int fill_args(AloArgs& a, const faop_cfg* cfg, int64_t N, const double* r, const double* q, const double* sigma,
+                     const double* K, const double* T, const double* t, const double* S, const uint8_t* is_put,
+                     const void* tables_dev) {
+    int rc = check_cfg(cfg);
+    if (rc) return rc;
+    if (N < 0) return FAOP_EINVAL;
+    if (N > 0 && (!r || !q || !sigma || !K || !T || !is_put || !tables_dev)) return FAOP_EINVAL;
+    memset(&a, 0, sizeof a);
+    a.cfg = *cfg;
+    a.tl = table_layout(cfg->n_colloc, cfg->n_quad, cfg->n_price_quad);
+    a.N = N;
+    a.r = r; a.q = q; a.sigma = sigma; a.K = K; a.T = T; a.t = t; a.S = S; a.is_put = is_put;
+    a.tables = (const double*)tables_dev;
+    return 0;
+}
+
+int faop_alo_price_batch(const faop_cfg* cfg, int64_t N, const double* r, const double* q, const double* sigma,
+                         const double* K, const double* T, const double* t, const double* S, const uint8_t* is_put,
+                         const void* tables_dev, const double* B0_in, double* price, double* european, double* B,
+                         double* B0_out, int32_t* iters, double* err, void* workspace, void* cuda_stream) {
+    AloArgs a;
+    int rc = fill_args(a, cfg, N, r, q, sigma, K, T, t, S, is_put, tables_dev);
+    if (rc) return rc;
+    if (N == 0) return 0;
+    if (!S || !price) return FAOP_EINVAL;
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    a.price = price; a.european = european; a.B = B; a.iters = iters; a.err = err;
+    const size_t seed_bytes = sizeof(double) * (size_t)N * (size_t)(cfg->n_colloc + 1);
+    if (B0_in) {
+        a.seeds_in = B0_in;
+        if (B0_out && B0_out != B0_in) FAOP_CUDA_OK(cudaMemcpyAsync(B0_out, B0_in, seed_bytes, cudaMemcpyDeviceToDevice, st));
+    } else {
+        a.seeds_out = B0_out ? B0_out : (double*)workspace;
+        if (!a.seeds_out) return FAOP_EINVAL;
+        rc = launch_qd_seed(a, st);
+        if (rc) return rc;
+        a.seeds_in = a.seeds_out;
+    }
+    if (cfg->kernel == 0) {
+        rc = launch_alo_fast(a, st);
+        if (rc != -1000) return rc;
+    }
+    return launch_alo_generic(a, st);
+}
+
+int faop_alo_surface_batch(const faop_cfg* cfg, const faop_surface* surf, int64_t first, int64_t count,
+                           const void* tables_dev, double* price, int32_t* iters, void* workspace,
+                           size_t workspace_bytes, void* cuda_stream) {
+    int rc = check_cfg(cfg);
+    if (rc) return rc;
+    if (!surf || first < 0 || count < 0 || surf->nK < 1 || surf->nT < 1 || surf->nV < 1) return FAOP_EINVAL;
+    if (first + count > (int64_t)surf->nK * surf->nT * surf->nV) return FAOP_EINVAL;
+    if (count == 0) return 0;
+    if (!price || !workspace || !tables_dev) return FAOP_EINVAL;
+    // per-option scratch: 6 parameter doubles + 8 B flag slot + the seed row
+    const size_t per = sizeof(double) * (size_t)(7 + cfg->n_colloc + 1);
+    int64_t chunk = (int64_t)(workspace_bytes / per) & ~(int64_t)255;
+    if (chunk < 256) return FAOP_EINVAL;
+    if (chunk > count) chunk = (count + 255) & ~(int64_t)255;
+    double* w = (double*)workspace;
+    double *d_r = w, *d_q = w + chunk, *d_s = w + 2 * chunk, *d_K = w + 3 * chunk, *d_T = w + 4 * chunk, *d_S = w + 5 * chunk;
+    uint8_t* d_put = (uint8_t*)(w + 6 * chunk);
+    double* d_seed = w + 7 * chunk;
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    for (int64_t off = 0; off < count; off += chunk) {
+        int64_t cnt = count - off < chunk ? count - off : chunk;
+        rc = launch_surface_decode(*surf, first + off, cnt, d_r, d_q, d_s, d_K, d_T, d_S, d_put, st);
+        if (rc) return rc;
+        rc = faop_alo_price_batch(cfg, cnt, d_r, d_q, d_s, d_K, d_T, nullptr, d_S, d_put, tables_dev, nullptr, price + off,
+                                  nullptr, nullptr, nullptr, iters ? iters + off : nullptr, nullptr, d_seed, st);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+int faop_alo_eval_nodes_batch(const faop_cfg* cfg, int64_t N, const double* r, const double* q, const double* sigma,
+                              const double* K, const double* T, const uint8_t* is_put, const void* tables_dev,
+                              const double* B, double* Nv, double* Dv, double* Np, double* Dp, double* f, double* fp,
+                              void* cuda_stream) {
+    AloArgs a;
+    int rc = fill_args(a, cfg, N, r, q, sigma, K, T, nullptr, nullptr, is_put, tables_dev);
+    if (rc) return rc;
+    if (N == 0) return 0;
+    if (!B) return FAOP_EINVAL;
+    a.seeds_in = B;
+    EvalOut eo = {Nv, Dv, Np, Dp, f, fp};
+    return launch_alo_eval_nodes(a, eo, (cudaStream_t)cuda_stream);
+}
+
+int faop_alo_price_known_boundary_batch(const faop_cfg* cfg, int64_t N, const double* r, const double* q,
+                                        const double* sigma, const double* K, const double* T, const double* t,
+                                        const double* S, const uint8_t* is_put, const void* tables_dev, const double* B,
+                                        double* price, double* european, void* cuda_stream) {
+    AloArgs a;
+    int rc = fill_args(a, cfg, N, r, q, sigma, K, T, t, S, is_put, tables_dev);
+    if (rc) return rc;
+    if (N == 0) return 0;
+    if (!B || !S || !price) return FAOP_EINVAL;
+    a.seeds_in = B;
+    a.price = price;
+    a.european = european;
+    return launch_alo_price_known(a, (cudaStream_t)cuda_stream);
+}
+
+int faop_qd_boundary_batch(int64_t N, const double* r, const double* q, const double* sigma, const double* K,
+                           const double* tau, const uint8_t* is_put, double* B, void* cuda_stream) {
+    if (N < 0 || (N > 0 && (!r || !q || !sigma || !K || !tau || !is_put || !B))) return FAOP_EINVAL;
+    return launch_qd_boundary(N, r, q, sigma, K, tau, is_put, B, (cudaStream_t)cuda_stream);
+}
+int faop_qd_residual_batch(int64_t N, const double* r, const double* q, const double* sigma, const double* K,
+                           const double* tau, const double* S, const uint8_t* is_put, double* F, void* cuda_stream) {
+    if (N < 0 || (N > 0 && (!r || !q || !sigma || !K || !tau || !S || !is_put || !F))) return FAOP_EINVAL;
+    return launch_qd_residual(N, r, q, sigma, K, tau, S, is_put, F, (cudaStream_t)cuda_stream);
+}
+int faop_qd_price_batch(int64_t N, const double* r, const double* q, const double* sigma, const double* K,
+                        const double* tau, const double* S, const uint8_t* is_put, double* price, double* boundary,
+                        void* cuda_stream) {
+    if (N < 0 || (N > 0 && (!r || !q || !sigma || !K || !tau || !S || !is_put || !price))) return FAOP_EINVAL;
+    return launch_qd_price(N, r, q, sigma, K, tau, S, is_put, price, boundary, (cudaStream_t)cuda_stream);
+}
+int faop_european_batch(int64_t N, const double* tau, const double* S, const double* r, const double* q,
+                        const double* sigma, const double* K, const uint8_t* is_put, double* price, void* cuda_stream) {
+    if (N < 0 || (N > 0 && (!tau || !S || !r || !q || !sigma || !K || !is_put || !price))) return FAOP_EINVAL;
+    return launch_european(N, tau, S, r, q, sigma, K, is_put, price, (cudaStream_t)cuda_stream);
+}
+int faop_european_greeks_batch(int64_t N, const double* tau, const double* S, const double* r, const double* q,
+                               const double* sigma, const double* K, double* theta, double* d1, double* d2,
+                               void* cuda_stream) {
+    if (N < 0 || (N > 0 && (!tau || !S || !r || !q || !sigma || !K))) return FAOP_EINVAL;
+    return launch_european_greeks(N, tau, S, r, q, sigma, K, theta, d1, d2, (cudaStream_t)cuda_stream);
+}
+int faop_cheb_fit_batch(int64_t N, int32_t n, const double* y, double* a, void* cuda_stream) {
+    if (N < 0 || n < 1 || (N > 0 && (!y || !a))) return FAOP_EINVAL;
+    return launch_cheb_fit(N, n, y, a, (cudaStream_t)cuda_stream);
+}
+int faop_cheb_eval_batch(int64_t N, int32_t n, int32_t npts, const double* a, const double* z, double* out,
+                         void* cuda_stream) {
+    if (N < 0 || n < 1 || npts < 0 || (N > 0 && npts > 0 && (!a || !z || !out))) return FAOP_EINVAL;
+    return launch_cheb_eval(N, n, npts, a, z, out, (cudaStream_t)cuda_stream);
+}
+
+int faop_measure_fp64_peak(int launches, double* tflops, double* ms_per_launch, void* cuda_stream) {
+    if (launches < 1) return FAOP_EINVAL;
+    return launch_fp64_peak(launches, tflops, ms_per_launch, (cudaStream_t)cuda_stream);
+}
+
+// ------------------------------------------------------------------------------------------ host-buffer path
+struct faop_ctx {
+    int device;
+    cudaStream_t stream;
+    void* dev;          // one growing device arena
+    size_t dev_bytes;
+    void* tables_dev;   // cached table blob
+    faop_cfg tables_cfg;
+    size_t tables_bytes;
+    std::vector<double> tables_key;  // the y/w values the cached blob was built from
+};
+
+int faop_ctx_create(int device, faop_ctx** out) {
+    if (!out) return FAOP_EINVAL;
+    FAOP_CUDA_OK(cudaSetDevice(device));
+    faop_ctx* c = new (std::nothrow) faop_ctx();
+    if (!c) return FAOP_ENOMEM;
+    c->device = device;
+    c->dev = nullptr; c->dev_bytes = 0; c->tables_dev = nullptr; c->tables_bytes = 0;
+    memset(&c->tables_cfg, 0, sizeof c->tables_cfg);
+    cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { delete c; return (int)e; }
+    *out = c;
+    return 0;
+}
+
+int faop_ctx_destroy(faop_ctx* c) {
+    if (!c) return 0;
+    cudaSetDevice(c->device);
+    if (c->dev) cudaFree(c->dev);
+    if (c->tables_dev) cudaFree(c->tables_dev);
+    cudaStreamDestroy(c->stream);
+    delete c;
+    return 0;
+}
+
+static int ctx_tables(faop_ctx* c, const faop_cfg* cfg, const double* y_l, const double* w_l, const double* y_m,
+                      const double* w_m) {
+    std::vector<double> key;
+    key.insert(key.end(), y_l, y_l + cfg->n_quad);
+    key.insert(key.end(), w_l, w_l + cfg->n_quad);
+    key.insert(key.end(), y_m, y_m + cfg->n_price_quad);
+    key.insert(key.end(), w_m, w_m + cfg->n_price_quad);
+    bool same = c->tables_dev && c->tables_cfg.n_colloc == cfg->n_colloc && c->tables_cfg.n_quad == cfg->n_quad &&
+                c->tables_cfg.n_price_quad == cfg->n_price_quad && key.size() == c->tables_key.size() &&
+                memcmp(key.data(), c->tables_key.data(), key.size() * sizeof(double)) == 0;
+    if (same) return 0;
+    size_t bytes = 0;
+    int rc = faop_tables_bytes(cfg, &bytes);
+    if (rc) return rc;
+    std::vector<char> host(bytes);
+    rc = faop_tables_build(cfg, y_l, w_l, y_m, w_m, host.data());
+    if (rc) return rc;
+    if (c->tables_dev) { cudaFree(c->tables_dev); c->tables_dev = nullptr; }
+    FAOP_CUDA_OK(cudaMalloc(&c->tables_dev, bytes));
+    FAOP_CUDA_OK(cudaMemcpy(c->tables_dev, host.data(), bytes, cudaMemcpyHostToDevice));
+    c->tables_cfg = *cfg;
+    c->tables_bytes = bytes;
+    c->tables_key.swap(key);
+    return 0;
+}
+
+int faop_alo_price_batch_host(faop_ctx* c, const faop_cfg* cfg, int64_t N, const double* r, const double* q,
+                              const double* sigma, const double* K, const double* T, const double* t, const double* S,
+                              const uint8_t* is_put, const double* y_l, const double* w_l, const double* y_m,
+                              const double* w_m, const double* B0_in, double* price, double* european, double* B,
+                              double* B0_out, int32_t* iters, double* err) {
+    if (!c) return FAOP_EINVAL;
+    int rc = check_cfg(cfg);
+    if (rc) return rc;
+    if (N < 0) return FAOP_EINVAL;
+    if (N == 0) return 0;
+    if (!r || !q || !sigma || !K || !T || !S || !is_put || !price || !y_l || !w_l || !y_m || !w_m) return FAOP_EINVAL;
+    FAOP_CUDA_OK(cudaSetDevice(c->device));
+    rc = ctx_tables(c, cfg, y_l, w_l, y_m, w_m);
+    if (rc) return rc;
+    const size_t nn = (size_t)cfg->n_colloc + 1;
+    const size_t vec = ((size_t)N * sizeof(double) + 255) & ~(size_t)255;
+    const size_t mat = ((size_t)N * nn * sizeof(double) + 255) & ~(size_t)255;
+    // arena: r q sigma K T t S | price european err | is_put iters | B0 B
+    size_t need = 10 * vec + 2 * vec + 2 * mat;
+    if (need > c->dev_bytes) {
+        if (c->dev) { cudaFree(c->dev); c->dev = nullptr; c->dev_bytes = 0; }
+        FAOP_CUDA_OK(cudaMalloc(&c->dev, need));
+        c->dev_bytes = need;
+    }
+    char* p = (char*)c->dev;
+    auto take = [&](size_t b) { char* q_ = p; p += b; return q_; };
+    double* d_r = (double*)take(vec); double* d_q = (double*)take(vec); double* d_s = (double*)take(vec);
+    double* d_K = (double*)take(vec); double* d_T = (double*)take(vec); double* d_t = (double*)take(vec);
+    double* d_S = (double*)take(vec); double* d_price = (double*)take(vec); double* d_eur = (double*)take(vec);
+    double* d_err = (double*)take(vec); uint8_t* d_put = (uint8_t*)take(vec); int32_t* d_it = (int32_t*)take(vec);
+    double* d_B0 = (double*)take(mat); double* d_B = (double*)take(mat);
+    cudaStream_t st = c->stream;
+    const size_t vb = (size_t)N * sizeof(double);
+    FAOP_CUDA_OK(cudaMemcpyAsync(d_r, r, vb, cudaMemcpyHostToDevice, st));
+    FAOP_CUDA_OK(cudaMemcpyAsync(d_q, q, vb, cudaMemcpyHostToDevice, st));
+    FAOP_CUDA_OK(cudaMemcpyAsync(d_s, sigma, vb, cudaMemcpyHostToDevice, st));
+    FAOP_CUDA_OK(cudaMemcpyAsync(d_K, K, vb, cudaMemcpyHostToDevice, st));
+    FAOP_CUDA_OK(cudaMemcpyAsync(d_T, T, vb, cudaMemcpyHostToDevice, st));
+    if (t) FAOP_CUDA_OK(cudaMemcpyAsync(d_t, t, vb, cudaMemcpyHostToDevice, st));
+    FAOP_CUDA_OK(cudaMemcpyAsync(d_S, S, vb, cudaMemcpyHostToDevice, st));
+    FAOP_CUDA_OK(cudaMemcpyAsync(d_put, is_put, (size_t)N, cudaMemcpyHostToDevice, st));
+    if (B0_in) FAOP_CUDA_OK(cudaMemcpyAsync(d_B0, B0_in, (size_t)N * nn * sizeof(double), cudaMemcpyHostToDevice, st));
+    rc = faop_alo_price_batch(cfg, N, d_r, d_q, d_s, d_K, d_T, t ? d_t : nullptr, d_S, d_put, c->tables_dev,
+                              B0_in ? d_B0 : nullptr, d_price, european ? d_eur : nullptr, B ? d_B : nullptr,
+                              B0_in ? nullptr : d_B0, iters ? d_it : nullptr, err ? d_err : nullptr, nullptr, st);
+    if (rc) return rc;
+    FAOP_CUDA_OK(cudaMemcpyAsync(price, d_price, vb, cudaMemcpyDeviceToHost, st));
+    if (european) FAOP_CUDA_OK(cudaMemcpyAsync(european, d_eur, vb, cudaMemcpyDeviceToHost, st));
+    if (err) FAOP_CUDA_OK(cudaMemcpyAsync(err, d_err, vb, cudaMemcpyDeviceToHost, st));
+    if (iters) FAOP_CUDA_OK(cudaMemcpyAsync(iters, d_it, (size_t)N * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    if (B) FAOP_CUDA_OK(cudaMemcpyAsync(B, d_B, (size_t)N * nn * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (B0_out) FAOP_CUDA_OK(cudaMemcpyAsync(B0_out, d_B0, (size_t)N * nn * sizeof(double), cudaMemcpyDeviceToHost, st));
+    FAOP_CUDA_OK(cudaStreamSynchronize(st));
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,50 @@
+// faop_kernels.h — internal launch interface between the C-ABI layer (faop_api.cu) and the kernels.
+#pragma once
+#include "faop_common.cuh"
+
+namespace faop {
+
+struct AloArgs {
+    faop_cfg cfg;
+    TableLayout tl;
+    int64_t N;
+    const double *r, *q, *sigma, *K, *T, *t, *S;
+    const uint8_t* is_put;
+    const double* tables;    // device table blob (faop_tables_build)
+    const double* seeds_in;  // N x (n+1) boundary the solve starts from (QD seed or borrowed B0)
+    double* seeds_out;       // where qd_seed_kernel writes
+    double *price, *european, *B;
+    int32_t* iters;
+    double* err;
+};
+
+struct EvalOut {
+    double *Nv, *Dv, *Np, *Dp, *f, *fp;
+};
+
+int launch_qd_seed(const AloArgs& a, cudaStream_t st);
+int launch_alo_generic(const AloArgs& a, cudaStream_t st);
+int launch_alo_eval_nodes(const AloArgs& a, const EvalOut& eo, cudaStream_t st);
+int launch_alo_price_known(const AloArgs& a, cudaStream_t st);
+// specialised kernels (faop_alo_fast.cu); returns -1000 when no specialisation matches the config
+int launch_alo_fast(const AloArgs& a, cudaStream_t st);
+
+int launch_qd_boundary(int64_t N, const double* r, const double* q, const double* sigma, const double* K,
+                       const double* tau, const uint8_t* is_put, double* B, cudaStream_t st);
+int launch_qd_residual(int64_t N, const double* r, const double* q, const double* sigma, const double* K,
+                       const double* tau, const double* S, const uint8_t* is_put, double* F, cudaStream_t st);
+int launch_qd_price(int64_t N, const double* r, const double* q, const double* sigma, const double* K,
+                    const double* tau, const double* S, const uint8_t* is_put, double* price, double* boundary,
+                    cudaStream_t st);
+int launch_european(int64_t N, const double* tau, const double* S, const double* r, const double* q,
+                    const double* sigma, const double* K, const uint8_t* is_put, double* price, cudaStream_t st);
+int launch_european_greeks(int64_t N, const double* tau, const double* S, const double* r, const double* q,
+                           const double* sigma, const double* K, double* theta, double* d1, double* d2, cudaStream_t st);
+int launch_cheb_fit(int64_t N, int n, const double* y, double* a, cudaStream_t st);
+int launch_cheb_eval(int64_t N, int n, int npts, const double* a, const double* z, double* out, cudaStream_t st);
+
+int launch_surface_decode(const faop_surface& s, int64_t first, int64_t count, double* r, double* q, double* sigma,
+                          double* K, double* T, double* S, uint8_t* is_put, cudaStream_t st);
+int launch_fp64_peak(int launches, double* tflops, double* ms_per_launch, cudaStream_t st);
+
+}  // namespace faop

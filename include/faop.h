@@ -1,0 +1,193 @@
+/* faop.h — C ABI of libfaop.so, the B200 (sm_100a) batched American option pricer.
+ *
+ * This is the drop-in boundary for the one data-parallel hot path of
+ * antdvid/FastAmericanOptionPricing: the Andersen-Lake-Offengenden spectral-collocation
+ * solve of the early-exercise boundary and the price integral, plus the leaf closed forms
+ * and the Crank-Nicolson cross-check solver.  The reference is pure Python with no FFI of
+ * its own; every entry point below names the reference interface (file:line, relative to
+ * the reference root) whose work it replaces.  INTEGRATION.md shows the ctypes stub a
+ * maintainer of the reference would add.
+ *
+ * Conventions
+ *  - plain C, no torch types: pointers + sizes.  All arrays are contiguous structure-of-arrays,
+ *    FP64 unless stated; `is_put` is one byte per option (1 = put, 0 = call; the reference's
+ *    OptionType enum Call=1/Put=2, QDplusAmericanOptionSolver.py:8-10, maps to this flag).
+ *  - functions ending in `_host` take HOST pointers and do their own H2D/D2H staging through a
+ *    faop_ctx; all others take DEVICE pointers owned by the caller, never allocate or free
+ *    user-visible memory, are asynchronous on `cuda_stream` (a cudaStream_t, NULL = default
+ *    stream) and keep no global mutable state.
+ *  - return value: 0 on success, a positive cudaError_t value for CUDA failures, or a negative
+ *    FAOP_E* code for bad arguments.  Never throws, never aborts.  Numerical failure is not an
+ *    error: NaN propagates and non-convergence is visible only through iters/err, exactly as in
+ *    the reference (FastAmericanOptionSolverBase.py:119-133).
+ *  - there is no CPU fallback anywhere in this library.
+ */
+#ifndef FAOP_H
+#define FAOP_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FAOP_VERSION 100
+
+#define FAOP_EINVAL  (-1) /* bad argument (null pointer, size out of range) */
+#define FAOP_ERANGE  (-2) /* configuration outside the compiled limits       */
+#define FAOP_ENOMEM  (-3) /* host allocation failed                          */
+
+#define FAOP_MAX_COLLOC 64  /* n  <= 64  (nodes n+1)                           */
+#define FAOP_MAX_QUAD   128 /* l, m <= 128                                     */
+
+/* Solver knobs = the reference's post-construction attributes
+ * (FastAmericanOptionSolverBase.py:19-23, 46-47; eta is the local at :145). */
+typedef struct faop_cfg {
+    int32_t solver;         /* 0 = FastAmericanOptionSolverA, 1 = FastAmericanOptionSolverB  */
+    int32_t use_derivative; /* self.use_derivative                                            */
+    int32_t n_colloc;       /* self.collocation_num  (n; nodes = n+1)                         */
+    int32_t n_quad;         /* self.quadrature_num   (l)                                      */
+    int32_t n_price_quad;   /* self.integration_num  (m)                                      */
+    int32_t max_iters;      /* self.max_iters                                                 */
+    double  iter_tol;       /* self.iter_tol                                                  */
+    double  eta;            /* 0.5 in the reference                                           */
+    int32_t kernel;         /* 0 = auto (specialised kernel when one exists for (solver,n,l)),
+                               1 = force the generic kernel; results agree to rounding          */
+    int32_t reserved;
+} faop_cfg;
+
+/* ---- tables ---------------------------------------------------------------------------------
+ * Gauss-Legendre nodes/weights are produced by the CALLER with numpy.polynomial.legendre.leggauss
+ * (the reference's own call, FastAmericanOptionSolverBase.py:175) so the device sees the same bits.
+ * faop_tables_build packs them, the Chebyshev nodes cos(i pi/n) (ChebyshevInterpolation.py:15-17),
+ * the cosine table of the DCT-I fit (ChebyshevInterpolation.py:43-51) and, when it fits in shared
+ * memory, the option-independent interpolation matrix M[(i,k), j] into one blob
+ * of faop_tables_bytes() bytes in HOST memory; the caller copies the blob to the device.            */
+int faop_tables_bytes(const faop_cfg* cfg, size_t* bytes);
+int faop_tables_build(const faop_cfg* cfg, const double* y_l, const double* w_l, /* leggauss(l) */
+                      const double* y_m, const double* w_m,                     /* leggauss(m) */
+                      void* host_out);
+
+/* Device scratch needed by faop_alo_price_batch for N options (QD seeds when B0_out is NULL). */
+int faop_workspace_bytes(const faop_cfg* cfg, int64_t N, size_t* bytes);
+
+/* ---- the hot path -----------------------------------------------------------------------------
+ * Replaces FastAmericanOptionSolver.solve(t, s0) (FastAmericanOptionSolverBase.py:49-76) for a
+ * batch: collocation grid (:221-223), QD seed (:258-265 -> QDplusAmericanOptionSolver.py:69-76),
+ * the damped Jacobi fixed-point / diagonal-Newton loop (:105-165) over the Solver A or B integral
+ * forms (FastAmericanOptionSolverA.py:5-83, FastAmericanOptionSolverB.py:5-75) and the price
+ * integral (:92-103).  q == 0 calls take the European shortcut (:50-53): iters = 0, err = 1e6,
+ * boundary rows NaN.
+ *   t        nullable (t = 0)
+ *   B0_in    nullable: N x (n+1) borrowed seed boundary (stage-wise parity); skips the seed kernel
+ *   B, B0_out nullable: N x (n+1) row-major, node i at tau_i = T (1+cos(i pi/n))^2/4, last node tau=0
+ *   iters, err nullable: realised iteration count and final ||B_old-B_new||_2 per option           */
+int faop_alo_price_batch(const faop_cfg* cfg, int64_t N,
+                         const double* r, const double* q, const double* sigma, const double* K,
+                         const double* T, const double* t, const double* S, const uint8_t* is_put,
+                         const void* tables_dev, const double* B0_in,
+                         double* price, double* european, double* B, double* B0_out,
+                         int32_t* iters, double* err, void* workspace, void* cuda_stream);
+
+/* Config-5 sweep: option i of [first, first+count) is decoded on the device from the flat index
+ * i = (iK*nT + iT)*nV + iV into K = linspace(K0,K1,nK)[iK], T = linspace(T0,T1,nT)[iT],
+ * sigma = linspace(V0,V1,nV)[iV] (numpy.linspace arithmetic), all puts or all calls with common
+ * S, r, q, t = 0.  Only prices (and optionally iters) are written back.  `workspace` (device, any size
+ * >= 256*(8+n+1)*8 bytes; ~0.5 GB is plenty) bounds the chunk the sweep is processed in.               */
+typedef struct faop_surface {
+    double K0, K1, T0, T1, V0, V1, S, r, q;
+    int32_t nK, nT, nV, is_put;
+} faop_surface;
+int faop_alo_surface_batch(const faop_cfg* cfg, const faop_surface* surf, int64_t first, int64_t count,
+                           const void* tables_dev, double* price, int32_t* iters /* nullable */,
+                           void* workspace, size_t workspace_bytes, void* cuda_stream);
+
+/* N, D, N', D', f, f' at the n active nodes of a GIVEN boundary (one Jacobi sweep's internals):
+ * FastAmericanOptionSolver.compute_f_and_fprime / N_func / D_func / Nprime_func / Dprime_func
+ * (FastAmericanOptionSolverBase.py:267-279 and the A/B files).  Outputs are N x n, nullable.
+ * f' is the analytic derivative when cfg->use_derivative, else 1 (as the reference returns).      */
+int faop_alo_eval_nodes_batch(const faop_cfg* cfg, int64_t N,
+                              const double* r, const double* q, const double* sigma, const double* K,
+                              const double* T, const uint8_t* is_put, const void* tables_dev,
+                              const double* B /* N x (n+1) */,
+                              double* Nv, double* Dv, double* Np, double* Dp, double* f, double* fp,
+                              void* cuda_stream);
+
+/* Price integral on a GIVEN boundary: american_value_with_known_boundary
+ * (FastAmericanOptionSolverBase.py:92-103, 211-219); tau = T - t may differ from T.              */
+int faop_alo_price_known_boundary_batch(const faop_cfg* cfg, int64_t N,
+                              const double* r, const double* q, const double* sigma, const double* K,
+                              const double* T, const double* t, const double* S, const uint8_t* is_put,
+                              const void* tables_dev, const double* B /* N x (n+1) */,
+                              double* price, double* european, void* cuda_stream);
+
+/* ---- leaf kernels -----------------------------------------------------------------------------*/
+/* QDplus.compute_exercise_boundary(tau) (QDplusAmericanOptionSolver.py:69-76; residual :110-125):
+ * safeguarded Newton from x0 = K instead of MINPACK hybr; tau == 0 -> B_at_zero (:78-88).         */
+int faop_qd_boundary_batch(int64_t N, const double* r, const double* q, const double* sigma,
+                           const double* K, const double* tau, const uint8_t* is_put,
+                           double* B, void* cuda_stream);
+/* QDplus.exercise_boundary_func(S, tau) residual itself (QDplusAmericanOptionSolver.py:110-125). */
+int faop_qd_residual_batch(int64_t N, const double* r, const double* q, const double* sigma,
+                           const double* K, const double* tau, const double* S, const uint8_t* is_put,
+                           double* F, void* cuda_stream);
+/* QDplus.price(tau, S) (QDplusAmericanOptionSolver.py:44-67), quirks included; boundary nullable. */
+int faop_qd_price_batch(int64_t N, const double* r, const double* q, const double* sigma,
+                        const double* K, const double* tau, const double* S, const uint8_t* is_put,
+                        double* price, double* boundary, void* cuda_stream);
+/* EuropeanOption.european_put_value / european_call_value (EuropeanOptionSolver.py:7-22). */
+int faop_european_batch(int64_t N, const double* tau, const double* S, const double* r, const double* q,
+                        const double* sigma, const double* K, const uint8_t* is_put,
+                        double* price, void* cuda_stream);
+/* EuropeanOption.european_option_theta / d1 / d2 (EuropeanOptionSolver.py:25-40); outputs nullable. */
+int faop_european_greeks_batch(int64_t N, const double* tau, const double* S, const double* r,
+                               const double* q, const double* sigma, const double* K,
+                               double* theta, double* d1, double* d2, void* cuda_stream);
+/* ChebyshevInterpolation.__init__/std_coeff (ChebyshevInterpolation.py:4-12, 43-51): y is N x (n+1). */
+int faop_cheb_fit_batch(int64_t N, int32_t n, const double* y, double* a, void* cuda_stream);
+/* ChebyshevInterpolation.value/std_cheby_single_value (:19-41): z is N x npts, already in [-1,1]. */
+int faop_cheb_eval_batch(int64_t N, int32_t n, int32_t npts, const double* a, const double* z,
+                         double* out, void* cuda_stream);
+
+/* ---- Crank-Nicolson (CNOptionSolver, CrankNicolsonOptionSolver.py:5-107), American puts --------
+ * One CTA per option; grid S_i = linspace(0, 3K, n_space); the dt schedule of solvePDE's float
+ * countdown (:36-45) is built by the caller: dts is N x max_steps, n_steps[i] entries valid.
+ *   mode 0: unprojected direct solve  == the reference default USE_PSOR=False (np.linalg.solve, :81-82)
+ *   mode 1: the reference's SOR-sweep-then-project loop (:84-107), operation for operation
+ *   mode 2: projected (Brennan-Schwartz) tridiagonal sweep — the throughput mode (not in the reference)
+ * X_out nullable: N x n_space final grid values (the reference's self.X).                          */
+int faop_cn_workspace_bytes(int64_t N, int32_t n_space, int32_t mode, size_t* bytes);
+int faop_cn_put_batch(int64_t N, int32_t n_space, int32_t mode,
+                      const double* r, const double* q, const double* sigma, const double* K,
+                      const double* S0, const double* dts, const int32_t* n_steps, int32_t max_steps,
+                      double omega, double tol, int32_t max_iter,
+                      double* price, double* X_out, void* workspace, void* cuda_stream);
+
+/* ---- host-buffer convenience (what a non-torch caller binds) ----------------------------------
+ * A context owns a device, a stream, device scratch, pinned staging buffers and the table blobs it
+ * has built; it grows on demand and is freed by faop_ctx_destroy.  One context per host thread.    */
+typedef struct faop_ctx faop_ctx;
+int faop_ctx_create(int device, faop_ctx** out);
+int faop_ctx_destroy(faop_ctx* ctx);
+/* Same semantics as faop_alo_price_batch with HOST arrays (y/w tables as in faop_tables_build);
+ * H2D, kernels and D2H run inside the call, which returns after the results are in host memory.  */
+int faop_alo_price_batch_host(faop_ctx* ctx, const faop_cfg* cfg, int64_t N,
+                              const double* r, const double* q, const double* sigma, const double* K,
+                              const double* T, const double* t, const double* S, const uint8_t* is_put,
+                              const double* y_l, const double* w_l, const double* y_m, const double* w_m,
+                              const double* B0_in, double* price, double* european, double* B,
+                              double* B0_out, int32_t* iters, double* err);
+
+/* Diagnostics */
+int faop_version(void);
+/* Kernels launched by this library in this process since load (for bench.py's gpu_launches). */
+int64_t faop_launch_count(void);
+/* FP64 FMA-pipe peak microbenchmark (the roofline denominator; MEASURED_PEAKS.json has no FP64
+ * figure): launches `launches` saturating DFMA kernels, returns measured TFLOP/s (2 flops/DFMA). */
+int faop_measure_fp64_peak(int launches, double* tflops, double* ms_per_launch, void* cuda_stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FAOP_H */
