@@ -1,0 +1,33 @@
+"""Drop-in for the reference's FastAmericanOptionSolverA.py (`from FastAmericanOptionSolverA import *` re-exports
+qd, np, plt, europ, intrp like the reference's star-import chain).  N/D use the pdf-heavy K12/K3 form
+(reference FastAmericanOptionSolverA.py:5-44, derivative terms :46-83), evaluated by the solver-0 CUDA kernels."""
+try:
+    from .FastAmericanOptionSolverBase import *  # noqa: F401,F403
+    from .FastAmericanOptionSolverBase import FastAmericanOptionSolver
+except ImportError:
+    from FastAmericanOptionSolverBase import *  # noqa: F401,F403
+    from FastAmericanOptionSolverBase import FastAmericanOptionSolver
+
+
+class FastAmericanOptionSolverA(FastAmericanOptionSolver):
+    _SOLVER = "A"
+
+    def K12(self, tau, B):
+        """reference :24-25 — recovered from D = phi(d+)/(sigma sqrt tau) +- Phi(+-d+) + q K12"""
+        return self.quadrature_sum(self.K12_integrand, tau, B, self.quadrature_num)
+
+    def K3(self, tau, B):
+        """reference :34-35"""
+        return self.quadrature_sum(self.K3_integrand, tau, B, self.quadrature_num)
+
+    def K12_integrand(self, tau, B_tau, u, B_u):
+        """reference :27-32 (host scalar helper)"""
+        if self._is_put():
+            return np.exp(self.q * u) * self.CDF_pos_dplus(tau - u, B_tau / B_u) \
+                + np.exp(self.q * u) / (self.sigma * np.sqrt(tau - u)) * self.PDF_dplus(tau - u, B_tau / B_u)
+        return -np.exp(self.q * u) * self.CDF_neg_dplus(tau - u, B_tau / B_u) \
+            + np.exp(self.q * u) / (self.sigma * np.sqrt(tau - u)) * self.PDF_neg_dplus(tau - u, B_tau / B_u)
+
+    def K3_integrand(self, tau, B_tau, u, B_u):
+        """reference :37-44 (host scalar helper)"""
+        return np.exp(self.r * u) / (self.sigma * np.sqrt(tau - u)) * self.PDF_dminus(tau - u, B_tau / B_u)

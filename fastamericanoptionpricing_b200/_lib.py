@@ -29,9 +29,10 @@ _SIGNATURES = {
     "faop_tables_bytes": (ctypes.c_int, [_P(FaopCfg), _P(c_sz)]),
     "faop_tables_build": (ctypes.c_int, [_P(FaopCfg), c_vp, c_vp, c_vp, c_vp, c_vp]),
     "faop_workspace_bytes": (ctypes.c_int, [_P(FaopCfg), c_i64, _P(c_sz)]),
-    "faop_alo_price_batch": (ctypes.c_int, [_P(FaopCfg), c_i64] + [c_vp] * 18),
+    "faop_alo_price_batch": (ctypes.c_int, [_P(FaopCfg), c_i64] + [c_vp] * 19),
     "faop_alo_surface_batch": (ctypes.c_int, [_P(FaopCfg), _P(FaopSurface), c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
-    "faop_alo_eval_nodes_batch": (ctypes.c_int, [_P(FaopCfg), c_i64] + [c_vp] * 15),
+    "faop_alo_eval_points_batch": (ctypes.c_int, [_P(FaopCfg), c_i64, c_i32] + [c_vp] * 18),
+    "faop_alo_interp_boundary_batch": (ctypes.c_int, [_P(FaopCfg), c_i64, c_i32] + [c_vp] * 10),
     "faop_alo_price_known_boundary_batch": (ctypes.c_int, [_P(FaopCfg), c_i64] + [c_vp] * 13),
     "faop_qd_boundary_batch": (ctypes.c_int, [c_i64] + [c_vp] * 8),
     "faop_qd_residual_batch": (ctypes.c_int, [c_i64] + [c_vp] * 9),
@@ -45,6 +46,7 @@ _SIGNATURES = {
     "faop_ctx_create": (ctypes.c_int, [ctypes.c_int, _P(c_vp)]),
     "faop_ctx_destroy": (ctypes.c_int, [c_vp]),
     "faop_alo_price_batch_host": (ctypes.c_int, [c_vp, _P(FaopCfg), c_i64] + [c_vp] * 19),
+    "faop_dev_math_batch": (ctypes.c_int, [c_i32, c_i64, c_vp, c_vp, c_vp]),
     "faop_measure_fp64_peak": (ctypes.c_int, [ctypes.c_int, _P(c_dbl), _P(c_dbl), c_vp]),
 }
 

@@ -96,11 +96,12 @@ def tables_for(cfg: AloConfig, dev):
 
 
 def price_batch(r, q, sigma, K, T, S, is_put, t=None, cfg: AloConfig = AloConfig(), B0=None,
-                want_boundary=True, device=None):
+                want_boundary=True, want_iter_errs=False, device=None):
     """FastAmericanOptionSolver{A,B}.solve(t, s0) for a batch (FastAmericanOptionSolverBase.py:49-76).
 
     Returns dict(price, european, iters, err[, B, B0, tau]); B/B0/tau are N x (n+1) (node i at
     tau_i = T (1 + cos(i pi/n))^2 / 4).  B0 (optional, N x (n+1)) borrows a seed boundary instead of the QD seed.
+    want_iter_errs adds iter_errs (N x max_iters, the errors of the reference's iter_records, NaN padded).
     """
     lib = _lib.load()
     dev = _device(device)
@@ -135,11 +136,14 @@ def price_batch(r, q, sigma, K, T, S, is_put, t=None, cfg: AloConfig = AloConfig
             check(lib.faop_workspace_bytes(ctypes.byref(c), N, ctypes.byref(nb)), "faop_workspace_bytes")
             ws = torch.empty(nb.value, dtype=torch.uint8, device=dev)
         c = cfg.c()
+        ierr = torch.empty((N, cfg.max_iters), dtype=torch.float64, device=dev) if want_iter_errs else None
         check(lib.faop_alo_price_batch(ctypes.byref(c), N, _ptr(r), _ptr(q), _ptr(sigma), _ptr(K), _ptr(T), _ptr(tt),
                                        _ptr(S), _ptr(is_put), _ptr(tab), _ptr(B0_in), _ptr(price), _ptr(eur), _ptr(B),
-                                       _ptr(B0_out), _ptr(iters), _ptr(err), _ptr(ws), _stream(dev)),
+                                       _ptr(B0_out), _ptr(iters), _ptr(err), _ptr(ierr), _ptr(ws), _stream(dev)),
               "faop_alo_price_batch")
         out = dict(price=price, european=eur, iters=iters, err=err)
+        if want_iter_errs:
+            out["iter_errs"] = ierr
         if want_boundary:
             out["B"] = B
             out["B0"] = B0_in if B0_in is not None else B0_out
@@ -153,9 +157,10 @@ def collocation_tau(T, n):
     return (c + 1).square()[None, :] * T[:, None] / 4
 
 
-def eval_nodes_batch(B, r, q, sigma, K, T, is_put, cfg: AloConfig = AloConfig(), device=None):
-    """N_func, D_func, Nprime_func, Dprime_func, compute_f_and_fprime on a given boundary (N x (n+1)).
-    Returns dict(N, D, Nprime, Dprime, f, fprime), each N x n (active nodes)."""
+def eval_points_batch(B, tau_pts, B_pts, r, q, sigma, K, T, is_put, cfg: AloConfig = AloConfig(), device=None):
+    """N_func, D_func, Nprime_func, Dprime_func, compute_f_and_fprime and the damped update at arbitrary
+    (tau, Q) points (N x p) on a given boundary B (N x (n+1)); FastAmericanOptionSolverBase.py:144-165, 267-279.
+    Returns dict(N, D, Nprime, Dprime, f, fprime, Bnew), each N x p."""
     lib = _lib.load()
     dev = _device(device)
     with torch.cuda.device(dev):
@@ -164,13 +169,48 @@ def eval_nodes_batch(B, r, q, sigma, K, T, is_put, cfg: AloConfig = AloConfig(),
         q, sigma, K, T = (_f64(x, dev, N) for x in (q, sigma, K, T))
         is_put = _u8(is_put, dev, N)
         Bd = torch.as_tensor(B, dtype=torch.float64).to(dev).reshape(N, cfg.n + 1).contiguous()
-        outs = [torch.empty((N, cfg.n), dtype=torch.float64, device=dev) for _ in range(6)]
+        tp = torch.as_tensor(tau_pts, dtype=torch.float64).to(dev).reshape(N, -1).contiguous()
+        bp = torch.as_tensor(B_pts, dtype=torch.float64).to(dev).reshape(N, -1).contiguous()
+        if tp.shape != bp.shape:
+            raise ValueError("tau_pts and B_pts must have the same shape")
+        p = tp.shape[1]
+        outs = [torch.empty((N, p), dtype=torch.float64, device=dev) for _ in range(7)]
         tab = tables_for(cfg, dev)
         c = cfg.c()
-        check(lib.faop_alo_eval_nodes_batch(ctypes.byref(c), N, _ptr(r), _ptr(q), _ptr(sigma), _ptr(K), _ptr(T),
-                                            _ptr(is_put), _ptr(tab), _ptr(Bd), *[_ptr(o) for o in outs], _stream(dev)),
-              "faop_alo_eval_nodes_batch")
-        return dict(zip(("N", "D", "Nprime", "Dprime", "f", "fprime"), outs))
+        check(lib.faop_alo_eval_points_batch(ctypes.byref(c), N, p, _ptr(r), _ptr(q), _ptr(sigma), _ptr(K), _ptr(T),
+                                             _ptr(is_put), _ptr(tab), _ptr(Bd), _ptr(tp), _ptr(bp),
+                                             *[_ptr(o) for o in outs], _stream(dev)), "faop_alo_eval_points_batch")
+        return dict(zip(("N", "D", "Nprime", "Dprime", "f", "fprime", "Bnew"), outs))
+
+
+def eval_nodes_batch(B, r, q, sigma, K, T, is_put, cfg: AloConfig = AloConfig(), device=None):
+    """eval_points_batch at the n active collocation nodes (tau_i, B_i) of the boundary itself."""
+    dev = _device(device)
+    Bd = torch.as_tensor(B, dtype=torch.float64).to(dev).reshape(-1, cfg.n + 1)
+    Td = _f64(T, dev, Bd.shape[0])
+    tau = collocation_tau(Td, cfg.n)
+    return eval_points_batch(Bd, tau[:, :cfg.n], Bd[:, :cfg.n], r, q, sigma, K, Td, is_put, cfg=cfg, device=device)
+
+
+def interp_boundary_batch(B, u, r, q, K, T, is_put, cfg: AloConfig = AloConfig(), device=None):
+    """B(u) at arbitrary u (N x p) from the Chebyshev interpolant of ln(B/X)^2 on [0, T]
+    (compute_integration_terms, FastAmericanOptionSolverBase.py:167-195)."""
+    lib = _lib.load()
+    dev = _device(device)
+    with torch.cuda.device(dev):
+        r = _f64(r, dev)
+        N = r.numel()
+        q, K, T = (_f64(x, dev, N) for x in (q, K, T))
+        is_put = _u8(is_put, dev, N)
+        Bd = torch.as_tensor(B, dtype=torch.float64).to(dev).reshape(N, cfg.n + 1).contiguous()
+        ud = torch.as_tensor(u, dtype=torch.float64).to(dev).reshape(N, -1).contiguous()
+        out = torch.empty_like(ud)
+        tab = tables_for(cfg, dev)
+        c = cfg.c()
+        check(lib.faop_alo_interp_boundary_batch(ctypes.byref(c), N, ud.shape[1], _ptr(r), _ptr(q), _ptr(K), _ptr(T),
+                                                 _ptr(is_put), _ptr(tab), _ptr(Bd), _ptr(ud), _ptr(out), _stream(dev)),
+              "faop_alo_interp_boundary_batch")
+        return out
 
 
 def price_known_boundary_batch(B, r, q, sigma, K, T, S, is_put, t=None, cfg: AloConfig = AloConfig(), device=None):
@@ -367,6 +407,17 @@ def cn_put_batch(r, q, sigma, K, T, S0, n_space=200, max_dt=1 / 12.0, mode=CN_MO
 # ------------------------------------------------------------------------------------------ misc
 def launch_count():
     return int(_lib.load().faop_launch_count())
+
+
+def dev_math_batch(kind, x, device=None):
+    """Unit-test hook: the device math of csrc/faop_fastmath.cuh applied elementwise (see faop_dev_math_batch)."""
+    lib = _lib.load()
+    dev = _device(device)
+    with torch.cuda.device(dev):
+        x = _f64(x, dev)
+        out = torch.empty_like(x)
+        check(lib.faop_dev_math_batch(int(kind), x.numel(), _ptr(x), _ptr(out), _stream(dev)), "faop_dev_math_batch")
+        return out
 
 
 def measure_fp64_peak(launches=20, device=None):

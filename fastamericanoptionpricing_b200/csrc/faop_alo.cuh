@@ -12,6 +12,7 @@
 //   quadrature weight W_ik = w_k tau_i h_k, and W_ik/(sigma sqrt(tau_i-u)) = w_k sqrt(tau_i)/sigma
 #pragma once
 #include "faop_common.cuh"
+#include "faop_kernels.h"
 
 namespace faop {
 
@@ -157,6 +158,112 @@ FAOP_D double price_point(const Opt& o, const NodeC& c, double lnz, double h, do
     double a = o.r * o.K * er * norm_cdf(-o.om * dm);
     double b = o.q * o.S * eq * norm_cdf(-o.om * dp);
     return o.om * (a - b);
+}
+
+// ---------------------------------------------------------------- per-warp shared-memory view (generic kernels)
+struct WarpSmem {
+    double *B, *L, *H, *A, *tau, *cinv, *disc, *s1, *s2, *s3, *s4;
+    static __host__ __device__ int doubles(int nn) { return 11 * nn; }
+    __device__ WarpSmem(double* base, int nn) {
+        B = base; L = B + nn; H = L + nn; A = H + nn; tau = A + nn; cinv = tau + nn; disc = cinv + nn;
+        s1 = disc + nn; s2 = s1 + nn; s3 = s2 + nn; s4 = s3 + nn;
+    }
+};
+
+struct CtaTables {
+    const double *wl, *hl, *rhl, *sgl, *wm, *hm, *rhm, *sgm, *c, *cs;
+    __device__ CtaTables(const double* s, const TableLayout& t) {
+        wl = s + t.off_wl; hl = s + t.off_hl; rhl = s + t.off_rhl; sgl = s + t.off_sgl;
+        wm = s + t.off_wm; hm = s + t.off_hm; rhm = s + t.off_rhm; sgm = s + t.off_sgm;
+        c = s + t.off_c; cs = s + t.off_cos;
+    }
+};
+
+FAOP_D void stage_tables(double* s_tab, const double* g_tab, int count) {
+    for (int i = threadIdx.x; i < count; i += blockDim.x) s_tab[i] = g_tab[i];
+    __syncthreads();
+}
+
+FAOP_D Opt load_option(const AloArgs& a, int64_t opt) {
+    Opt o;
+    o.r = a.r[opt]; o.q = a.q[opt]; o.sg = a.sigma[opt]; o.K = a.K[opt]; o.T = a.T[opt];
+    o.t = a.t ? a.t[opt] : 0.0;
+    o.S = a.S ? a.S[opt] : 0.0;
+    o.put = a.is_put[opt] != 0;
+    o.X = b_at_zero(o.r, o.q, o.K, o.put);
+    o.om = o.put ? 1.0 : -1.0;
+    return o;
+}
+
+// L_j = ln(B_j/X), H_j = L_j^2 (FastAmericanOptionSolverBase.py:184) and the DCT-I fit
+// a_k = (2/n) sum'' H_j cos(j k pi/n) (ChebyshevInterpolation.py:43-51), lanes over j / k.
+FAOP_D void fit_boundary(const WarpSmem& w, const CtaTables& tb, int n, double X, int lane) {
+    for (int j = lane; j <= n; j += 32) {
+        double L = log(w.B[j] / X);
+        w.L[j] = L;
+        w.H[j] = L * L;
+    }
+    __syncwarp();
+    const int n2 = 2 * n;
+    for (int k = lane; k <= n; k += 32) {
+        double ans = 0.0;
+        int idx = 0;  // (j*k) mod 2n
+        for (int j = 0; j <= n; ++j) {
+            double term = w.H[j] * tb.cs[idx];
+            if (j == 0 || j == n) term *= 0.5;
+            ans += term;
+            idx += k;
+            if (idx >= n2) idx -= n2;
+        }
+        w.A[k] = ans * (2.0 / n);
+    }
+    __syncwarp();
+}
+
+FAOP_D NodeC node_from_smem(const WarpSmem& w, const Opt& o, int j) {
+    NodeC c;
+    c.tau = w.tau[j];
+    c.cinv = w.cinv[j];
+    c.ssu = o.sg * sqrt(c.tau);
+    c.apc = ((o.r - o.q) + 0.5 * o.sg * o.sg) * (c.ssu / (o.sg * o.sg));
+    c.qtau = o.q * c.tau;
+    c.rtau = o.r * c.tau;
+    return c;
+}
+
+FAOP_D void setup_nodes(const WarpSmem& w, const CtaTables& tb, int n, const Opt& o, int lane) {
+    for (int j = lane; j <= n; j += 32) {
+        double c = tb.c[j];
+        double tau = (c + 1) * (c + 1) * o.T / 4;
+        w.tau[j] = tau;
+        w.cinv[j] = 1.0 / (o.sg * sqrt(tau));
+        w.disc[j] = o.K * exp(-tau * (o.r - o.q));
+    }
+}
+
+// Price integral on the boundary currently in w.B: american_value_with_known_boundary
+// (FastAmericanOptionSolverBase.py:92-103).  Returns price; *eur gets the European value.
+FAOP_D double price_integral(const WarpSmem& w, const CtaTables& tb, const TableLayout& tl, const Opt& o, int lane,
+                             double* eur) {
+    double tau = o.T - o.t;
+    double e = euro_value(tau, o.S, o.r, o.q, o.sg, o.K, o.put);
+    *eur = e;
+    if (tau == 0) return e + 0.0;  // quadrature_sum returns 0 at tau == 0 (:382-383)
+    fit_boundary(w, tb, tl.n, o.X, lane);
+    NodeC c = node_consts(o, tau);
+    double LS = log(o.S / o.X);
+    double zf = sqrt(4 * tau / o.T);  // z = sqrt(4 u/T) - 1 with u = tau g_k
+    double acc = 0;
+    for (int k = lane; k < tl.MP; k += 32) {
+        double h = tb.hm[k];
+        double z = fma(zf, tb.sgm[k], -1.0);
+        double Hu = clenshaw(tl.n, w.A, z);
+        double root = sqrt(Hu < 0.0 ? 0.0 : Hu);  // np.maximum(0, H): NaN propagates (fmax would drop it)
+        double lnz = fma(o.om, root, LS);
+        acc = fma(tb.wm[k] * h, price_point(o, c, lnz, h, tb.rhm[k]), acc);
+    }
+    acc = warp_sum(acc);
+    return e + acc * tau;
 }
 
 }  // namespace faop

@@ -1,5 +1,250 @@
-// placeholder, replaced by the specialised kernels
+// faop_alo_fast.cu — specialised boundary + price kernel for the flagship configuration
+// (FastAmericanOptionSolverA, no derivative, n = 12 collocation nodes, l <= 32 quadrature points):
+// BASELINE.json configs[1] (C2), configs[4] (C5) and the reference's own testA case (C1).
+//
+// One option per warp, lane = quadrature index k.  What makes it fast (all FP64-pipe instruction savings):
+//   * H(u_ik) comes from the option-independent interpolation matrix M[i][j][k] staged once per CTA in shared
+//     memory (13 DFMA per point instead of a Clenshaw recurrence); the iterate H_j lives in registers;
+//   * e^{q u_ik} (iteration invariant) is computed once per option into shared memory;
+//   * per point: 2 fast_exp + 1 mills_half + 1 fast_sqrt, ~95 FP64 instructions (faop_fastmath.cuh);
+//   * the 24 per-node sums of one sweep are reduced by a transposing butterfly (10 shuffles per 4 nodes
+//     instead of 40) and closed by lanes 0..11 in one pass.
+// 16 warps per CTA, one CTA per SM, grid = min(#SM, ceil(N/16)) persistent CTAs striding over the batch.
+#include "faop_alo.cuh"
+#include "faop_fastmath.cuh"
 #include "faop_kernels.h"
+
 namespace faop {
-int launch_alo_fast(const AloArgs& a, cudaStream_t st) { (void)a; (void)st; return -1000; }
+
+constexpr int NC = 12;        // collocation n
+constexpr int NN = NC + 1;    // nodes
+constexpr int kGroup = 4;     // nodes per transposing reduction
+
+struct FastWarpSmem {
+    double eq[NC * 32];   // e^{q u_ik}, [i][k]
+    double B[16], L[16], H[16], A[16];
+    double tau[16], cinv[16], apc[16], ssu[16], disc[16];
+    double sN[16], sD[16];
+    double par[8];   // X, 1/X, ln(X/K)
+};
+
+struct FastSmem {
+    // followed in dynamic shared memory by: small tables (tl.small doubles), M (NC*NN*32 doubles), FastWarpSmem[kFastWarps]
+};
+
+// Reduce 8 per-lane values over the 32 lanes with a transposing butterfly.  On return every lane of the 4-lane group
+// g = lane >> 2 holds the total of value index g in v[0].
+FAOP_D double transpose_reduce8(double (&v)[8], int lane) {
+    {   // xor 16: keep 4
+        const bool up = lane & 16;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            double send = up ? v[j] : v[j + 4];
+            double keep = up ? v[j + 4] : v[j];
+            v[j] = keep + __shfl_xor_sync(kFull, send, 16);
+        }
+    }
+    {   // xor 8: keep 2
+        const bool up = lane & 8;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            double send = up ? v[j] : v[j + 2];
+            double keep = up ? v[j + 2] : v[j];
+            v[j] = keep + __shfl_xor_sync(kFull, send, 8);
+        }
+    }
+    {   // xor 4: keep 1
+        const bool up = lane & 4;
+        double send = up ? v[0] : v[1];
+        double keep = up ? v[1] : v[0];
+        v[0] = keep + __shfl_xor_sync(kFull, send, 4);
+    }
+    v[0] += __shfl_xor_sync(kFull, v[0], 2);
+    v[0] += __shfl_xor_sync(kFull, v[0], 1);
+    return v[0];
 }
+
+template <int kFastWarps>
+__global__ void __launch_bounds__(kFastWarps * 32, 1) alo_fast_A12_kernel(AloArgs a) {
+    extern __shared__ double smem[];
+    const TableLayout tl = a.tl;
+    double* s_tab = smem;
+    double* s_M = smem + tl.small;
+    FastWarpSmem* s_w = reinterpret_cast<FastWarpSmem*>(s_M + NC * NN * 32);
+    for (int i = threadIdx.x; i < tl.small + NC * NN * 32; i += blockDim.x) smem[i] = a.tables[i];
+    __syncthreads();
+    const CtaTables tb(s_tab, tl);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    FastWarpSmem& ws = s_w[warp];
+
+    // lane constants of the l-point rule
+    const double h = tb.hl[lane], rh = tb.rhl[lane], sgk = tb.sgl[lane], wk = tb.wl[lane];
+    const double g = sgk * sgk;            // 1 - h^2
+    const double wh = wk * h;
+
+    // generic-kernel view of the same per-warp arrays, for the price integral
+    WarpSmem gw(ws.B, 16);
+    gw.B = ws.B; gw.L = ws.L; gw.H = ws.H; gw.A = ws.A;
+
+    const int64_t stride = (int64_t)gridDim.x * kFastWarps;
+    for (int64_t opt = (int64_t)blockIdx.x * kFastWarps + warp; opt < a.N; opt += stride) {
+        double om, oq, orr;     // the only option scalars the sweep needs in registers
+        bool degenerate;
+        {
+            const Opt o = load_option(a, opt);
+            if (o.q == 0 && !o.put) {  // European shortcut, FastAmericanOptionSolverBase.py:50-53
+                double e = euro_value(o.T - o.t, o.S, o.r, o.q, o.sg, o.K, false);
+                if (lane == 0) {
+                    a.price[opt] = e;
+                    if (a.european) a.european[opt] = e;
+                    if (a.iters) a.iters[opt] = 0;
+                    if (a.err) a.err[opt] = 1e6;
+                }
+                if (a.B && lane < NN) a.B[opt * NN + lane] = nan("");
+                continue;
+            }
+            // ---- per-option setup: node constants (lanes 0..12) and the invariant e^{q u_ik} table
+            if (lane < NN) {
+                double c = tb.c[lane];
+                double tau = (c + 1) * (c + 1) * o.T / 4;      // to_orig_point, FastAmericanOptionSolverBase.py:239-240
+                double sqt = sqrt(tau);
+                ws.tau[lane] = tau;
+                ws.ssu[lane] = o.sg * sqt;
+                ws.cinv[lane] = 1.0 / (o.sg * sqt);
+                ws.apc[lane] = ((o.r - o.q) + 0.5 * o.sg * o.sg) * sqt / o.sg;
+                ws.disc[lane] = o.K * exp(-tau * (o.r - o.q));
+                ws.B[lane] = a.seeds_in[opt * NN + lane];
+            }
+            if (lane == 0) {
+                ws.par[0] = o.X;
+                ws.par[1] = 1.0 / o.X;
+                ws.par[2] = log(o.X / o.K);
+            }
+            om = o.om; oq = o.q; orr = o.r;
+            degenerate = !(o.T > 0);     // T == 0: every node has tau == 0 and is pinned to X
+        }
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < NC; ++i) ws.eq[i * 32 + lane] = fast_exp(oq * ws.tau[i] * g);
+
+        int count = 0;
+        double err = 1.0;
+        while (err > a.cfg.iter_tol && count < a.cfg.max_iters) {
+            ++count;
+            // ---- L_j = ln(B_j/X), H_j = L_j^2 (FastAmericanOptionSolverBase.py:184), broadcast through shared memory
+            if (lane < NN) {
+                double L = log(ws.B[lane] * ws.par[1]);
+                ws.L[lane] = L;
+                ws.H[lane] = L * L;
+            }
+            __syncwarp();
+            double Hj[NN];
+#pragma unroll
+            for (int j = 0; j < NN; ++j) Hj[j] = ws.H[j];
+
+            // ---- quadrature of K12 / K3 at the 12 active nodes, 4 nodes per transposing reduction
+            if (!degenerate) {
+#pragma unroll
+                for (int grp = 0; grp < NC / kGroup; ++grp) {
+                    double acc[8];
+#pragma unroll
+                    for (int ii = 0; ii < kGroup; ++ii) {
+                        const int i = grp * kGroup + ii;
+                        const double* Mi = s_M + (i * NN) * 32 + lane;
+                        // H(u_ik) = sum_j M[i][j][k] H_j, two partial chains for ILP
+                        double s0 = Mi[0] * Hj[0], s1 = Mi[32] * Hj[1];
+#pragma unroll
+                        for (int j = 2; j < NN - 1; j += 2) {
+                            s0 = fma(Mi[j * 32], Hj[j], s0);
+                            s1 = fma(Mi[(j + 1) * 32], Hj[j + 1], s1);
+                        }
+                        s0 = fma(Mi[(NN - 1) * 32], Hj[NN - 1], s0);
+                        const double Hu = s0 + s1;
+                        const double root = (Hu <= 1e-290) ? 0.0 : fast_sqrt_pos(Hu);   // sqrt(max(0, H)); NaN propagates
+                        const double lnz = fma(om, root, ws.L[i]);
+                        const double cinv = ws.cinv[i];
+                        const double inv = cinv * rh;
+                        const double dp = fma(lnz, inv, ws.apc[i] * h);
+                        const double dm = fma(-ws.ssu[i], h, dp);
+                        const double taug = ws.tau[i] * g;                          // u_ik
+                        const double Eq = fast_exp(fma(-0.5 * dp, dp, oq * taug));  // e^{qu} phi(d+) sqrt(2 pi)
+                        const double Er = fast_exp(fma(-0.5 * dm, dm, orr * taug));  // e^{ru} phi(d-) sqrt(2 pi)
+                        // put: +e^{qu} Phi(d+); call: -e^{qu} Phi(-d+)   (FastAmericanOptionSolverA.py:27-32)
+                        const double cdf = om * fast_scaled_cdf(om * dp, Eq, ws.eq[i * 32 + lane]);
+                        double d = wh * cdf;
+                        d = fma(cinv * kInvSqrt2Pi * wk, Eq, d);
+                        acc[2 * ii] = wk * Er;       // -> K3  = tau cinv/sqrt(2 pi) * sum
+                        acc[2 * ii + 1] = d;         // -> K12 = tau * sum
+                    }
+                    const double tot = transpose_reduce8(acc, lane);
+                    // lanes 8 ii .. 8 ii + 3 hold the K3 sum of node grp*4+ii, lanes 8 ii + 4 .. 8 ii + 7 its K12 sum
+                    if ((lane & 3) == 0) {
+                        const int node = grp * kGroup + (lane >> 3);
+                        if (lane & 4) ws.sD[node] = tot; else ws.sN[node] = tot;
+                    }
+                }
+            }
+            __syncwarp();
+            // ---- close N, D, f and the damped update at the nodes (lanes 0..12)
+            double dd = 0.0;
+            if (lane < NN) {
+                const double Bj = ws.B[lane];
+                double Bn;
+                const double tau = ws.tau[lane];
+                if (tau == 0) {
+                    Bn = ws.par[0];                // iterate_once_foreach_tau: tau_i == 0 -> B_at_zero
+                } else {
+                    const double cinv = ws.cinv[lane];
+                    const double LK = ws.L[lane] + ws.par[2];
+                    const double dpK = fma(LK, cinv, ws.apc[lane]);
+                    const double dmK = dpK - ws.ssu[lane];
+                    const double Ep = fast_exp(-0.5 * dpK * dpK), Em = fast_exp(-0.5 * dmK * dmK);
+                    const double K3 = tau * cinv * kInvSqrt2Pi * ws.sN[lane];
+                    const double K12 = tau * ws.sD[lane];
+                    const double Nv = Em * kInvSqrt2Pi * cinv + orr * K3;                                  // A.py:5-10
+                    const double Dv = Ep * kInvSqrt2Pi * cinv + om * fast_scaled_cdf(om * dpK, Ep, 1.0) + oq * K12;  // A.py:13-19
+                    const double f = ws.disc[lane] * Nv / Dv;                                               // Base.py:273
+                    Bn = Bj + a.cfg.eta * (Bj - f) / (0.0 - 1.0);                                           // Base.py:164
+                }
+                dd = fabs(Bj - Bn);
+                ws.B[lane] = Bn;
+            }
+            err = sqrt(warp_sum(dd * dd));         // norm1_error is the 2-norm over all n+1 nodes (:230-233)
+            __syncwarp();
+        }
+        if (a.B && lane < NN) a.B[opt * NN + lane] = ws.B[lane];
+        double eur;
+        const Opt o = load_option(a, opt);
+        const double v = price_integral(gw, tb, tl, o, lane, &eur);
+        if (lane == 0) {
+            a.price[opt] = v;
+            if (a.european) a.european[opt] = eur;
+            if (a.iters) a.iters[opt] = count;
+            if (a.err) a.err[opt] = err;
+        }
+        __syncwarp();
+    }
+}
+
+template <int kFastWarps>
+static int launch_fast_t(const AloArgs& a, cudaStream_t st) {
+    const size_t sm = sizeof(double) * (size_t)(a.tl.small + NC * NN * 32) + sizeof(FastWarpSmem) * kFastWarps;
+    FAOP_CUDA_OK(cudaFuncSetAttribute(alo_fast_A12_kernel<kFastWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    int64_t ctas = (a.N + kFastWarps - 1) / kFastWarps;
+    int grid = (int)(ctas < kSMs ? ctas : kSMs);
+    alo_fast_A12_kernel<kFastWarps><<<grid, kFastWarps * 32, sm, st>>>(a);
+    count_launch();
+    return launch_status();
+}
+
+// cfg.kernel: 0 = default (16 warps/CTA, 128 registers/thread), 2 = 12 warps/CTA with up to 168 registers/thread
+int launch_alo_fast(const AloArgs& a, cudaStream_t st) {
+    const bool match = a.cfg.solver == 0 && !a.cfg.use_derivative && a.tl.n == NC && a.tl.LP == 32 && a.tl.has_matrix &&
+                       a.iter_errs == nullptr;
+    if (!match) return -1000;
+    if (a.N == 0) return 0;
+    if (a.cfg.kernel == 2) return launch_fast_t<12>(a, st);
+    return launch_fast_t<16>(a, st);
+}
+
+}  // namespace faop

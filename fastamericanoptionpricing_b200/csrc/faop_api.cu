@@ -119,14 +119,15 @@ static int fill_args(AloArgs& a, const faop_cfg* cfg, int64_t N, const double* r
 int faop_alo_price_batch(const faop_cfg* cfg, int64_t N, const double* r, const double* q, const double* sigma,
                          const double* K, const double* T, const double* t, const double* S, const uint8_t* is_put,
                          const void* tables_dev, const double* B0_in, double* price, double* european, double* B,
-                         double* B0_out, int32_t* iters, double* err, void* workspace, void* cuda_stream) {
+                         double* B0_out, int32_t* iters, double* err, double* iter_errs, void* workspace,
+                         void* cuda_stream) {
     AloArgs a;
     int rc = fill_args(a, cfg, N, r, q, sigma, K, T, t, S, is_put, tables_dev);
     if (rc) return rc;
     if (N == 0) return 0;
     if (!S || !price) return FAOP_EINVAL;
     cudaStream_t st = (cudaStream_t)cuda_stream;
-    a.price = price; a.european = european; a.B = B; a.iters = iters; a.err = err;
+    a.price = price; a.european = european; a.B = B; a.iters = iters; a.err = err; a.iter_errs = iter_errs;
     const size_t seed_bytes = sizeof(double) * (size_t)N * (size_t)(cfg->n_colloc + 1);
     if (B0_in) {
         a.seeds_in = B0_in;
@@ -138,7 +139,7 @@ int faop_alo_price_batch(const faop_cfg* cfg, int64_t N, const double* r, const 
         if (rc) return rc;
         a.seeds_in = a.seeds_out;
     }
-    if (cfg->kernel == 0) {
+    if (cfg->kernel != 1 && !iter_errs) {  // the per-iteration error history is a generic-kernel feature
         rc = launch_alo_fast(a, st);
         if (rc != -1000) return rc;
     }
@@ -169,24 +170,41 @@ int faop_alo_surface_batch(const faop_cfg* cfg, const faop_surface* surf, int64_
         rc = launch_surface_decode(*surf, first + off, cnt, d_r, d_q, d_s, d_K, d_T, d_S, d_put, st);
         if (rc) return rc;
         rc = faop_alo_price_batch(cfg, cnt, d_r, d_q, d_s, d_K, d_T, nullptr, d_S, d_put, tables_dev, nullptr, price + off,
-                                  nullptr, nullptr, nullptr, iters ? iters + off : nullptr, nullptr, d_seed, st);
+                                  nullptr, nullptr, nullptr, iters ? iters + off : nullptr, nullptr, nullptr, d_seed, st);
         if (rc) return rc;
     }
     return 0;
 }
 
-int faop_alo_eval_nodes_batch(const faop_cfg* cfg, int64_t N, const double* r, const double* q, const double* sigma,
-                              const double* K, const double* T, const uint8_t* is_put, const void* tables_dev,
-                              const double* B, double* Nv, double* Dv, double* Np, double* Dp, double* f, double* fp,
-                              void* cuda_stream) {
+int faop_alo_eval_points_batch(const faop_cfg* cfg, int64_t N, int32_t npts, const double* r, const double* q,
+                               const double* sigma, const double* K, const double* T, const uint8_t* is_put,
+                               const void* tables_dev, const double* B, const double* pts_tau, const double* pts_B,
+                               double* Nv, double* Dv, double* Np, double* Dp, double* f, double* fp, double* Bnew,
+                               void* cuda_stream) {
     AloArgs a;
     int rc = fill_args(a, cfg, N, r, q, sigma, K, T, nullptr, nullptr, is_put, tables_dev);
     if (rc) return rc;
-    if (N == 0) return 0;
-    if (!B) return FAOP_EINVAL;
+    if (npts < 0) return FAOP_EINVAL;
+    if (N == 0 || npts == 0) return 0;
+    if (!B || !pts_tau || !pts_B) return FAOP_EINVAL;
     a.seeds_in = B;
-    EvalOut eo = {Nv, Dv, Np, Dp, f, fp};
+    a.npts = npts; a.pts_tau = pts_tau; a.pts_B = pts_B;
+    EvalOut eo = {Nv, Dv, Np, Dp, f, fp, Bnew};
     return launch_alo_eval_nodes(a, eo, (cudaStream_t)cuda_stream);
+}
+
+int faop_alo_interp_boundary_batch(const faop_cfg* cfg, int64_t N, int32_t npts, const double* r, const double* q,
+                                   const double* K, const double* T, const uint8_t* is_put, const void* tables_dev,
+                                   const double* B, const double* u, double* Bu, void* cuda_stream) {
+    AloArgs a;
+    int rc = fill_args(a, cfg, N, r, q, r /* sigma unused */, K, T, nullptr, nullptr, is_put, tables_dev);
+    if (rc) return rc;
+    if (npts < 0) return FAOP_EINVAL;
+    if (N == 0 || npts == 0) return 0;
+    if (!B || !u || !Bu) return FAOP_EINVAL;
+    a.seeds_in = B;
+    a.npts = npts; a.pts_tau = u;
+    return launch_alo_interp(a, Bu, (cudaStream_t)cuda_stream);
 }
 
 int faop_alo_price_known_boundary_batch(const faop_cfg* cfg, int64_t N, const double* r, const double* q,
@@ -239,6 +257,11 @@ int faop_cheb_eval_batch(int64_t N, int32_t n, int32_t npts, const double* a, co
                          void* cuda_stream) {
     if (N < 0 || n < 1 || npts < 0 || (N > 0 && npts > 0 && (!a || !z || !out))) return FAOP_EINVAL;
     return launch_cheb_eval(N, n, npts, a, z, out, (cudaStream_t)cuda_stream);
+}
+
+int faop_dev_math_batch(int32_t kind, int64_t N, const double* x, double* out, void* cuda_stream) {
+    if (N < 0 || (N > 0 && (!x || !out))) return FAOP_EINVAL;
+    return launch_dev_math(kind, N, x, out, (cudaStream_t)cuda_stream);
 }
 
 int faop_measure_fp64_peak(int launches, double* tflops, double* ms_per_launch, void* cuda_stream) {
@@ -352,7 +375,7 @@ int faop_alo_price_batch_host(faop_ctx* c, const faop_cfg* cfg, int64_t N, const
     if (B0_in) FAOP_CUDA_OK(cudaMemcpyAsync(d_B0, B0_in, (size_t)N * nn * sizeof(double), cudaMemcpyHostToDevice, st));
     rc = faop_alo_price_batch(cfg, N, d_r, d_q, d_s, d_K, d_T, t ? d_t : nullptr, d_S, d_put, c->tables_dev,
                               B0_in ? d_B0 : nullptr, d_price, european ? d_eur : nullptr, B ? d_B : nullptr,
-                              B0_in ? nullptr : d_B0, iters ? d_it : nullptr, err ? d_err : nullptr, nullptr, st);
+                              B0_in ? nullptr : d_B0, iters ? d_it : nullptr, err ? d_err : nullptr, nullptr, nullptr, st);
     if (rc) return rc;
     FAOP_CUDA_OK(cudaMemcpyAsync(price, d_price, vb, cudaMemcpyDeviceToHost, st));
     if (european) FAOP_CUDA_OK(cudaMemcpyAsync(european, d_eur, vb, cudaMemcpyDeviceToHost, st));

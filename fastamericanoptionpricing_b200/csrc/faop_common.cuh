@@ -130,18 +130,21 @@ FAOP_HD void qd_resid(const QdConst& c, double S, double K, bool is_put, double*
     }
 }
 // QDplus.compute_exercise_boundary, QDplusAmericanOptionSolver.py:69-76: root from x0 = K.
-// Safeguarded Newton (positivity, at most doubling per step) instead of MINPACK hybr.
+// Safeguarded Newton (positivity, at most doubling per step) instead of MINPACK hybr (xtol 1.49e-8).
 FAOP_HD double qd_boundary(double tau, double r, double q, double sg, double K, bool is_put) {
     if (tau == 0) return b_at_zero(r, q, K, is_put);
     QdConst c = qd_const(tau, r, q, sg, is_put);
-    double S = K;
+    double S = K, prev = 1.79e308;
     for (int it = 0; it < 100; ++it) {
         double F, dF;
         qd_resid(c, S, K, is_put, &F, &dF);
         double Sn = S - F / dF;
         if (!(Sn > 0) || !(Sn < 1.79e308)) Sn = 0.5 * S;
         if (Sn > 2.0 * S) Sn = 2.0 * S;
-        bool done = fabs(Sn - S) <= 1e-15 * fabs(Sn);
+        double d = fabs(Sn - S);
+        // converged (the next Newton step would be ~d^2), or stalled at the rounding floor of a flat residual
+        bool done = d <= 1e-10 * fabs(Sn) || (d >= 0.5 * prev && prev <= 1e-7 * fabs(Sn));
+        prev = d;
         S = Sn;
         if (done) break;
     }

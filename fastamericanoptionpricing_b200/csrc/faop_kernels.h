@@ -16,16 +16,21 @@ struct AloArgs {
     double *price, *european, *B;
     int32_t* iters;
     double* err;
+    double* iter_errs;       // nullable: N x max_iters, per-iteration ||B_old - B_new||_2 (NaN padded)
+    // eval / interpolation kernels: npts points per option at arbitrary (tau, B) / u
+    int npts;
+    const double *pts_tau, *pts_B;
 };
 
 struct EvalOut {
-    double *Nv, *Dv, *Np, *Dp, *f, *fp;
+    double *Nv, *Dv, *Np, *Dp, *f, *fp, *Bnew;
 };
 
 int launch_qd_seed(const AloArgs& a, cudaStream_t st);
 int launch_alo_generic(const AloArgs& a, cudaStream_t st);
 int launch_alo_eval_nodes(const AloArgs& a, const EvalOut& eo, cudaStream_t st);
 int launch_alo_price_known(const AloArgs& a, cudaStream_t st);
+int launch_alo_interp(const AloArgs& a, double* Bu, cudaStream_t st);
 // specialised kernels (faop_alo_fast.cu); returns -1000 when no specialisation matches the config
 int launch_alo_fast(const AloArgs& a, cudaStream_t st);
 
@@ -45,6 +50,7 @@ int launch_cheb_eval(int64_t N, int n, int npts, const double* a, const double* 
 
 int launch_surface_decode(const faop_surface& s, int64_t first, int64_t count, double* r, double* q, double* sigma,
                           double* K, double* T, double* S, uint8_t* is_put, cudaStream_t st);
+int launch_dev_math(int kind, int64_t N, const double* x, double* out, cudaStream_t st);
 int launch_fp64_peak(int launches, double* tflops, double* ms_per_launch, cudaStream_t st);
 
 }  // namespace faop

@@ -2,6 +2,7 @@
 // Clenshaw evaluation, and the FP64 FMA-pipe peak microbenchmark used as the roofline denominator.
 // One thread per element, coalesced structure-of-arrays loads, grid sized to the batch.
 #include "faop_kernels.h"
+#include "faop_fastmath.cuh"
 
 namespace faop {
 
@@ -154,6 +155,28 @@ int launch_surface_decode(const faop_surface& s, int64_t first, int64_t count, d
     double stepT = s.nT > 1 ? (s.T1 - s.T0) / (s.nT - 1) : 0.0;
     double stepV = s.nV > 1 ? (s.V1 - s.V0) / (s.nV - 1) : 0.0;
     surface_decode_kernel<<<blocks_for(count, 256), 256, 0, st>>>(s, stepK, stepT, stepV, first, count, r, q, sigma, K, T, S, is_put);
+    count_launch();
+    return launch_status();
+}
+
+// Unit-test hook for the device math of faop_fastmath.cuh: out[i] = f_kind(x[i]).
+__global__ void __launch_bounds__(256) dev_math_kernel(int kind, int64_t N, const double* x, double* out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    double v = x[i], r;
+    switch (kind) {
+        case 0: r = fast_exp(v); break;
+        case 1: r = mills_half(v); break;
+        case 2: r = fast_sqrt_pos(v); break;
+        case 3: r = fast_rcp(v); break;
+        case 4: r = fast_scaled_cdf(v, fast_exp(-0.5 * v * v), 1.0); break;   // Phi(v)
+        default: r = nan("");
+    }
+    out[i] = r;
+}
+int launch_dev_math(int kind, int64_t N, const double* x, double* out, cudaStream_t st) {
+    if (N == 0) return 0;
+    dev_math_kernel<<<blocks_for(N, 256), 256, 0, st>>>(kind, N, x, out);
     count_launch();
     return launch_status();
 }

@@ -1,0 +1,46 @@
+"""Multi-GPU: options are independent, so the batch is cut into contiguous slices, one per rank, with no collective
+on the data path; an optional all_gather of the 8 B/option prices closes the job."""
+import torch
+
+
+def shard_bounds(N, world_size, rank):
+    """Contiguous slice [lo, hi) of rank `rank`: sizes differ by at most one, lower ranks take the remainder."""
+    base, rem = divmod(int(N), int(world_size))
+    lo = rank * base + min(rank, rem)
+    hi = lo + base + (1 if rank < rem else 0)
+    return lo, hi
+
+
+def price_batch_sharded(r, q, sigma, K, T, S, is_put, t=None, cfg=None, gather=True, group=None):
+    """Every rank holds (or can index) the full input arrays; it prices its own slice on its own GPU and, if
+    `gather`, all ranks receive the full price vector (one all_gather of padded slices over NCCL/NVLink, or gloo
+    when the tensors live on the CPU in tests).  Returns (prices, (lo, hi))."""
+    import torch.distributed as dist
+    from . import batch
+    cfg = cfg or batch.AloConfig()
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    N = len(r)
+    lo, hi = shard_bounds(N, world, rank)
+    sl = slice(lo, hi)
+    out = batch.price_batch(r[sl], q[sl], sigma[sl], K[sl], T[sl], S[sl], is_put[sl], t=None if t is None else t[sl],
+                            cfg=cfg, want_boundary=False)
+    local = out["price"]
+    if not gather or world == 1:
+        return local, (lo, hi)
+    return gather_slices(local, N, world, group), (lo, hi)
+
+
+def gather_slices(local, N, world, group=None):
+    """all_gather of per-rank slices of unequal length (padded to the longest) back into one length-N vector."""
+    import torch.distributed as dist
+    longest = -(-N // world)
+    pad = torch.zeros(longest, dtype=local.dtype, device=local.device)
+    pad[:local.numel()] = local
+    parts = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(parts, pad, group=group)
+    full = torch.empty(N, dtype=local.dtype, device=local.device)
+    for rk in range(world):
+        lo, hi = shard_bounds(N, world, rk)
+        full[lo:hi] = parts[rk][:hi - lo]
+    return full

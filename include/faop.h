@@ -82,13 +82,14 @@ int faop_workspace_bytes(const faop_cfg* cfg, int64_t N, size_t* bytes);
  *   t        nullable (t = 0)
  *   B0_in    nullable: N x (n+1) borrowed seed boundary (stage-wise parity); skips the seed kernel
  *   B, B0_out nullable: N x (n+1) row-major, node i at tau_i = T (1+cos(i pi/n))^2/4, last node tau=0
- *   iters, err nullable: realised iteration count and final ||B_old-B_new||_2 per option           */
+ *   iters, err nullable: realised iteration count and final ||B_old-B_new||_2 per option
+ *   iter_errs nullable: N x max_iters, the per-iteration errors of self.iter_records (:130), NaN padded       */
 int faop_alo_price_batch(const faop_cfg* cfg, int64_t N,
                          const double* r, const double* q, const double* sigma, const double* K,
                          const double* T, const double* t, const double* S, const uint8_t* is_put,
                          const void* tables_dev, const double* B0_in,
                          double* price, double* european, double* B, double* B0_out,
-                         int32_t* iters, double* err, void* workspace, void* cuda_stream);
+                         int32_t* iters, double* err, double* iter_errs, void* workspace, void* cuda_stream);
 
 /* Config-5 sweep: option i of [first, first+count) is decoded on the device from the flat index
  * i = (iK*nT + iT)*nV + iV into K = linspace(K0,K1,nK)[iK], T = linspace(T0,T1,nT)[iT],
@@ -103,16 +104,25 @@ int faop_alo_surface_batch(const faop_cfg* cfg, const faop_surface* surf, int64_
                            const void* tables_dev, double* price, int32_t* iters /* nullable */,
                            void* workspace, size_t workspace_bytes, void* cuda_stream);
 
-/* N, D, N', D', f, f' at the n active nodes of a GIVEN boundary (one Jacobi sweep's internals):
- * FastAmericanOptionSolver.compute_f_and_fprime / N_func / D_func / Nprime_func / Dprime_func
- * (FastAmericanOptionSolverBase.py:267-279 and the A/B files).  Outputs are N x n, nullable.
- * f' is the analytic derivative when cfg->use_derivative, else 1 (as the reference returns).      */
-int faop_alo_eval_nodes_batch(const faop_cfg* cfg, int64_t N,
-                              const double* r, const double* q, const double* sigma, const double* K,
-                              const double* T, const uint8_t* is_put, const void* tables_dev,
-                              const double* B /* N x (n+1) */,
-                              double* Nv, double* Dv, double* Np, double* Dp, double* f, double* fp,
-                              void* cuda_stream);
+/* N, D, N', D', f, f' (and the damped update B_new) at `npts` arbitrary (tau, Q) points per option on a GIVEN
+ * boundary B (N x (n+1)) — one Jacobi sweep's internals:
+ * FastAmericanOptionSolver.compute_f_and_fprime / N_func / D_func / Nprime_func / Dprime_func /
+ * iterate_once_foreach_tau (FastAmericanOptionSolverBase.py:144-165, 267-279 and the A/B files).
+ * pts_tau, pts_B and all outputs are N x npts (outputs nullable).  f' is the analytic derivative when
+ * cfg->use_derivative, else 1 (as the reference returns); tau == 0 gives f = B_at_zero, f' = 1.       */
+int faop_alo_eval_points_batch(const faop_cfg* cfg, int64_t N, int32_t npts,
+                               const double* r, const double* q, const double* sigma, const double* K,
+                               const double* T, const uint8_t* is_put, const void* tables_dev,
+                               const double* B, const double* pts_tau, const double* pts_B,
+                               double* Nv, double* Dv, double* Np, double* Dp, double* f, double* fp,
+                               double* Bnew, void* cuda_stream);
+
+/* B(u) at `npts` arbitrary u per option from the Chebyshev interpolant of ln(B/X)^2:
+ * compute_integration_terms (FastAmericanOptionSolverBase.py:167-195).  u, Bu are N x npts.         */
+int faop_alo_interp_boundary_batch(const faop_cfg* cfg, int64_t N, int32_t npts,
+                                   const double* r, const double* q, const double* K, const double* T,
+                                   const uint8_t* is_put, const void* tables_dev,
+                                   const double* B, const double* u, double* Bu, void* cuda_stream);
 
 /* Price integral on a GIVEN boundary: american_value_with_known_boundary
  * (FastAmericanOptionSolverBase.py:92-103, 211-219); tau = T - t may differ from T.              */
@@ -183,6 +193,9 @@ int faop_alo_price_batch_host(faop_ctx* ctx, const faop_cfg* cfg, int64_t N,
 int faop_version(void);
 /* Kernels launched by this library in this process since load (for bench.py's gpu_launches). */
 int64_t faop_launch_count(void);
+/* Unit-test hook for the device math the specialised kernel is built from (csrc/faop_fastmath.cuh):
+ * kind 0 = fast_exp, 1 = mills_half (Phi(-y)/exp(-y^2/2)), 2 = fast_sqrt_pos, 3 = fast_rcp, 4 = Phi via fast path. */
+int faop_dev_math_batch(int32_t kind, int64_t N, const double* x, double* out, void* cuda_stream);
 /* FP64 FMA-pipe peak microbenchmark (the roofline denominator; MEASURED_PEAKS.json has no FP64
  * figure): launches `launches` saturating DFMA kernels, returns measured TFLOP/s (2 flops/DFMA). */
 int faop_measure_fp64_peak(int launches, double* tflops, double* ms_per_launch, void* cuda_stream);

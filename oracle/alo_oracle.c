@@ -67,14 +67,17 @@ static void qd_resid(double S, double tau, double r, double q, double sg, double
 /* QDplusAmericanOptionSolver.py:69-76, Newton from x0 = K (see header for the hybr deviation) */
 static double qd_boundary(double tau, double r, double q, double sg, double K, int is_put) {
     if (tau == 0) return b_at_zero(r, q, K, is_put);
-    double S = K;
+    double S = K, prev = 1.79e308;
     for (int it = 0; it < 100; ++it) {
         double F, dF;
         qd_resid(S, tau, r, q, sg, K, is_put, &F, &dF);
         double Sn = S - F / dF;
         if (!isfinite(Sn) || Sn <= 0) Sn = 0.5 * S;
         if (Sn > 2.0 * S) Sn = 2.0 * S;
-        int done = fabs(Sn - S) <= 1e-15 * fabs(Sn);
+        double d = fabs(Sn - S);
+        /* converged (the next Newton step would be ~d^2), or stalled at the rounding floor of a flat residual */
+        int done = d <= 1e-10 * fabs(Sn) || (d >= 0.5 * prev && prev <= 1e-7 * fabs(Sn));
+        prev = d;
         S = Sn;
         if (done) break;
     }

@@ -165,13 +165,15 @@ def qd_boundary(tau, r, q, sigma, K, is_put, max_newton=100):
     """QDplusAmericanOptionSolver.py:69-76: root of the QD residual started from x0 = K; tau == 0 -> B_at_zero.
 
     The reference calls scipy.optimize.root (MINPACK hybr); this restatement uses Newton with the
-    analytic derivative, a positivity safeguard (halve towards 0 / step-limit) and a relative stop of 1e-15.
+    analytic derivative, a positivity safeguard (halve towards 0 / step-limit), a relative stop of 1e-10 (quadratic
+    convergence makes the accepted iterate exact to rounding) and a stall test for flat residuals.
     All arguments broadcast; returns an array.
     """
     tau, r, q, sigma, K = np.broadcast_arrays(*[np.asarray(a, dtype=float) for a in (tau, r, q, sigma, K)])
     is_put = np.broadcast_to(np.asarray(is_put, dtype=bool), tau.shape)
     S = K.astype(float).copy()
     act = tau > 0
+    prev = np.full(S.shape, np.inf)
     with np.errstate(all="ignore"):
         for _ in range(max_newton):
             if not act.any():
@@ -183,7 +185,10 @@ def qd_boundary(tau, r, q, sigma, K, is_put, max_newton=100):
             Snew = np.where(bad, 0.5 * S, Snew)
             # limit growth to a factor of 2 per step (keeps the flat small-tau cases on the near root)
             Snew = np.minimum(Snew, 2.0 * S)
-            done = np.abs(Snew - S) <= 1e-15 * np.abs(Snew)
+            d = np.abs(Snew - S)
+            # converged (the next Newton step would be ~d^2), or stalled at the rounding floor of a flat residual
+            done = (d <= 1e-10 * np.abs(Snew)) | ((d >= 0.5 * prev) & (prev <= 1e-7 * np.abs(Snew)))
+            prev = np.where(act, d, prev)
             S = np.where(act, Snew, S)
             act = act & ~done
     return np.where(tau == 0, B_at_zero(r, q, K, is_put), S)

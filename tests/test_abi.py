@@ -1,0 +1,86 @@
+"""CPU: the C-ABI library loads, exports every symbol include/faop.h declares, and its host-only helpers work.
+No kernel is launched here."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import REPO
+from fastamericanoptionpricing_b200 import _lib, batch
+
+
+def _header_symbols():
+    src = open(os.path.join(REPO, "include", "faop.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(faop_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib.load()
+    names = _header_symbols()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(lib, n), "libfaop.so does not export %s" % n
+    assert sorted(names) == _lib.declared_symbols()       # the ctypes table covers the whole header
+    assert lib.faop_version() == 100
+
+
+def test_cfg_struct_layout_matches_header():
+    assert ctypes.sizeof(_lib.FaopCfg) == 6 * 4 + 2 * 8 + 2 * 4
+    assert ctypes.sizeof(_lib.FaopSurface) == 9 * 8 + 4 * 4
+
+
+def test_tables_build_host_only():
+    lib = _lib.load()
+    cfg = batch.AloConfig(n=12, l=32, m=64)
+    c = cfg.c()
+    nb = ctypes.c_size_t()
+    assert lib.faop_tables_bytes(ctypes.byref(c), ctypes.byref(nb)) == 0
+    host = np.empty(nb.value // 8)
+    yl, wl = batch.gauss_legendre(32)
+    ym, wm = batch.gauss_legendre(64)
+    assert lib.faop_tables_build(ctypes.byref(c), yl.ctypes.data, wl.ctypes.data, ym.ctypes.data, wm.ctypes.data,
+                                 host.ctypes.data) == 0
+    LP, MP, n = 32, 64, 12
+    w, h, rh, sg = host[0:LP], host[LP:2 * LP], host[2 * LP:3 * LP], host[3 * LP:4 * LP]
+    assert np.array_equal(w, wl) and np.allclose(h, (1 + yl) / 2, rtol=0, atol=0)
+    assert np.allclose(rh * h, 1.0, rtol=1e-15) and np.allclose(sg, np.sqrt(1 - h * h), rtol=1e-13)
+    off_c = 4 * LP + 4 * MP
+    c_nodes = host[off_c:off_c + n + 1]
+    assert np.array_equal(c_nodes, np.cos(np.arange(n + 1) * np.pi / n))     # ChebyshevInterpolation.py:15-17
+    # interpolation matrix rows sum to 1 (interpolant of a constant) and reproduce node values at z = node
+    off_M = (off_c + (n + 1) + 2 * n + 1) & ~1
+    M = host[off_M:off_M + n * (n + 1) * LP].reshape(n, n + 1, LP)
+    assert np.max(np.abs(M.sum(axis=1) - 1.0)) < 1e-13
+    from oracle import alo_oracle as o                                    # checker only
+    z = (1 + c_nodes[:n, None]) * sg[None, :] - 1
+    Hj = np.random.default_rng(1).normal(size=n + 1)
+    ref = o.cheb_eval(o.cheb_fit(Hj), z.reshape(-1)).reshape(n, LP)
+    assert np.max(np.abs(np.einsum("ijk,j->ik", M, Hj) - ref)) < 1e-13
+    # bad configurations are refused with FAOP_E codes, not crashes
+    bad = batch.AloConfig(n=1).c()
+    assert lib.faop_tables_bytes(ctypes.byref(bad), ctypes.byref(nb)) == -2
+    bad = batch.AloConfig(l=129).c()
+    assert lib.faop_tables_bytes(ctypes.byref(bad), ctypes.byref(nb)) == -2
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(_lib.FaopError):
+        batch.price_batch([0.04], [0.01], [0.2], [100.0], [3.0], [80.0], [1])
+    with pytest.raises(_lib.FaopError):
+        batch.european_batch([1.0], [80.0], [0.04], [0.01], [0.2], [100.0], [1])
+
+
+def test_product_never_imports_oracle():
+    """The oracle is test infrastructure: nothing under the package may import or load it."""
+    pkg = os.path.join(REPO, "fastamericanoptionpricing_b200")
+    for root, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                txt = open(os.path.join(root, f)).read()
+                assert not re.search(r"(import\s+oracle|from\s+oracle|from\s+\.+oracle|liboracle|oracle/|oracle\.)", txt), (root, f)

@@ -1,0 +1,285 @@
+"""GPU: the CUDA path (through the C ABI, via fastamericanoptionpricing_b200.batch) against the golden outputs of the
+unmodified reference and against the oracle.  Bars (BASELINE.json north_star): |price - ref| <= 1e-9 absolute,
+boundary nodes <= 1e-10 relative, on the parity set (reference result finite with error < 1e-2)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import BOUNDARY_REL_TOL, PRICE_ABS_TOL, load_golden, parity_set
+from fastamericanoptionpricing_b200 import batch, workloads as wl
+from fastamericanoptionpricing_b200.batch import AloConfig
+
+pytestmark = pytest.mark.gpu
+
+KERNELS = [0, 1, 2]  # 0 = auto (specialised where available), 1 = generic, 2 = specialised, 12 warps/CTA
+
+
+def _np(d):
+    return {k: v.cpu().numpy() for k, v in d.items()}
+
+
+def _inputs(g, ix=slice(None)):
+    return [g["in_" + k][ix] for k in ("r", "q", "sigma", "K", "T", "S", "is_put")]
+
+
+def _check(out, g, ix=slice(None), strict_iters=True, tag=""):
+    ps = parity_set({k: g[k][ix] for k in ("price", "err")})
+    nn = out["B"].shape[1]
+    dprice = np.abs(out["price"] - g["price"][ix])[ps]
+    relB = np.abs(out["B"] / g["B"][ix][:, :nn] - 1)[ps]
+    assert dprice.max() <= PRICE_ABS_TOL, (tag, dprice.max())
+    assert np.nanmax(relB) <= BOUNDARY_REL_TOL, (tag, np.nanmax(relB))
+    if strict_iters:
+        assert np.array_equal(out["iters"][ps], g["iters"][ix][ps]), tag
+    return ps
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_c1_testA(kernel):
+    g = load_golden("ref_c1_testA.npz")
+    cfg = AloConfig("A", 12, 24, 48, 1e-5, 20, kernel=kernel)
+    out = _np(batch.price_batch(*_inputs(g), cfg=cfg))
+    _check(out, g, tag="c1")
+    assert abs(out["price"][0] - 21.135486471314067) <= PRICE_ABS_TOL     # reference testA.py output
+    assert abs(out["european"][0] - 17.78865238332743) <= 1e-12
+    assert out["iters"][0] == 19 and abs(out["err"][0] - 6.763708524497298e-06) < 1e-12
+    assert np.max(np.abs(out["tau"] - g["tau"])) <= 1e-15
+    assert np.max(np.abs(out["B0"] / g["B0"] - 1)) <= 1e-9
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_c2_golden(kernel):
+    g = load_golden("ref_c2_A.npz")
+    cfg = AloConfig(kernel=kernel, **wl.C2_CFG)
+    out = _np(batch.price_batch(*_inputs(g), cfg=cfg))
+    ps = _check(out, g, tag="c2")
+    assert ps.sum() >= 1000
+    assert np.nanmax(np.abs(out["B0"] / g["B0"] - 1)[ps]) <= 1e-8        # Newton vs MINPACK hybr (xtol 1.49e-8)
+    assert np.max(np.abs(out["european"] - g["european"])) <= 1e-11
+    assert np.max(np.abs(out["err"] / g["err"] - 1)[ps]) <= 1e-6
+    # borrowed reference seeds isolate the iteration itself
+    out2 = _np(batch.price_batch(*_inputs(g), cfg=cfg, B0=g["B0"]))
+    ps = _check(out2, g, tag="c2 borrowed")
+    assert np.nanmax(np.abs(out2["B"] / g["B"] - 1)[ps]) <= 1e-12
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_c3_golden(kernel):
+    g = load_golden("ref_c3_B.npz")
+    cfg = AloConfig(kernel=kernel, **wl.C3_CFG)
+    out = _np(batch.price_batch(*_inputs(g), cfg=cfg, B0=g["B0"]))
+    ps = _check(out, g, tag="c3 borrowed")
+    assert ps.all()
+    out = _np(batch.price_batch(*_inputs(g), cfg=cfg))
+    seed_ok = np.nanmax(np.abs(out["B0"] / g["B0"] - 1), axis=1) <= 1e-6     # hybr misses one extreme call's root
+    assert seed_ok.sum() >= 95
+    _check({k: v[seed_ok] for k, v in out.items()}, {k: g[k][seed_ok] for k in ("price", "err", "B", "iters")}, tag="c3")
+    assert np.max(np.abs(out["price"] - g["price"])) <= PRICE_ABS_TOL
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_misc_variants(kernel):
+    m = load_golden("ref_misc.npz")
+    keys = sorted(set(zip(m["solver"], m["n"], m["l"], m["m"], m["iter_tol"], m["max_iters"], m["use_derivative"])))
+    for k in keys:
+        sel = np.ones(len(m["price"]), dtype=bool)
+        for nm, v in zip(("solver", "n", "l", "m", "iter_tol", "max_iters", "use_derivative"), k):
+            sel &= m[nm] == v
+        ix = np.nonzero(sel)[0]
+        cfg = AloConfig(str(k[0]), int(k[1]), int(k[2]), int(k[3]), float(k[4]), int(k[5]), bool(k[6]), kernel=kernel)
+        out = _np(batch.price_batch(*_inputs(m, ix), t=m["in_t"][ix], cfg=cfg))
+        if str(k[0]) == "B" and bool(k[6]):      # reference diverges to NaN: NaN-for-NaN, loosely
+            assert (np.isnan(out["price"]) == np.isnan(m["price"][ix])).mean() >= 0.9
+            continue
+        _check(out, m, ix, tag="misc %s" % (k,))
+        short = (m["in_q"][ix] == 0) & ~m["in_is_put"][ix]
+        assert out["iters"][short][0] == 0 and out["err"][short][0] == 1e6 and np.isnan(out["B"][short]).all()
+        assert abs(out["price"][short][0] - m["price"][ix][short][0]) <= 1e-12
+        assert np.array_equal(np.isnan(out["price"]), np.isnan(m["price"][ix]))
+
+
+def test_stage_values():
+    s = load_golden("ref_stage.npz")
+    for solver in ("A", "B"):
+        sel = s["solver"] == solver
+        cfg = AloConfig(solver, 12, 24, 48, use_derivative=True)
+        a = [s["in_" + k][sel] for k in ("r", "q", "sigma", "K", "T", "is_put")]
+        ev = _np(batch.eval_nodes_batch(s["B"][sel], *a, cfg=cfg))
+        n = 12
+        for mine, ref in (("N", "N"), ("D", "D"), ("f", "f")):
+            assert np.max(np.abs(ev[mine] / s[ref][sel][:, :n] - 1)) <= 1e-10, (solver, mine)
+        # N', D': the reference forms tau - u by cancellation (relative error up to ~6e-11 at the outermost
+        # quadrature node) and divides by it, so its own derivative sums carry ~1e-9 noise at the smallest tau;
+        # the boundary computed WITH these derivatives still meets 1e-10 (test_misc_variants, use_derivative=True)
+        for mine, ref in (("Nprime", "Np"), ("Dprime", "Dp")):
+            assert np.max(np.abs(ev[mine] / s[ref][sel][:, :n] - 1)) <= 2e-8, (solver, mine)
+        scale = np.max(np.abs(s["fp"][sel][:, :n]), axis=1, keepdims=True)
+        assert np.max(np.abs(ev["fprime"] - s["fp"][sel][:, :n]) / scale) <= 2e-8
+        k = 0
+        K, T = s["in_K"][sel], s["in_T"][sel]
+        for S0 in (0.8 * K, K, 1.2 * K):
+            for tt in (T, 0.5 * T):
+                v, _ = batch.price_known_boundary_batch(s["B"][sel], a[0], a[1], a[2], a[3], a[4], S0, a[5], t=T - tt, cfg=cfg)
+                assert np.max(np.abs(v.cpu().numpy() - s["v"][sel][:, k])) <= PRICE_ABS_TOL
+                k += 1
+
+
+def test_qd_leaf():
+    q = load_golden("ref_qd.npz")
+    B = batch.qd_boundary_batch(q["in_tau"], q["in_r"], q["in_q"], q["in_sigma"], q["in_K"], q["in_is_put"]).cpu().numpy()
+    rel = np.abs(B / q["B"] - 1)
+    assert rel.max() <= 1e-8 and np.median(rel) <= 1e-13
+    from oracle import c_oracle as co
+    Bo = co.qd_boundary_batch(q["in_tau"], q["in_r"], q["in_q"], q["in_sigma"], q["in_K"], q["in_is_put"])
+    # same Newton rule on both sides; flat residuals (tiny tau, r >> q calls) pin the root only to ~1e-10
+    assert np.max(np.abs(B / Bo - 1)) <= 1e-9 and np.median(np.abs(B / Bo - 1)) <= 1e-14
+    Bc = batch.qd_boundary_batch(q["curve_tau"], float(q["curve_r"]), float(q["curve_q"]), float(q["curve_sigma"]),
+                                 float(q["curve_K"]), True).cpu().numpy()
+    assert np.max(np.abs(Bc / q["curve_B"] - 1)) <= 1e-11
+    F = batch.qd_residual_batch(q["resid_S"], float(q["resid_tau"]), float(q["curve_r"]), float(q["curve_q"]),
+                                float(q["curve_sigma"]), float(q["curve_K"]), True).cpu().numpy()
+    assert np.max(np.abs(F - q["resid_put"])) <= 1e-10
+    rc, qc, sc, Kc = q["resid_call_params"]
+    F = batch.qd_residual_batch(q["resid_S"], float(q["resid_tau"]), rc, qc, sc, Kc, False).cpu().numpy()
+    assert np.max(np.abs(F - q["resid_call"])) <= 1e-10
+    n = len(q["price"])
+    P, Bd = batch.qd_price_batch(q["in_tau"][:n], q["price_S"], q["in_r"][:n], q["in_q"][:n], q["in_sigma"][:n], q["in_K"][:n],
+                                 q["in_is_put"][:n])
+    assert np.max(np.abs(P.cpu().numpy() - q["price"]) / np.maximum(1.0, np.abs(q["price"]))) <= 1e-6
+    assert np.max(np.abs(Bd.cpu().numpy() / q["price_boundary"] - 1)) <= 1e-8
+    P, Bd = batch.qd_price_batch(0.000870786986, 30.543317986992072, float(q["curve_r"]), float(q["curve_q"]),
+                                 float(q["curve_sigma"]), float(q["curve_K"]), True)
+    assert abs(P.item() - 75.07450516104376) <= 1e-9          # reference test_QDplus.py output
+
+
+def test_european_leaf():
+    e = load_golden("ref_european.npz")
+    a = (e["tau"], e["S"], e["r"], e["q"], e["sigma"], e["K"])
+    assert np.max(np.abs(batch.european_batch(*a, True).cpu().numpy() - e["put"])) <= 1e-11
+    assert np.max(np.abs(batch.european_batch(*a, False).cpu().numpy() - e["call"])) <= 1e-11
+    th, d1, d2 = batch.european_greeks_batch(*a)
+    assert np.max(np.abs(th.cpu().numpy() - e["theta"])) <= 1e-11 * np.max(np.abs(e["theta"]))
+    ok = e["tau"] > 0
+    assert np.max(np.abs(d1.cpu().numpy() - e["d1"])[ok] / (1 + np.abs(e["d1"][ok]))) <= 1e-13
+    assert np.max(np.abs(d2.cpu().numpy() - e["d2"])[ok] / (1 + np.abs(e["d2"][ok]))) <= 1e-13
+    assert abs(batch.european_batch(3.0, 80.0, 0.04, 0.01, 0.2, 100.0, True).item() - 17.78865238332743) <= 1e-12
+
+
+def test_cheb_leaf():
+    c = load_golden("ref_cheb.npz")
+    for n in (2, 5, 12, 24, 40):
+        a = batch.cheb_fit_batch(c["n%d_y" % n]).cpu().numpy()[0]
+        assert np.max(np.abs(a - c["n%d_a" % n])) <= 1e-14
+        v = batch.cheb_eval_batch(c["n%d_a" % n], c["n%d_z" % n]).cpu().numpy()[0]
+        assert np.max(np.abs(v - c["n%d_val" % n])) <= 1e-13
+    y = np.random.default_rng(3).normal(size=(1000, 13))
+    a = batch.cheb_fit_batch(y)
+    nodes = np.cos(np.arange(13) * np.pi / 12)
+    back = batch.cheb_eval_batch(a, np.tile(nodes, (1000, 1))).cpu().numpy()
+    assert np.max(np.abs(back - y)) <= 1e-13            # exactness at the nodes (reference test_cheb_intrp.py)
+
+
+def test_device_math():
+    """The FP64 building blocks of the specialised kernel (csrc/faop_fastmath.cuh) against scipy/numpy."""
+    from scipy.special import erfcx, ndtr
+    g = np.random.default_rng(11)
+    x = np.concatenate([g.uniform(-745, 1, 200000), g.uniform(-40, 0.5, 200000), [-800.0, -708.5, -1e-300, 0.0, 0.3]])
+    got = batch.dev_math_batch(0, x).cpu().numpy()
+    ref = np.exp(x)
+    ok = x >= -708
+    assert np.max(np.abs(got[ok] / ref[ok] - 1)) <= 4e-15 and np.all(got[~ok] == 0)
+    assert torch.isnan(batch.dev_math_batch(0, [float("nan")])).all()
+    y = np.concatenate([g.uniform(0, 10, 200000), g.uniform(10, 60, 50000), [0.0, 1e-300, 1e6, float("inf")]])
+    got = batch.dev_math_batch(1, y).cpu().numpy()
+    ref = 0.5 * erfcx(y / np.sqrt(2))
+    fin = np.isfinite(y)
+    assert np.max(np.abs(got[fin] / ref[fin] - 1)) <= 5e-14 and got[~fin][0] == 0
+    s = np.concatenate([10 ** g.uniform(-280, 3, 200000), [1.0, 4.0, 1e-289]])
+    got = batch.dev_math_batch(2, s).cpu().numpy()
+    assert np.max(np.abs(got / np.sqrt(s) - 1)) <= 4e-16
+    a = g.uniform(5, 1e6, 200000)
+    assert np.max(np.abs(batch.dev_math_batch(3, a).cpu().numpy() * a - 1)) <= 4e-16
+    v = g.uniform(-38, 9, 200000)
+    got = batch.dev_math_batch(4, v).cpu().numpy()
+    assert np.max(np.abs(got / ndtr(v) - 1)) <= 6e-14
+
+
+def test_vs_c_oracle_32k():
+    """Same seeded inputs as the bench (prefix of the 1M C2 batch), CUDA vs the plain-C oracle."""
+    from oracle import c_oracle as co
+    N = 32768
+    b = {k: v[:N] for k, v in wl.c2_batch().items()}
+    ref = co.alo_price_batch("A", b["r"], b["q"], b["sigma"], b["K"], b["T"], b["S"], b["is_put"], **{
+        k: wl.C2_CFG[k] for k in ("n", "l", "m", "iter_tol", "max_iters")})
+    for kernel in KERNELS:
+        out = _np(batch.price_batch(b["r"], b["q"], b["sigma"], b["K"], b["T"], b["S"], b["is_put"],
+                                    cfg=AloConfig(kernel=kernel, **wl.C2_CFG)))
+        ps = np.isfinite(ref["price"]) & (ref["err"] < 1e-2)
+        assert ps.sum() >= 0.99 * N
+        assert np.max(np.abs(out["price"] - ref["price"])[ps]) <= PRICE_ABS_TOL
+        assert np.nanmax(np.abs(out["B"] / ref["B"] - 1)[ps]) <= BOUNDARY_REL_TOL
+        assert (out["iters"][ps] != ref["iters"][ps]).sum() <= 1          # a rounding-level flip at the 1e-5 threshold
+        assert np.array_equal(np.isnan(out["price"]), np.isnan(ref["price"]))
+
+
+def test_full_size_properties():
+    """BASELINE size (1M): size-independent properties — determinism, slice invariance, American >= European,
+    generic and specialised kernels agree, host-buffer entry point agrees with the device-pointer one."""
+    N = 1_000_000
+    b = wl.c2_batch(N)
+    a = [b[k] for k in ("r", "q", "sigma", "K", "T", "S", "is_put")]
+    cfg = AloConfig(**wl.C2_CFG)
+    dev = [torch.as_tensor(x).cuda() for x in a]
+    o1 = batch.price_batch(*dev, cfg=cfg, want_boundary=False)
+    o2 = batch.price_batch(*dev, cfg=cfg, want_boundary=False)
+    assert torch.equal(o1["price"], o2["price"]) and torch.equal(o1["iters"], o2["iters"])       # deterministic
+    p = o1["price"].cpu().numpy()
+    ok = np.isfinite(p) & (o1["err"].cpu().numpy() < 1e-2)
+    assert ok.mean() > 0.99
+    assert np.all(p[ok] >= o1["european"].cpu().numpy()[ok] - 1e-7)                               # early exercise premium >= 0
+    intrinsic = np.where(b["is_put"], b["K"] - b["S"], b["S"] - b["K"])
+    assert np.all(p[ok] >= intrinsic[ok] - 1e-4 * b["K"][ok])
+    # slices priced separately are bit-identical to the whole (the multi-GPU sharding invariant)
+    lo, hi = 123_457, 345_679
+    o3 = batch.price_batch(*[x[lo:hi] for x in dev], cfg=cfg, want_boundary=False)
+    assert torch.equal(o3["price"], o1["price"][lo:hi])
+    # generic kernel agrees with the specialised one to rounding
+    o4 = batch.price_batch(*[x[:200_000] for x in dev], cfg=AloConfig(kernel=1, **wl.C2_CFG), want_boundary=False)
+    d = (o4["price"] - o1["price"][:200_000]).abs().cpu().numpy()
+    assert np.nanmax(d[ok[:200_000]]) <= PRICE_ABS_TOL
+    # host-buffer C-ABI entry point
+    ctx = batch.HostContext(0)
+    oh = ctx.price_batch(*[np.ascontiguousarray(x[:100_000]) if x.dtype != bool else x[:100_000].astype(np.uint8) for x in a], cfg=cfg)
+    assert np.array_equal(oh["price"], p[:100_000], equal_nan=True)
+    ctx.close()
+
+
+def test_edge_cases():
+    cfg = AloConfig(**wl.C2_CFG)
+    # empty batch
+    out = batch.price_batch([], [], [], [], [], [], [], cfg=cfg)
+    assert out["price"].numel() == 0 and out["B"].shape == (0, 13)
+    # ragged inputs are refused
+    with pytest.raises(ValueError):
+        batch.price_batch([0.04, 0.05], [0.01, 0.01], [0.2, 0.2], [100.0, 100.0], [3.0, 3.0], [80.0, 80.0, 80.0], [1, 1], cfg=cfg)
+    # sizes that are not multiples of the warp/CTA tiling
+    b = wl.c2_batch(1000)
+    a = [b[k] for k in ("r", "q", "sigma", "K", "T", "S", "is_put")]
+    full = batch.price_batch(*a, cfg=cfg)["price"]
+    for n in (1, 7, 33, 257, 999):
+        part = batch.price_batch(*[x[:n] for x in a], cfg=cfg)["price"]
+        assert torch.equal(part, full[:n])
+    # NaN inputs propagate to NaN outputs without disturbing neighbours
+    r = b["r"].copy()
+    r[5] = np.nan
+    out = batch.price_batch(r, *a[1:], cfg=cfg)["price"]
+    assert torch.isnan(out[5]) and torch.equal(out[:5], full[:5]) and torch.equal(out[6:], full[6:])
+    # t == T: tau = 0 -> intrinsic value, boundary still solved on [0, T]
+    o = batch.price_batch(0.04, 0.01, 0.2, 100.0, 3.0, 80.0, 1, t=3.0, cfg=cfg)
+    assert o["price"].item() == 20.0 and o["iters"].item() >= 15
+    # maximum compiled sizes
+    big = AloConfig("B", 64, 128, 128, 1e-5, 50)
+    o = batch.price_batch(0.04, 0.01, 0.2, 100.0, 3.0, 80.0, 1, cfg=big)
+    assert abs(o["price"].item() - 21.1355) < 1e-3
+    with pytest.raises(Exception):
+        batch.price_batch(0.04, 0.01, 0.2, 100.0, 3.0, 80.0, 1, cfg=AloConfig("A", 65, 24, 48))
