@@ -20,10 +20,24 @@ constexpr int NC = 12;        // collocation n
 constexpr int NN = NC + 1;    // nodes
 constexpr int kGroup = 4;     // nodes per transposing reduction
 
+// Node constants the sweep reads per point, packed so that a lane fetches them with four 16-byte broadcast loads.
+// The d+- arguments are carried as x = d/sqrt2 (exp(-d^2/2) = exp(-x^2), Phi(-d) = erfcx(x)/2 exp(-x^2)).
+struct __align__(16) NodePack {
+    double L;      // ln(B_i/X), refreshed every iteration
+    double cinv2;  // 1/(sigma sqrt(2 tau_i))
+    double apc2;   // ((r-q) + sigma^2/2) sqrt(tau_i/2)/sigma
+    double ssu2;   // sigma sqrt(tau_i/2)
+    double qtau;   // q tau_i
+    double rtau;   // r tau_i
+    double cis;    // 1/(sigma sqrt(2 pi tau_i))
+    double pad;
+};
+
 struct FastWarpSmem {
     double eq[NC * 32];   // e^{q u_ik}, [i][k]
+    NodePack node[16];
     double B[16], L[16], H[16], A[16];
-    double tau[16], cinv[16], apc[16], ssu[16], disc[16];
+    double tau[16], disc[16];
     double sN[16], sD[16];
     double par[8];   // X, 1/X, ln(X/K)
 };
@@ -69,9 +83,14 @@ __global__ void __launch_bounds__(kFastWarps * 32, 1) alo_fast_A12_kernel(AloArg
     extern __shared__ double smem[];
     const TableLayout tl = a.tl;
     double* s_tab = smem;
-    double* s_M = smem + tl.small;
-    FastWarpSmem* s_w = reinterpret_cast<FastWarpSmem*>(s_M + NC * NN * 32);
-    for (int i = threadIdx.x; i < tl.small + NC * NN * 32; i += blockDim.x) smem[i] = a.tables[i];
+    double* s_M = smem + tl.small;          // re-laid out as M2[i][j/2][k][j&1], j < 12: one 16-byte load feeds two DFMAs
+    FastWarpSmem* s_w = reinterpret_cast<FastWarpSmem*>(s_M + NC * NC * 32);
+    for (int i = threadIdx.x; i < tl.small; i += blockDim.x) smem[i] = a.tables[i];
+    for (int e = threadIdx.x; e < NC * NC * 32; e += blockDim.x) {
+        const int k = e & 31, j = (e >> 5) % NC, i = e / (32 * NC);
+        // the j = n column multiplies H_n = ln(X/X)^2 = 0 (the tau = 0 node is pinned to X) and is dropped
+        s_M[((i * (NC / 2) + (j >> 1)) * 32 + k) * 2 + (j & 1)] = a.tables[tl.off_M + (i * NN + j) * 32 + k];
+    }
     __syncthreads();
     const CtaTables tb(s_tab, tl);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -89,6 +108,7 @@ __global__ void __launch_bounds__(kFastWarps * 32, 1) alo_fast_A12_kernel(AloArg
     const int64_t stride = (int64_t)gridDim.x * kFastWarps;
     for (int64_t opt = (int64_t)blockIdx.x * kFastWarps + warp; opt < a.N; opt += stride) {
         double om, oq, orr;     // the only option scalars the sweep needs in registers
+        int sgn;
         bool degenerate;
         {
             const Opt o = load_option(a, opt);
@@ -109,11 +129,20 @@ __global__ void __launch_bounds__(kFastWarps * 32, 1) alo_fast_A12_kernel(AloArg
                 double tau = (c + 1) * (c + 1) * o.T / 4;      // to_orig_point, FastAmericanOptionSolverBase.py:239-240
                 double sqt = sqrt(tau);
                 ws.tau[lane] = tau;
-                ws.ssu[lane] = o.sg * sqt;
-                ws.cinv[lane] = 1.0 / (o.sg * sqt);
-                ws.apc[lane] = ((o.r - o.q) + 0.5 * o.sg * o.sg) * sqt / o.sg;
+                NodePack np;
+                np.L = 0.0;
+                np.cinv2 = kInvSqrt2 / (o.sg * sqt);
+                np.apc2 = kInvSqrt2 * ((o.r - o.q) + 0.5 * o.sg * o.sg) * sqt / o.sg;
+                np.ssu2 = kInvSqrt2 * o.sg * sqt;
+                np.qtau = o.q * tau;
+                np.rtau = o.r * tau;
+                np.cis = kInvSqrt2Pi / (o.sg * sqt);
+                np.pad = 0.0;
+                ws.node[lane] = np;
                 ws.disc[lane] = o.K * exp(-tau * (o.r - o.q));
-                ws.B[lane] = a.seeds_in[opt * NN + lane];
+                // the tau = 0 node is pinned to X: the reference's seed has it (QDplus.compute_exercise_boundary(0) ->
+                // B_at_zero) and every sweep re-imposes it; a borrowed B0 row is normalised the same way
+                ws.B[lane] = (lane == NC) ? o.X : a.seeds_in[opt * NN + lane];
             }
             if (lane == 0) {
                 ws.par[0] = o.X;
@@ -121,6 +150,7 @@ __global__ void __launch_bounds__(kFastWarps * 32, 1) alo_fast_A12_kernel(AloArg
                 ws.par[2] = log(o.X / o.K);
             }
             om = o.om; oq = o.q; orr = o.r;
+            sgn = o.put ? 0 : (int)0x80000000;   // sign flip of the call side, applied with integer XOR
             degenerate = !(o.T > 0);     // T == 0: every node has tau == 0 and is pinned to X
         }
         __syncwarp();
@@ -133,48 +163,68 @@ __global__ void __launch_bounds__(kFastWarps * 32, 1) alo_fast_A12_kernel(AloArg
             ++count;
             // ---- L_j = ln(B_j/X), H_j = L_j^2 (FastAmericanOptionSolverBase.py:184), broadcast through shared memory
             if (lane < NN) {
-                double L = log(ws.B[lane] * ws.par[1]);
+                double L = (lane == NC) ? 0.0 : log(ws.B[lane] * ws.par[1]);
                 ws.L[lane] = L;
+                ws.node[lane].L = L;
                 ws.H[lane] = L * L;
             }
             __syncwarp();
-            double Hj[NN];
+            double Hj[NC];
 #pragma unroll
-            for (int j = 0; j < NN; ++j) Hj[j] = ws.H[j];
+            for (int j = 0; j < NC; ++j) Hj[j] = ws.H[j];
 
-            // ---- quadrature of K12 / K3 at the 12 active nodes, 4 nodes per transposing reduction
+            // ---- quadrature of K12 / K3 at the 12 active nodes: 4 nodes per transposing reduction, the nodes of a
+            //      group advanced two at a time in lock step (2 sqrt, 4 exp and 2 erfcx chains in flight per lane)
             if (!degenerate) {
-#pragma unroll
+#pragma unroll 1
                 for (int grp = 0; grp < NC / kGroup; ++grp) {
                     double acc[8];
 #pragma unroll
-                    for (int ii = 0; ii < kGroup; ++ii) {
-                        const int i = grp * kGroup + ii;
-                        const double* Mi = s_M + (i * NN) * 32 + lane;
-                        // H(u_ik) = sum_j M[i][j][k] H_j, two partial chains for ILP
-                        double s0 = Mi[0] * Hj[0], s1 = Mi[32] * Hj[1];
+                    for (int pr = 0; pr < kGroup / 2; ++pr) {
+                        const int i0 = grp * kGroup + pr * 2;
+                        double Hu[2], root[2];
 #pragma unroll
-                        for (int j = 2; j < NN - 1; j += 2) {
-                            s0 = fma(Mi[j * 32], Hj[j], s0);
-                            s1 = fma(Mi[(j + 1) * 32], Hj[j + 1], s1);
+                        for (int p = 0; p < 2; ++p) {
+                            const double2* Mi = reinterpret_cast<const double2*>(s_M) + ((i0 + p) * (NC / 2)) * 32 + lane;
+                            // H(u_ik) = sum_{j<n} M[i][j][k] H_j
+                            double2 m = Mi[0];
+                            double acc0 = m.x * Hj[0];
+                            acc0 = fma(m.y, Hj[1], acc0);
+#pragma unroll
+                            for (int jp = 1; jp < NC / 2; ++jp) {
+                                m = Mi[jp * 32];
+                                acc0 = fma(m.x, Hj[2 * jp], acc0);
+                                acc0 = fma(m.y, Hj[2 * jp + 1], acc0);
+                            }
+                            Hu[p] = acc0;
                         }
-                        s0 = fma(Mi[(NN - 1) * 32], Hj[NN - 1], s0);
-                        const double Hu = s0 + s1;
-                        const double root = (Hu <= 1e-290) ? 0.0 : fast_sqrt_pos(Hu);   // sqrt(max(0, H)); NaN propagates
-                        const double lnz = fma(om, root, ws.L[i]);
-                        const double cinv = ws.cinv[i];
-                        const double inv = cinv * rh;
-                        const double dp = fma(lnz, inv, ws.apc[i] * h);
-                        const double dm = fma(-ws.ssu[i], h, dp);
-                        const double taug = ws.tau[i] * g;                          // u_ik
-                        const double Eq = fast_exp(fma(-0.5 * dp, dp, oq * taug));  // e^{qu} phi(d+) sqrt(2 pi)
-                        const double Er = fast_exp(fma(-0.5 * dm, dm, orr * taug));  // e^{ru} phi(d-) sqrt(2 pi)
-                        // put: +e^{qu} Phi(d+); call: -e^{qu} Phi(-d+)   (FastAmericanOptionSolverA.py:27-32)
-                        const double cdf = om * fast_scaled_cdf(om * dp, Eq, ws.eq[i * 32 + lane]);
-                        double d = wh * cdf;
-                        d = fma(cinv * kInvSqrt2Pi * wk, Eq, d);
-                        acc[2 * ii] = wk * Er;       // -> K3  = tau cinv/sqrt(2 pi) * sum
-                        acc[2 * ii + 1] = d;         // -> K12 = tau * sum
+                        sqrt_clamped_n<2>(Hu, root);        // sqrt(max(0, H)), NaN propagates
+                        double ex[4], xa[2], xp[2], cisw[2];
+#pragma unroll
+                        for (int p = 0; p < 2; ++p) {
+                            const NodePack& nd = ws.node[i0 + p];
+                            const double lnz = fma(om, root[p], nd.L);
+                            xp[p] = fma(lnz, nd.cinv2 * rh, nd.apc2 * h);        // d+ / sqrt2
+                            const double xm = fma(-nd.ssu2, h, xp[p]);             // d- / sqrt2
+                            ex[2 * p] = fma(-xp[p], xp[p], nd.qtau * g);           // q u - d+^2/2
+                            ex[2 * p + 1] = fma(-xm, xm, nd.rtau * g);             // r u - d-^2/2
+                            xa[p] = fabs(xp[p]);
+                            cisw[p] = nd.cis * wk;
+                        }
+                        double E[4], G[2];
+                        fast_exp_n<4, true>(ex, E);               // E[2p] = e^{qu} phi(d+) sqrt(2 pi), E[2p+1] = e^{ru} phi(d-) sqrt(2 pi)
+                        half_erfcx_n<2, true>(xa, G);
+#pragma unroll
+                        for (int p = 0; p < 2; ++p) {
+                            // put: +e^{qu} Phi(d+); call: -e^{qu} Phi(-d+)   (FastAmericanOptionSolverA.py:27-32)
+                            const double ec = E[2 * p] * G[p];
+                            const double eqv = ws.eq[(i0 + p) * 32 + lane];
+                            const bool neg = (__double2hiint(xp[p]) ^ sgn) < 0;   // om * d+ < 0 (both branches agree at 0)
+                            double cdf = neg ? ec : eqv - ec;
+                            cdf = __hiloint2double(__double2hiint(cdf) ^ sgn, __double2loint(cdf));  // times om
+                            acc[4 * pr + 2 * p] = wk * E[2 * p + 1];                 // -> K3  = tau cinv/sqrt(2 pi) * sum
+                            acc[4 * pr + 2 * p + 1] = fma(cisw[p], E[2 * p], wh * cdf);  // -> K12 = tau * sum
+                        }
                     }
                     const double tot = transpose_reduce8(acc, lane);
                     // lanes 8 ii .. 8 ii + 3 hold the K3 sum of node grp*4+ii, lanes 8 ii + 4 .. 8 ii + 7 its K12 sum
@@ -194,15 +244,15 @@ __global__ void __launch_bounds__(kFastWarps * 32, 1) alo_fast_A12_kernel(AloArg
                 if (tau == 0) {
                     Bn = ws.par[0];                // iterate_once_foreach_tau: tau_i == 0 -> B_at_zero
                 } else {
-                    const double cinv = ws.cinv[lane];
-                    const double LK = ws.L[lane] + ws.par[2];
-                    const double dpK = fma(LK, cinv, ws.apc[lane]);
-                    const double dmK = dpK - ws.ssu[lane];
-                    const double Ep = fast_exp(-0.5 * dpK * dpK), Em = fast_exp(-0.5 * dmK * dmK);
-                    const double K3 = tau * cinv * kInvSqrt2Pi * ws.sN[lane];
+                    const NodePack nd = ws.node[lane];
+                    const double LK = nd.L + ws.par[2];
+                    const double xpK = fma(LK, nd.cinv2, nd.apc2);      // d+(tau_i, B_i/K) / sqrt2
+                    const double xmK = xpK - nd.ssu2;
+                    const double Ep = fast_exp(-xpK * xpK), Em = fast_exp(-xmK * xmK);
+                    const double K3 = tau * nd.cis * ws.sN[lane];
                     const double K12 = tau * ws.sD[lane];
-                    const double Nv = Em * kInvSqrt2Pi * cinv + orr * K3;                                  // A.py:5-10
-                    const double Dv = Ep * kInvSqrt2Pi * cinv + om * fast_scaled_cdf(om * dpK, Ep, 1.0) + oq * K12;  // A.py:13-19
+                    const double Nv = Em * nd.cis + orr * K3;                                               // A.py:5-10
+                    const double Dv = Ep * nd.cis + om * fast_half_erfcx_cdf(om * xpK, Ep) + oq * K12;      // A.py:13-19
                     const double f = ws.disc[lane] * Nv / Dv;                                               // Base.py:273
                     Bn = Bj + a.cfg.eta * (Bj - f) / (0.0 - 1.0);                                           // Base.py:164
                 }
@@ -228,7 +278,7 @@ __global__ void __launch_bounds__(kFastWarps * 32, 1) alo_fast_A12_kernel(AloArg
 
 template <int kFastWarps>
 static int launch_fast_t(const AloArgs& a, cudaStream_t st) {
-    const size_t sm = sizeof(double) * (size_t)(a.tl.small + NC * NN * 32) + sizeof(FastWarpSmem) * kFastWarps;
+    const size_t sm = sizeof(double) * (size_t)(a.tl.small + NC * NC * 32) + sizeof(FastWarpSmem) * kFastWarps;
     FAOP_CUDA_OK(cudaFuncSetAttribute(alo_fast_A12_kernel<kFastWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     int64_t ctas = (a.N + kFastWarps - 1) / kFastWarps;
     int grid = (int)(ctas < kSMs ? ctas : kSMs);
@@ -237,13 +287,15 @@ static int launch_fast_t(const AloArgs& a, cudaStream_t st) {
     return launch_status();
 }
 
-// cfg.kernel: 0 = default (16 warps/CTA, 128 registers/thread), 2 = 12 warps/CTA with up to 168 registers/thread
+// cfg.kernel: 0 = default (16 warps/CTA, <= 128 registers/thread); tuning variants 2 / 3 / 4 = 12 / 20 / 24 warps per CTA
 int launch_alo_fast(const AloArgs& a, cudaStream_t st) {
     const bool match = a.cfg.solver == 0 && !a.cfg.use_derivative && a.tl.n == NC && a.tl.LP == 32 && a.tl.has_matrix &&
                        a.iter_errs == nullptr;
     if (!match) return -1000;
     if (a.N == 0) return 0;
     if (a.cfg.kernel == 2) return launch_fast_t<12>(a, st);
+    if (a.cfg.kernel == 3) return launch_fast_t<20>(a, st);
+    if (a.cfg.kernel == 4) return launch_fast_t<24>(a, st);
     return launch_fast_t<16>(a, st);
 }
 

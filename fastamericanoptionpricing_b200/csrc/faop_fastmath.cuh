@@ -12,6 +12,39 @@
 
 namespace faop {
 
+// Polynomial coefficients live in constant memory so that every DFMA takes its coefficient as a constant-bank operand
+// (c[bank][offset]) instead of two 32-bit immediate moves into registers per coefficient.
+// kExpC[k]: exp(r) = sum_k kExpC[k] r^k on |r| <= ln2/2.
+// kMillsC[k]: (x + kMillsShift) * erfcx(x)/2 = sum_k kMillsC[k] t^k with t = 1 - 2 kMillsShift/(x + kMillsShift)
+//             (the degree-18 fit of (y+5) Phi(-y)/exp(-y^2/2) in y = sqrt2 x, divided by sqrt2).
+static __constant__ double kExpC[11] = {1.0, 1.00000000000000666e+00, 5.00000000000001887e-01, 1.66666666665542140e-01,
+                                 4.16666666664877935e-02, 8.33333338573419465e-03, 1.38888889523942471e-03,
+                                 1.98411701867620645e-04, 2.48014853976660804e-05, 2.76402154411630899e-06,
+                                 2.76326708447496886e-07};
+// Reduced-degree fits for the quadrature points, where the terms enter N and D with weight ~ r tau, q tau <= 0.3
+// (max rel 1.1e-12 for exp, 3.0e-11 for erfcx/2; the node-level closure keeps the full-accuracy tables):
+static __constant__ double kExp8[9] = {1.00000000000001354e+00, 9.99999999979748533e-01, 4.99999999994376054e-01,
+                                       1.66666668913440119e-01, 4.16666670410351936e-02, 8.33326603932144604e-03,
+                                       1.38888016753182446e-03, 1.99158990839349160e-04, 2.48844948414224168e-05};
+// (x + 3) erfcx(x)/2 = sum_k kErfcx14[k] t^k, t = 1 - 6/(x + 3)
+static __constant__ double kErfcx14[15] = {
+    5.37003453547791554e-01, -4.41697226390743936e-01, 2.95114178084050105e-01, -1.55233638330990936e-01,
+    5.97638905924903277e-02, -1.34135356524479627e-02, -6.06289213047839443e-04, 1.51662855789247821e-03,
+    -2.73829690347347061e-04, -1.37352260196071919e-04, 5.30630226822841820e-05, 1.37163947469176610e-05,
+    -7.83813889147139852e-06, -1.19644291282268299e-06, 7.67685587370318563e-07};
+#define FAOP_S2 0.70710678118654752440
+static __constant__ double kMillsC[19] = {
+    7.69193049750053093e-01 * FAOP_S2, -6.65382502890239702e-01 * FAOP_S2, 4.95305615971961821e-01 * FAOP_S2,
+    -3.13533156660161738e-01 * FAOP_S2, 1.65020366104179528e-01 * FAOP_S2, -6.91186389062564549e-02 * FAOP_S2,
+    2.07950676583355080e-02 * FAOP_S2, -2.99337512829167757e-03 * FAOP_S2, -7.97875070561768315e-04 * FAOP_S2,
+    5.44891678680881932e-04 * FAOP_S2, -5.93541001006240258e-05 * FAOP_S2, -4.97429386785415854e-05 * FAOP_S2,
+    1.66306732961883153e-05 * FAOP_S2, 3.94749285187075274e-06 * FAOP_S2, -2.69546304181993080e-06 * FAOP_S2,
+    -3.01053062131189312e-07 * FAOP_S2, 3.67057836016596013e-07 * FAOP_S2, 1.86058824387743594e-08 * FAOP_S2,
+    -3.23812507239800613e-08 * FAOP_S2};
+constexpr double kMillsShift = 5.0 * FAOP_S2;
+
+template <int NCH, bool LOW> FAOP_D void half_erfcx_n(const double (&x)[NCH], double (&out)[NCH]);
+
 FAOP_D double fast_rcp(double a) {
     double x0;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x0) : "d"(a));  // ~20 good bits
@@ -46,6 +79,7 @@ FAOP_D double fast_exp(double x) {
 FAOP_D double mills_half(double y) {
     const double c = 5.0;
     double w = fast_rcp(y + c);
+    if (__double2hiint(y) == 0x7ff00000) w = 0.0;   // y = +inf (integer test: no FP64-pipe slot); NaN falls through
     double t = fma(-2.0 * c, w, 1.0);
     double q = -3.23812507239800613e-08;
     q = fma(q, t, 1.86058824387743594e-08);
@@ -75,6 +109,14 @@ FAOP_D double fast_scaled_cdf(double x, double E, double ea) {
     return (x <= 0.0) ? ec : ea - ec;
 }
 
+// Phi(sqrt2 x) from E = exp(-x^2): the node-level closure (one value per lane, not on the hot path).
+FAOP_D double fast_half_erfcx_cdf(double x, double E) {
+    double xa[1] = {fabs(x)}, G[1];
+    half_erfcx_n<1, false>(xa, G);
+    double ec = E * G[0];
+    return (x <= 0.0) ? ec : 1.0 - ec;
+}
+
 // sqrt(x) for x > 0 and normal; callers clamp non-positive inputs.  NaN propagates.
 FAOP_D double fast_sqrt_pos(double x) {
     double y0;
@@ -85,6 +127,78 @@ FAOP_D double fast_sqrt_pos(double x) {
     h = fma(h, r, h);
     r = fma(-g, h, 0.5);
     return fma(g, r, g);
+}
+
+// ---- chain-interleaved versions: NCH independent evaluations advance in lock step so that the FP64 pipe always has
+// NCH independent DFMAs in flight per warp (a lone Horner chain is latency-bound).
+
+// exp(x[c]) for NCH arguments.  Arguments below -700 are clamped to ~-700 on the high word with one integer min (the
+// result, < 1e-304, is zero for every sum it enters); NaN propagates.  LOW selects the degree-8 table.
+template <int NCH, bool LOW = false>
+FAOP_D void fast_exp_n(const double (&xin)[NCH], double (&out)[NCH]) {
+    const double kL2E = 1.4426950408889634074, kMagic = 6755399441055744.0;
+    double x[NCH], t[NCH], r[NCH], p[NCH];
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+        unsigned hi = min((unsigned)__double2hiint(xin[c]), 0xC085E000u);   // 0xC085E000 = high word of -700.0
+        x[c] = __hiloint2double((int)hi, __double2loint(xin[c]));
+        t[c] = fma(x[c], kL2E, kMagic);
+    }
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+        double kf = t[c] - kMagic;
+        // one-step reduction: the rounding of ln2 costs |kf| * 2.3e-17 relative, < 1.4e-15 for every argument above -40
+        r[c] = fma(kf, -6.93147180559945309e-01, x[c]);
+        p[c] = LOW ? kExp8[8] : kExpC[10];
+    }
+#pragma unroll
+    for (int k = (LOW ? 7 : 9); k >= 0; --k) {
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) p[c] = fma(p[c], r[c], LOW ? kExp8[k] : kExpC[k]);
+    }
+#pragma unroll
+    for (int c = 0; c < NCH; ++c)
+        out[c] = __hiloint2double(__double2hiint(p[c]) + (__double2loint(t[c]) << 20), __double2loint(p[c]));
+}
+
+// erfcx(x[c]) / 2 for NCH arguments x >= 0.  The argument is clamped to ~1e300 on the high word (integer min), so
+// x = +inf gives ~0; a NaN argument always arrives with a NaN exp factor, which keeps the product NaN.
+template <int NCH, bool LOW = false>
+FAOP_D void half_erfcx_n(const double (&xin)[NCH], double (&out)[NCH]) {
+    const double sh = LOW ? 3.0 : kMillsShift;
+    double w[NCH], t[NCH], q[NCH];
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+        int hi = min(__double2hiint(xin[c]), 0x7E37E43C);                    // high word of 1e300
+        double x = __hiloint2double(hi, __double2loint(xin[c]));
+        w[c] = fast_rcp(x + sh);
+        t[c] = fma(-2.0 * sh, w[c], 1.0);
+        q[c] = LOW ? kErfcx14[14] : kMillsC[18];
+    }
+#pragma unroll
+    for (int k = (LOW ? 13 : 17); k >= 0; --k) {
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) q[c] = fma(q[c], t[c], LOW ? kErfcx14[k] : kMillsC[k]);
+    }
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) out[c] = q[c] * w[c];
+}
+
+// sqrt(max(0, x[c])) for NCH arguments, branch-free; values below ~1e-289 (or negative) give 0, NaN propagates.
+// One rsqrt seed (>= 20 bits) and one third-order step: g (1 + r + 3/2 r^2) with r = 1/2 - g h, error ~ r^3.
+template <int NCH>
+FAOP_D void sqrt_clamped_n(const double (&x)[NCH], double (&out)[NCH]) {
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+        double y0;
+        asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(x[c]));
+        double g = x[c] * y0, h = 0.5 * y0;
+        double r = fma(-g, h, 0.5);
+        double r2 = fma(1.5 * r, r, r);
+        g = fma(g, r2, g);
+        // x < ~1e-289 or negative (signed test on the high word, integer ALU); NaN is not tiny and stays NaN
+        out[c] = (__double2hiint(x[c]) < 0x03C00000) ? 0.0 : g;
+    }
 }
 
 }  // namespace faop

@@ -170,6 +170,11 @@ __global__ void __launch_bounds__(256) dev_math_kernel(int kind, int64_t N, cons
         case 2: r = fast_sqrt_pos(v); break;
         case 3: r = fast_rcp(v); break;
         case 4: r = fast_scaled_cdf(v, fast_exp(-0.5 * v * v), 1.0); break;   // Phi(v)
+        case 5: { double a[1] = {v}, o[1]; half_erfcx_n<1, false>(a, o); r = o[0]; break; }      // erfcx(v)/2
+        case 6: { double a[1] = {v}, o[1]; sqrt_clamped_n<1>(a, o); r = o[0]; break; }    // sqrt(max(0, v))
+        case 8: { double a[1] = {v}, o[1]; half_erfcx_n<1, true>(a, o); r = o[0]; break; }       // erfcx(v)/2, degree 14
+        case 9: { double a[1] = {v}, o[1]; fast_exp_n<1, true>(a, o); r = o[0]; break; }         // e^v, degree 8
+        case 7: { double a[2] = {v, v - 1.0}, o[2]; fast_exp_n<2>(a, o); r = o[0] + o[1]; break; }  // e^v + e^(v-1)
         default: r = nan("");
     }
     out[i] = r;
@@ -181,18 +186,23 @@ int launch_dev_math(int kind, int64_t N, const double* x, double* out, cudaStrea
     return launch_status();
 }
 
-// FP64 FMA-pipe peak: 8 independent DFMA chains per thread, 4096 rounds, full occupancy.
+// FP64 FMA-pipe peak: 8 independent DFMA chains per thread with all three operands in regular registers (a DFMA whose
+// multiplicand sits in a uniform register or immediate issues at only ~65-77 % of this rate on sm_100a, measured with
+// tools/dfma_peak.cu), 4096 rounds, 8 resident CTAs/SM.
 constexpr int kPeakIters = 4096;
 constexpr int kPeakChains = 8;
-__global__ void __launch_bounds__(256) fp64_peak_kernel(double* sink, double seed) {
-    double x[kPeakChains];
+__global__ void __launch_bounds__(256) fp64_peak_kernel(double* sink, const double* coef) {
+    double x[kPeakChains], b[kPeakChains];
+    const double m = coef[threadIdx.x & 1];   // opaque per-thread values: they live in regular registers
 #pragma unroll
-    for (int c = 0; c < kPeakChains; ++c) x[c] = seed + c + threadIdx.x * 1e-9;
-    const double m = 0.999999, b = 1e-7;
+    for (int c = 0; c < kPeakChains; ++c) {
+        x[c] = 1.0 + c + threadIdx.x * 1e-9;
+        b[c] = coef[2 + c];
+    }
 #pragma unroll 1
     for (int it = 0; it < kPeakIters; ++it) {
 #pragma unroll
-        for (int c = 0; c < kPeakChains; ++c) x[c] = fma(x[c], m, b);
+        for (int c = 0; c < kPeakChains; ++c) x[c] = fma(x[c], m, b[c]);
     }
     double s = 0;
 #pragma unroll
@@ -250,15 +260,21 @@ int launch_cheb_eval(int64_t N, int n, int npts, const double* a, const double* 
 }
 
 int launch_fp64_peak(int launches, double* tflops, double* ms_per_launch, cudaStream_t st) {
-    double* sink = nullptr;
-    FAOP_CUDA_OK(cudaMalloc(&sink, sizeof(double)));
+    double* buf = nullptr;
+    FAOP_CUDA_OK(cudaMalloc(&buf, 16 * sizeof(double)));
+    double h[16];
+    h[0] = 0.0;
+    for (int i = 1; i < 16; ++i) h[i] = 1e-7 * i;
+    h[1] = 0.999999; h[2] = 0.999998;
+    // layout: [0] sink, [1..2] multipliers, [3..10] addends
+    FAOP_CUDA_OK(cudaMemcpyAsync(buf, h, sizeof h, cudaMemcpyHostToDevice, st));
     cudaEvent_t e0, e1;
     FAOP_CUDA_OK(cudaEventCreate(&e0));
     FAOP_CUDA_OK(cudaEventCreate(&e1));
     const int blocks = kSMs * 8 * 4, threads = 256;  // 8 resident CTAs/SM x 4 waves
-    for (int w = 0; w < 2; ++w) { fp64_peak_kernel<<<blocks, threads, 0, st>>>(sink, 1.0); count_launch(); }
+    for (int w = 0; w < 2; ++w) { fp64_peak_kernel<<<blocks, threads, 0, st>>>(buf, buf + 1); count_launch(); }
     FAOP_CUDA_OK(cudaEventRecord(e0, st));
-    for (int i = 0; i < launches; ++i) { fp64_peak_kernel<<<blocks, threads, 0, st>>>(sink, 1.0 + i); count_launch(); }
+    for (int i = 0; i < launches; ++i) { fp64_peak_kernel<<<blocks, threads, 0, st>>>(buf, buf + 1); count_launch(); }
     FAOP_CUDA_OK(cudaEventRecord(e1, st));
     FAOP_CUDA_OK(cudaEventSynchronize(e1));
     float ms = 0;
@@ -268,7 +284,7 @@ int launch_fp64_peak(int launches, double* tflops, double* ms_per_launch, cudaSt
     if (ms_per_launch) *ms_per_launch = ms / launches;
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
-    cudaFree(sink);
+    cudaFree(buf);
     return launch_status();
 }
 
