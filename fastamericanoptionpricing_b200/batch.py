@@ -366,6 +366,24 @@ def cn_dt_schedule(T, max_dt):
     return out
 
 
+def cn_dt_schedule_batch(T, max_dt):
+    """cn_dt_schedule for many options at once: the same float countdown, vectorised over options (one numpy pass per
+    time step).  Returns (dts [N x max_steps], n_steps [N])."""
+    t = np.array(T, dtype=np.float64, copy=True)
+    max_dt = np.asarray(max_dt, dtype=np.float64)
+    cols = []
+    ns = np.zeros(t.shape[0], dtype=np.int32)
+    live = t > 0
+    while live.any():
+        dt = np.where(live, np.minimum(t, max_dt), 0.0)
+        cols.append(dt)
+        ns += live
+        t = np.where(live, t - dt, t)
+        live = t > 0
+    dts = np.stack(cols, axis=1) if cols else np.zeros((t.shape[0], 1))
+    return np.ascontiguousarray(dts), ns
+
+
 CN_MODE_DIRECT, CN_MODE_SOR, CN_MODE_PROJECTED = 0, 1, 2
 
 
@@ -377,20 +395,7 @@ def cn_put_batch(r, q, sigma, K, T, S0, n_space=200, max_dt=1 / 12.0, mode=CN_MO
     lib = _lib.load()
     dev, N, (r, q, sigma, K, T, S0) = _common([r, q, sigma, K, T, S0], device)
     with torch.cuda.device(dev):
-        Th = T.cpu().numpy()
-        mdt = np.broadcast_to(np.asarray(max_dt, dtype=np.float64), (N,))
-        if np.all(Th == Th[0]) and np.all(mdt == mdt[0]):
-            s0 = cn_dt_schedule(Th[0], mdt[0])
-            dts = np.tile(np.asarray(s0), (N, 1))
-            ns = np.full(N, len(s0), dtype=np.int32)
-        else:
-            sched = [cn_dt_schedule(Th[i], mdt[i]) for i in range(N)]
-            ms = max(len(s) for s in sched)
-            dts = np.zeros((N, ms))
-            ns = np.zeros(N, dtype=np.int32)
-            for i, s in enumerate(sched):
-                dts[i, :len(s)] = s
-                ns[i] = len(s)
+        dts, ns = cn_dt_schedule_batch(T.cpu().numpy(), np.broadcast_to(np.asarray(max_dt, dtype=np.float64), (N,)))
         dts_d = torch.from_numpy(np.ascontiguousarray(dts)).to(dev)
         ns_d = torch.from_numpy(ns).to(dev)
         price = torch.empty(N, dtype=torch.float64, device=dev)

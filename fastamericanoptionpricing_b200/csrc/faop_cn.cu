@@ -1,9 +1,433 @@
 // faop_cn.cu — batched Crank-Nicolson American put solver (CNOptionSolver, CrankNicolsonOptionSolver.py:5-107).
+//
+// Grid S_i = linspace(0, 3K, N), payoff max(K - S, 0), time stepping over the host-built dt schedule of solvePDE's
+// float countdown (:36-45).  Rows (setCoeff, :55-79), with a = sigma S_i/dS and m = (r-q) S_i/dS:
+//   alpha = dt/4 (a^2 - m), beta = dt/2 (r + a^2), gamma = dt/4 (a^2 + m)
+//   row 0      : (1+beta_0) X_0 = (1-beta_0) X_0^old
+//   rows 1..N-2: -alpha X_{i-1} + (1+beta) X_i - gamma X_{i+1} = alpha X^old_{i-1} + (1-beta) X^old_i + gamma X^old_{i+1}
+//   row N-1    : -X_{N-4} + 4 X_{N-3} - 5 X_{N-2} + 2 X_{N-1} = 0
+// mode 0 (the reference default, np.linalg.solve, no early-exercise projection) and mode 2 (Brennan-Schwartz
+// projected back-substitution max(., K - S_i), the throughput mode) run ONE CTA PER OPTION with the grid values in
+// registers (NPT consecutive nodes per thread): per time step the right-hand side is a 3-point stencil, the forward
+// elimination d'_i = P_i + Q_i d'_{i-1} is an affine recurrence and the (projected) back-substitution
+// X_i = max(d'_i + R_i X_{i+1}, g_i) a max-affine one (R_i >= 0), both evaluated as parallel scans of composed maps:
+// thread-local composition, shuffle scan inside the warp, a short pass over the warp totals in shared memory.
+// The 4-term last row is closed exactly by writing X_{N-2}, X_{N-3}, X_{N-4} as affine functions of X_{N-1}.
+// mode 1 is the reference's SOR-sweep-then-project loop (:84-107) operation for operation (Gauss-Seidel is
+// sequential: one thread per option, small grids only) and reproduces its quirks (leaked index, j = N-1 self term).
+// Compiled with -fmad=false: the reference (numpy) never fuses a*b+c, and mode 1 is bit-comparable to it.
 #include "faop_kernels.h"
+
+namespace faop {
+
+constexpr int kCnThreads = 256;
+constexpr int kCnWarps = kCnThreads / 32;
+constexpr unsigned kFullMask = 0xffffffffu;
+
+struct CnArgs {
+    int64_t N;
+    int n_space, max_steps, mode, max_iter;
+    const double *r, *q, *sigma, *K, *S0, *dts;
+    const int32_t* n_steps;
+    double omega, tol;
+    double *price, *X_out, *ws;
+};
+
+__device__ __forceinline__ double grid_point(int i, int n, double K) {
+    // np.linspace(0, 3K, N): i * step + 0, last point == 3K exactly
+    if (i == n - 1) return 3.0 * K;
+    double step = (3.0 * K - 0.0) / (double)(n - 1);
+    return (double)i * step + 0.0;
+}
+
+// np.interp(S0, S, X) on the uniform grid; X read through a functor
+template <typename XF>
+__device__ double interp_uniform(double S0, int n, double K, XF X) {
+    double S_first = 0.0, S_last = 3.0 * K;
+    if (!(S0 > S_first)) return X(0);
+    if (!(S0 < S_last)) return X(n - 1);
+    double dS = grid_point(1, n, K) - grid_point(0, n, K);
+    int j = (int)(S0 / dS);
+    if (j > n - 2) j = n - 2;
+    while (j > 0 && grid_point(j, n, K) > S0) --j;
+    while (j < n - 2 && grid_point(j + 1, n, K) <= S0) ++j;
+    double xj = X(j), xj1 = X(j + 1);
+    double sj = grid_point(j, n, K), sj1 = grid_point(j + 1, n, K);
+    double slope = (xj1 - xj) / (sj1 - sj);
+    return slope * (S0 - sj) + xj;
+}
+
+// ---------------------------------------------------------------- modes 0 / 2: one CTA per option, scans
+// affine map x -> A x + B
+struct Aff { double A, B; };
+// max-affine map x -> max(A x + B, C), A >= 0
+struct MaxAff { double A, B, C; };
+
+__device__ __forceinline__ Aff compose(const Aff& outer, const Aff& inner) {  // outer(inner(x))
+    return {outer.A * inner.A, outer.A * inner.B + outer.B};
+}
+__device__ __forceinline__ MaxAff compose(const MaxAff& outer, const MaxAff& inner) {
+    // max(a1 max(a2 x + b2, c2) + b1, c1) = max(a1 a2 x + a1 b2 + b1, max(a1 c2 + b1, c1)),  a1 >= 0
+    return {outer.A * inner.A, outer.A * inner.B + outer.B, fmax(outer.A * inner.C + outer.B, outer.C)};
+}
+__device__ __forceinline__ double apply(const Aff& f, double x) { return f.A * x + f.B; }
+__device__ __forceinline__ double apply(const MaxAff& f, double x) { return fmax(f.A * x + f.B, f.C); }
+
+__device__ __forceinline__ Aff shfl_up_map(const Aff& m, int d) {
+    return {__shfl_up_sync(kFullMask, m.A, d), __shfl_up_sync(kFullMask, m.B, d)};
+}
+__device__ __forceinline__ MaxAff shfl_down_map(const MaxAff& m, int d) {
+    return {__shfl_down_sync(kFullMask, m.A, d), __shfl_down_sync(kFullMask, m.B, d), __shfl_down_sync(kFullMask, m.C, d)};
+}
+
+template <int NPT, bool PROJ>
+__global__ void __launch_bounds__(kCnThreads, (NPT <= 8 ? 2 : 1)) cn_scan_kernel(CnArgs a) {
+    constexpr int NS = kCnThreads * NPT;  // padded node slots
+    extern __shared__ double sm[];
+    double* s_alpha = sm;                // [j * T + t] for node t*NPT + j
+    double* s_gamma = s_alpha + NS;
+    double* s_omb = s_gamma + NS;        // 1 - beta
+    double* s_rden = s_omb + NS;         // 1 / (1 + beta + alpha c'_{i-1})
+    double* s_seq = s_rden + NS;         // natural-order scratch (c' recurrence, closure, fallback back-substitution)
+    double* s_edgeL = s_seq + NS;        // first X of every thread
+    double* s_edgeR = s_edgeL + kCnThreads;
+    double* s_wmap = s_edgeR + kCnThreads;   // warp totals: up to 3 doubles per warp
+    double* s_misc = s_wmap + 3 * kCnWarps;  // [0] X_{N-1}, [1] flag: some R_i < 0 outside thread 0
+
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int n = a.n_space;
+    for (int64_t opt = blockIdx.x; opt < a.N; opt += gridDim.x) {
+        const double r = a.r[opt], q = a.q[opt], sg = a.sigma[opt], K = a.K[opt];
+        const double dS = grid_point(1, n, K) - grid_point(0, n, K);
+        double X[NPT], g[NPT];
+#pragma unroll
+        for (int j = 0; j < NPT; ++j) {
+            int i = t * NPT + j;
+            double S = grid_point(i < n ? i : n - 1, n, K);
+            g[j] = K - S;                         // payoff (applyConstraint, :106-107)
+            X[j] = (i < n) ? fmax(K - S, 0.0) : 0.0;   // setInitialCondition, :48-52
+        }
+        const int nsteps = a.n_steps[opt];
+        double dt_prev = -1.0;
+        for (int st = 0; st < nsteps; ++st) {
+            const double dt = a.dts[opt * a.max_steps + st];
+            if (dt != dt_prev) {
+                // ---- coefficients for this dt (setCoeff, :55-79) and the c' recurrence of the elimination
+                __syncthreads();
+#pragma unroll
+                for (int j = 0; j < NPT; ++j) {
+                    int i = t * NPT + j;
+                    double al = 0.0, be = 0.0, ga = 0.0;
+                    if (i < n - 1) {
+                        double S = grid_point(i, n, K);
+                        double aa = sg * S / dS;
+                        double m = (r - q) * S / dS;
+                        al = 0.25 * dt * (aa * aa - m);
+                        be = 0.5 * dt * (r + aa * aa);
+                        ga = 0.25 * dt * (aa * aa + m);
+                    }
+                    s_alpha[j * kCnThreads + t] = al;
+                    s_gamma[j * kCnThreads + t] = ga;
+                    s_omb[j * kCnThreads + t] = 1.0 - be;
+                    s_seq[i] = 1.0 + be;          // diagonal, natural order, for the sequential recurrence below
+                }
+                __syncthreads();
+                if (t == 0) {
+                    // den_i = (1+beta_i) - (-alpha_i)(c'_{i-1}),  c'_i = -gamma_i / den_i   (rows 0..N-2)
+                    double cp = 0.0;
+                    int neg = 0;
+                    for (int i = 0; i < n - 1; ++i) {
+                        int tt = i / NPT, jj = i - tt * NPT;
+                        double al = s_alpha[jj * kCnThreads + tt], ga = s_gamma[jj * kCnThreads + tt];
+                        double den = s_seq[i] + al * cp;
+                        double rd = 1.0 / den;
+                        s_rden[jj * kCnThreads + tt] = rd;
+                        cp = -ga * rd;
+                        if (ga * rd < 0.0 && tt > 0) neg = 1;
+                    }
+                    for (int i = n - 1; i < NS; ++i) {
+                        int tt = i / NPT, jj = i - tt * NPT;
+                        s_rden[jj * kCnThreads + tt] = 0.0;
+                    }
+                    s_misc[1] = (double)neg;
+                }
+                __syncthreads();
+                dt_prev = dt;
+            }
+            // ---- right-hand side b_i = alpha X_{i-1} + (1-beta) X_i + gamma X_{i+1}
+            s_edgeL[t] = X[0];
+            s_edgeR[t] = X[NPT - 1];
+            __syncthreads();
+            const double xl = (t > 0) ? s_edgeR[t - 1] : 0.0;
+            const double xr = (t < kCnThreads - 1) ? s_edgeL[t + 1] : 0.0;
+            double P[NPT], Q[NPT], R[NPT];
+#pragma unroll
+            for (int j = 0; j < NPT; ++j) {
+                const double al = s_alpha[j * kCnThreads + t], ga = s_gamma[j * kCnThreads + t];
+                const double ob = s_omb[j * kCnThreads + t], rd = s_rden[j * kCnThreads + t];
+                const double xm = (j == 0) ? xl : X[j - 1];
+                const double xp = (j == NPT - 1) ? xr : X[j + 1];
+                const double b = al * xm + ob * X[j] + ga * xp;
+                P[j] = b * rd;        // d'_i = P_i + Q_i d'_{i-1}
+                Q[j] = al * rd;
+                R[j] = ga * rd;       // X_i  = d'_i + R_i X_{i+1}
+            }
+            // ---- forward elimination as a prefix scan of affine maps
+            Aff loc = {1.0, 0.0};
+#pragma unroll
+            for (int j = 0; j < NPT; ++j) loc = compose(Aff{Q[j], P[j]}, loc);
+            Aff inc = loc;  // inclusive scan over lanes: inc_l = loc_l o ... o loc_0
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                Aff o = shfl_up_map(inc, d);
+                if (lane >= d) inc = compose(inc, o);
+            }
+            if (lane == 31) { s_wmap[2 * warp] = inc.A; s_wmap[2 * warp + 1] = inc.B; }
+            __syncthreads();
+            double din = 0.0;  // d' entering this warp
+            for (int w = 0; w < warp; ++w) din = s_wmap[2 * w] * din + s_wmap[2 * w + 1];
+            Aff exc = shfl_up_map(inc, 1);
+            double dprev = (lane == 0) ? din : apply(exc, din);
+            double D[NPT];
+#pragma unroll
+            for (int j = 0; j < NPT; ++j) {
+                dprev = Q[j] * dprev + P[j];
+                D[j] = dprev;
+            }
+            // ---- close the last row: X_{N-2}, X_{N-3}, X_{N-4} as affine functions of x = X_{N-1}
+#pragma unroll
+            for (int j = 0; j < NPT; ++j) {
+                int i = t * NPT + j;
+                if (i >= n - 4 && i <= n - 2) { s_seq[2 * (i - (n - 4))] = D[j]; s_seq[2 * (i - (n - 4)) + 1] = R[j]; }
+            }
+            __syncthreads();
+            if (t == 0) {
+                double p2 = s_seq[4], m2 = s_seq[5];
+                double p3 = s_seq[2] + s_seq[3] * p2, m3 = s_seq[3] * m2;
+                double p4 = s_seq[0] + s_seq[1] * p3, m4 = s_seq[1] * m3;
+                double x = (p4 - 4.0 * p3 + 5.0 * p2) / (2.0 - m4 + 4.0 * m3 - 5.0 * m2);
+                if (PROJ) x = fmax(x, K - 3.0 * K);
+                s_misc[0] = x;
+            }
+            __syncthreads();
+            const double xlast = s_misc[0];
+            const bool fallback = PROJ && s_misc[1] != 0.0;
+            if (!fallback) {
+                // ---- (projected) back-substitution as a suffix scan; padding nodes carry the identity map
+                double xin;
+                if (PROJ) {
+                    MaxAff locb = {1.0, 0.0, -1.79e308};
+#pragma unroll
+                    for (int j = NPT - 1; j >= 0; --j) {
+                        int i = t * NPT + j;
+                        if (i <= n - 2) locb = compose(MaxAff{R[j], D[j], g[j]}, locb);
+                    }
+                    MaxAff incb = locb;  // inclusive suffix scan: incb_l = locb_l o ... o locb_31
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) {
+                        MaxAff o = shfl_down_map(incb, d);
+                        if (lane + d < 32) incb = compose(incb, o);
+                    }
+                    if (lane == 0) { s_wmap[3 * warp] = incb.A; s_wmap[3 * warp + 1] = incb.B; s_wmap[3 * warp + 2] = incb.C; }
+                    __syncthreads();
+                    double v = xlast;
+                    for (int w = kCnWarps - 1; w > warp; --w) v = fmax(s_wmap[3 * w] * v + s_wmap[3 * w + 1], s_wmap[3 * w + 2]);
+                    MaxAff nxt = shfl_down_map(incb, 1);
+                    xin = (lane == 31) ? v : apply(nxt, v);
+                } else {
+                    Aff locb = {1.0, 0.0};
+#pragma unroll
+                    for (int j = NPT - 1; j >= 0; --j) {
+                        int i = t * NPT + j;
+                        if (i <= n - 2) locb = compose(Aff{R[j], D[j]}, locb);
+                    }
+                    Aff incb = locb;
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) {
+                        Aff o = {__shfl_down_sync(kFullMask, incb.A, d), __shfl_down_sync(kFullMask, incb.B, d)};
+                        if (lane + d < 32) incb = compose(incb, o);
+                    }
+                    if (lane == 0) { s_wmap[3 * warp] = incb.A; s_wmap[3 * warp + 1] = incb.B; }
+                    __syncthreads();
+                    double v = xlast;
+                    for (int w = kCnWarps - 1; w > warp; --w) v = s_wmap[3 * w] * v + s_wmap[3 * w + 1];
+                    Aff nxt = {__shfl_down_sync(kFullMask, incb.A, 1), __shfl_down_sync(kFullMask, incb.B, 1)};
+                    xin = (lane == 31) ? v : apply(nxt, v);
+                }
+#pragma unroll
+                for (int j = NPT - 1; j >= 0; --j) {
+                    int i = t * NPT + j;
+                    double xn;
+                    if (i <= n - 2) {
+                        xn = R[j] * xin + D[j];
+                        if (PROJ) xn = fmax(xn, g[j]);
+                    } else {
+                        xn = xin;   // i == n-1 holds X_{N-1}; slots beyond mirror it (never read back)
+                    }
+                    X[j] = xn;
+                    xin = xn;
+                }
+            } else {
+                // some R_i < 0 away from S = 0 (q >> r with tiny sigma): the max-affine maps are not monotone there,
+                // so this step falls back to a sequential projected back-substitution by one thread
+#pragma unroll
+                for (int j = 0; j < NPT; ++j) {
+                    int i = t * NPT + j;
+                    if (i <= n - 2) { s_seq[i] = D[j]; }
+                }
+                __syncthreads();
+                if (t == 0) {
+                    double x = xlast;
+                    s_seq[n - 1] = x;
+                    for (int i = n - 2; i >= 0; --i) {
+                        int tt = i / NPT, jj = i - tt * NPT;
+                        double Ri = s_gamma[jj * kCnThreads + tt] * s_rden[jj * kCnThreads + tt];
+                        x = fmax(Ri * x + s_seq[i], K - grid_point(i, n, K));
+                        s_seq[i] = x;
+                    }
+                }
+                __syncthreads();
+#pragma unroll
+                for (int j = 0; j < NPT; ++j) {
+                    int i = t * NPT + j;
+                    X[j] = s_seq[i < n ? i : n - 1];
+                }
+            }
+            __syncthreads();   // s_edge*, s_wmap, s_seq are reused by the next step
+        }
+        // ---- output: X (optional) and np.interp(S0, S, X) (:32-34)
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < NPT; ++j) {
+            int i = t * NPT + j;
+            if (i < n) {
+                s_seq[i] = X[j];
+                if (a.X_out) a.X_out[opt * n + i] = X[j];
+            }
+        }
+        __syncthreads();
+        if (t == 0) a.price[opt] = interp_uniform(a.S0[opt], n, K, [&](int i) { return s_seq[i]; });
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------- mode 1: the reference's SOR-then-project loop
+// One thread per option; arrays in global scratch laid out [node][option] so that neighbouring threads coalesce.
+__global__ void __launch_bounds__(64) cn_sor_kernel(CnArgs a) {
+    int64_t opt = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (opt >= a.N) return;
+    const int n = a.n_space;
+    const int64_t ld = a.N;
+    double* X = a.ws + opt;              // X[i] at X[i*ld]
+    double* b = X + (int64_t)n * ld;
+    double* lo = b + (int64_t)n * ld;
+    double* di = lo + (int64_t)n * ld;
+    double* up = di + (int64_t)n * ld;
+    double* xo = up + (int64_t)n * ld;
+    const double r = a.r[opt], q = a.q[opt], sg = a.sigma[opt], K = a.K[opt];
+    const double omega = a.omega;
+    for (int i = 0; i < n; ++i) X[i * ld] = fmax(K - grid_point(i, n, K), 0.0);
+    const double dS = grid_point(1, n, K) - grid_point(0, n, K);
+    const int nsteps = a.n_steps[opt];
+    for (int st = 0; st < nsteps; ++st) {
+        const double dt = a.dts[opt * a.max_steps + st];
+        for (int i = 0; i < n - 1; ++i) {
+            double S = grid_point(i, n, K);
+            double aa = sg * S / dS;
+            double alpha = 0.25 * dt * (aa * aa - (r - q) * S / dS);
+            double beta = 0.5 * dt * (r + aa * aa);
+            double gamma = 0.25 * dt * (aa * aa + (r - q) * S / dS);
+            if (i == 0) {
+                b[0] = X[0] * (1 - beta); lo[0] = 0; di[0] = 1 + beta; up[0] = 0;
+            } else {
+                b[i * ld] = alpha * X[(i - 1) * ld] + (1 - beta) * X[i * ld] + gamma * X[(i + 1) * ld];
+                lo[i * ld] = -alpha; di[i * ld] = 1 + beta; up[i * ld] = -gamma;
+            }
+        }
+        int it = 0;
+        double err = 1000.0;
+        while (err > a.tol && it < a.max_iter) {   // solvePSOR, :84-104
+            ++it;
+            for (int i = 0; i < n; ++i) xo[i * ld] = X[i * ld];
+            for (int k = 0; k < n - 1; ++k) {
+                double d = di[k * ld];
+                double xk = (1 - omega) * X[k * ld] + omega * b[k * ld] / d;
+                xk -= up[k * ld] * X[(k + 1) * ld] * omega / d;
+                xk -= lo[k * ld] * X[(k == 0 ? n - 1 : k - 1) * ld] * omega / d;   // k == 0 reads X[-1] with a zero coefficient
+                X[k * ld] = xk;
+            }
+            const int k = n - 2;   // the loop index leaks into the last-row update (:98)
+            X[(n - 1) * ld] = (1 - omega) * X[k * ld] + omega * b[k * ld] / di[k * ld];
+            const double lastc[4] = {-1.0, 4.0, -5.0, 2.0};
+            for (int jj = 0; jj < 4; ++jj) X[(n - 1) * ld] -= lastc[jj] * X[(n - 4 + jj) * ld] * omega / 2.0;
+            double ss = 0.0;
+            for (int i = 0; i < n; ++i) {
+                double v = fmax(X[i * ld], K - grid_point(i, n, K));   // applyConstraint on the whole vector
+                X[i * ld] = v;
+                double dd = xo[i * ld] - v;
+                ss += dd * dd;
+            }
+            err = sqrt(ss);
+        }
+    }
+    if (a.X_out) for (int i = 0; i < n; ++i) a.X_out[opt * n + i] = X[i * ld];
+    a.price[opt] = interp_uniform(a.S0[opt], n, K, [&](int i) { return X[i * ld]; });
+}
+
+template <int NPT, bool PROJ>
+static int launch_scan(const CnArgs& a, cudaStream_t st) {
+    constexpr int NS = kCnThreads * NPT;
+    size_t sm = sizeof(double) * (size_t)(5 * NS + 2 * kCnThreads + 3 * kCnWarps + 8);
+    FAOP_CUDA_OK(cudaFuncSetAttribute(cn_scan_kernel<NPT, PROJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    int64_t grid = a.N < (int64_t)kSMs * 8 ? a.N : (int64_t)kSMs * 8;
+    cn_scan_kernel<NPT, PROJ><<<(unsigned)grid, kCnThreads, sm, st>>>(a);
+    count_launch();
+    return launch_status();
+}
+
+template <bool PROJ>
+static int launch_scan_npt(const CnArgs& a, cudaStream_t st) {
+    int npt = (a.n_space + kCnThreads - 1) / kCnThreads;
+    if (npt <= 1) return launch_scan<1, PROJ>(a, st);
+    if (npt <= 2) return launch_scan<2, PROJ>(a, st);
+    if (npt <= 4) return launch_scan<4, PROJ>(a, st);
+    if (npt <= 8) return launch_scan<8, PROJ>(a, st);
+    if (npt <= 16) return launch_scan<16, PROJ>(a, st);
+    return FAOP_ERANGE;
+}
+
+}  // namespace faop
+
+using namespace faop;
+
 extern "C" {
-int faop_cn_workspace_bytes(int64_t N, int32_t n_space, int32_t mode, size_t* bytes) { if (bytes) *bytes = 0; return 0; }
+
+int faop_cn_workspace_bytes(int64_t N, int32_t n_space, int32_t mode, size_t* bytes) {
+    if (!bytes || N < 0 || n_space < 5) return FAOP_EINVAL;
+    *bytes = (mode == 1) ? sizeof(double) * 6 * (size_t)N * (size_t)n_space : 0;
+    return 0;
+}
+
 int faop_cn_put_batch(int64_t N, int32_t n_space, int32_t mode, const double* r, const double* q, const double* sigma,
                       const double* K, const double* S0, const double* dts, const int32_t* n_steps, int32_t max_steps,
                       double omega, double tol, int32_t max_iter, double* price, double* X_out, void* workspace,
-                      void* cuda_stream) { return FAOP_ERANGE; }
+                      void* cuda_stream) {
+    if (N < 0 || n_space < 5 || mode < 0 || mode > 2 || max_steps < 0) return FAOP_EINVAL;
+    if (n_space > kCnThreads * 16) return FAOP_ERANGE;
+    if (N == 0) return 0;
+    if (!r || !q || !sigma || !K || !S0 || !dts || !n_steps || !price) return FAOP_EINVAL;
+    if (mode == 1 && !workspace) return FAOP_EINVAL;
+    CnArgs a;
+    a.N = N; a.n_space = n_space; a.max_steps = max_steps; a.mode = mode; a.max_iter = max_iter;
+    a.r = r; a.q = q; a.sigma = sigma; a.K = K; a.S0 = S0; a.dts = dts; a.n_steps = n_steps;
+    a.omega = omega; a.tol = tol; a.price = price; a.X_out = X_out; a.ws = (double*)workspace;
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    if (mode == 1) {
+        cn_sor_kernel<<<(unsigned)((N + 63) / 64), 64, 0, st>>>(a);
+        count_launch();
+        return launch_status();
+    }
+    return mode == 2 ? launch_scan_npt<true>(a, st) : launch_scan_npt<false>(a, st);
 }
+
+}  // extern "C"
