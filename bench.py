@@ -253,9 +253,16 @@ def main():
                            "mean_iterations": iters_mean, "kernel": "auto" if args.kernel == 0 else "generic"},
                 "max_abs_err_vs_cpu_port": max_abs, "parity_sample": int(ok.sum()),
                 "roofline": {"bound": "fp64", "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s",
-                             "frac": achieved / tf_peak, "traffic": None,
+                             "frac": achieved / tf_peak,
+                             # dram__bytes_read+write of the dominant kernel, per launch: 153.5 B/option measured by
+                             # ncu --set full (profiles/r1_alo_fast_A12_ncu_full.csv) == the algorithmic 49 B in + 104 B seeds
+                             "traffic": 153.5 * Nopt if args.kernel == 0 else None,
+                             "kernel": "alo_fast_A12_kernel" if args.kernel == 0 else "alo_generic_kernel",
                              "kernel_ms": ms_kernel, "flops_per_option": fl,
-                             "peak_source": "DFMA microbenchmark measured in this run (faop_measure_fp64_peak); "
+                             "flop_model": "SURVEY 8d nominal: add/mul 1, FMA 2, div/sqrt 16, exp 40, log 56, Phi 120, phi 42 "
+                                           "at the realised mean iteration count",
+                             "executed_fp64_pipe_active_pct_ncu": 67.1 if args.kernel == 0 else None,
+                             "peak_source": "register-operand DFMA chains measured in this run (faop_measure_fp64_peak); "
                                             "MEASURED_PEAKS.json has no FP64 figure"},
                 "cpu_baseline": {"value": cpu_rate, "unit": UNIT, "cores": threads, "kind": "port",
                                  "sample": "first %d options of rank 0's batch, %.1f s, plain-C port of the reference "

@@ -359,3 +359,104 @@ def test_cn_projected_vs_oracle_and_spectral():
     s = CNOptionSolver(0.04, 0.04, 0.2, 100, 3.0)
     s.USE_PSOR = True
     assert abs(s.solve(80) - 23.209084798867803) <= 1e-9 and len(s.X) == 200 and s.S[-1] == 300.0
+
+
+def test_dropin_classes(capsys):
+    """The reference's own scripts, through the drop-in modules: testA.py, testB.py, test_QDplus.py, stage helpers."""
+    from fastamericanoptionpricing_b200.FastAmericanOptionSolverA import FastAmericanOptionSolverA, qd, np as np_reexport
+    from fastamericanoptionpricing_b200.FastAmericanOptionSolverB import FastAmericanOptionSolverB
+    from fastamericanoptionpricing_b200.EuropeanOptionSolver import EuropeanOption
+    from fastamericanoptionpricing_b200.ChebyshevInterpolation import ChebyshevInterpolation
+    assert np_reexport is np
+    g = load_golden("ref_c1_testA.npz")
+    # testA.py:7-21
+    solver = FastAmericanOptionSolverA(0.04, 0.01, 0.2, 100, 3, qd.OptionType.Put)
+    solver.use_derivative = False
+    solver.iter_tol = 1e-5
+    solver.max_iters = 20
+    price = solver.solve(0.0, 80)                                  # DEBUG defaults to True: prints like the reference
+    printed = capsys.readouterr().out
+    assert "step 5" in printed or "exercise boundary" in printed
+    assert abs(price - 21.135486471314067) <= PRICE_ABS_TOL and abs(solver.european_price - 17.78865238332743) <= 1e-12
+    assert solver.num_iters == 19 and abs(solver.error - 6.763708524497298e-06) <= 1e-12
+    assert np.max(np.abs(np.array(solver.shared_B) / g["B"][0] - 1)) <= BOUNDARY_REL_TOL
+    assert np.max(np.abs(np.array(solver.shared_B0) / g["B0"][0] - 1)) <= 1e-9
+    assert np.max(np.abs(np.array(solver.shared_tau) - g["tau"][0])) <= 1e-15
+    errs = np.array([e for _, e in solver.iter_records])
+    assert len(errs) == 19 and np.max(np.abs(errs / g["iter_errs"][0][:19] - 1)) <= 1e-6      # iter_records (Base.py:130)
+    assert abs(solver.check_value_match_condition2() - 0.0) < 1e-3
+    solver.DEBUG = False
+    solver.solve(0.0, 80)
+    assert len(solver.iter_records) == 38                          # accumulates across solves (SURVEY App. B#5)
+    # testB.py:4-18: call with q == 0 -> European shortcut, counters untouched
+    sb = FastAmericanOptionSolverB(0.04, 0.0, 0.2, 100, 3, qd.OptionType.Call)
+    sb.DEBUG = False
+    assert abs(sb.solve(0.0, 80) - 7.757100994706658) <= 1e-12 and sb.num_iters == 0 and sb.error == 1000000
+    # stage helpers against the reference's values on its own seed boundary
+    st = load_golden("ref_stage.npz")
+    for i in (0, 1, 12, 13):
+        cls = FastAmericanOptionSolverA if str(st["solver"][i]) == "A" else FastAmericanOptionSolverB
+        s_ = cls(float(st["in_r"][i]), float(st["in_q"][i]), float(st["in_sigma"][i]), float(st["in_K"][i]), float(st["in_T"][i]),
+                 qd.OptionType.Put if st["in_is_put"][i] else qd.OptionType.Call)
+        s_.DEBUG = False
+        s_.use_derivative = True
+        s_.set_collocation_points()
+        s_.set_initial_guess()
+        assert np.max(np.abs(np.array(s_.shared_B) / st["B"][i] - 1)) <= 1e-8
+        s_.shared_B = list(st["B"][i])
+        for node in (0, 5, 11):
+            tau_i, B_i = s_.shared_tau[node], s_.shared_B[node]
+            assert abs(s_.N_func(tau_i, B_i) / st["N"][i][node] - 1) <= 1e-10
+            assert abs(s_.D_func(tau_i, B_i) / st["D"][i][node] - 1) <= 1e-10
+            f, fp = s_.compute_f_and_fprime(tau_i, B_i)
+            assert abs(f / st["f"][i][node] - 1) <= 1e-10 and abs(fp - st["fp"][i][node]) <= 2e-8 * np.max(np.abs(st["fp"][i][:12]))
+        assert s_.compute_f_and_fprime(0, s_.shared_B[12]) == [s_.B_at_zero(), 1]
+        K, T = s_.K, s_.T
+        assert abs(s_.american_value_with_known_boundary(T, 0.8 * K, s_.r, s_.q, s_.sigma, K) - st["v"][i][0]) <= PRICE_ABS_TOL
+        assert abs(s_.american_value_with_known_boundary(0.5 * T, K, s_.r, s_.q, s_.sigma, K) - st["v"][i][3]) <= PRICE_ABS_TOL
+        assert abs(s_.check_value_match_condition2() - st["match2"][i]) <= 1e-9 * max(1.0, st["match2"][i])
+        Bn = s_.iterate_once(s_.shared_tau, s_.shared_B)
+        assert len(Bn) == 13 and Bn[12] == s_.B_at_zero()
+    # quadrature_sum with a host callable: the reference's DEBUG self-test integral of 2 u e^{u^2} (Base.py:78-86)
+    solver.set_collocation_points()
+    solver.set_initial_guess()
+    num = solver.quadrature_sum(solver.test_integrand, 3.0, 2, solver.quadrature_num)
+    assert abs(num - 8102.083927575384) <= 1e-8
+    # QDplus (test_QDplus.py:8-21), EuropeanOption, ChebyshevInterpolation
+    q = qd.QDplus(0.0975729097939295, 0.011804520625954162, 0.2, 105.61782314803582, qd.OptionType.Put)
+    assert abs(q.price(0.000870786986, 30.543317986992072) - 75.07450516104376) <= 1e-9
+    assert "err" in capsys.readouterr().out and abs(q.exercise_boundary - 104.2155098819196) <= 1e-7
+    F = q.exercise_boundary_func(np.linspace(1, 120, 7), 0.5)
+    assert F.shape == (7,) and q.exercise_boundary_func(3.0, 0) == 0
+    assert abs(EuropeanOption.european_put_value(3, 80, 0.04, 0.01, 0.2, 100) - 17.78865238332743) <= 1e-12
+    assert abs(EuropeanOption.european_call_value(3, 80, 0.04, 0.01, 0.2, 100) - 6.732251395492323) <= 1e-12
+    assert abs(EuropeanOption.european_option_theta(3, 80, 0.04, 0.01, 0.2, 100) - 0.3220660371928161) <= 1e-12
+    assert EuropeanOption.european_put_value(3, np.array([70.0, 80.0]), 0.04, 0.01, 0.2, 100).shape == (2,)
+    c = load_golden("ref_cheb.npz")
+    ci = ChebyshevInterpolation(c["n12_y"], lambda x, a, b: np.sqrt(4 * (x - a) / (b - a)) - 1, 0.0, 2.5)
+    assert np.max(np.abs(np.array(ci.a) - c["n12_a"])) <= 1e-14
+    assert np.max(np.abs(np.array(ci.value(c["n12_x"])) - c["n12_valx"])) <= 1e-13
+    assert np.array_equal(ChebyshevInterpolation.get_std_cheby_points(12), c["n12_nodes"])
+
+
+def test_surface_sweep_c5():
+    """Config 5: options decoded on the device from the flat index == the same options passed as arrays (bit-exact),
+    including chunking through a small workspace."""
+    cfg = AloConfig(**wl.C5_CFG)
+    surf = dict(K0=50.0, K1=150.0, T0=1.0 / 52, T1=3.0, V0=0.10, V1=0.60, S=100.0, r=0.04, q=0.01, nK=1000, nT=1000, nV=100)
+    for first, count in ((0, 5000), (49_999_000, 3000), (100_000_000 - 2500, 2500)):
+        b = wl.c5_surface(first, count)
+        ref = batch.price_batch(b["r"], b["q"], b["sigma"], b["K"], b["T"], b["S"], b["is_put"], cfg=cfg, want_boundary=False)
+        got, it = batch.surface_batch(surf, first, count, cfg, want_iters=True, workspace_mb=1)
+        assert torch.equal(got, ref["price"]) and torch.equal(it, ref["iters"])
+    assert torch.isfinite(got).all()
+
+
+def test_sharded_single_process():
+    """price_batch_sharded without a process group = plain pricing of the whole batch."""
+    from fastamericanoptionpricing_b200 import price_batch_sharded
+    b = wl.c2_batch(1000)
+    a = [b[k] for k in ("r", "q", "sigma", "K", "T", "S", "is_put")]
+    cfg = AloConfig(**wl.C2_CFG)
+    p, (lo, hi) = price_batch_sharded(*a, cfg=cfg)
+    assert (lo, hi) == (0, 1000) and torch.equal(p, batch.price_batch(*a, cfg=cfg)["price"])
