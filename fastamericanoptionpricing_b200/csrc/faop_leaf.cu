@@ -186,16 +186,14 @@ int launch_dev_math(int kind, int64_t N, const double* x, double* out, cudaStrea
     return launch_status();
 }
 
-// FP64 FMA-pipe peak: 8 independent DFMA chains per thread with all three operands in regular registers (a DFMA whose
-// multiplicand sits in a uniform register or immediate issues at only ~65-77 % of this rate on sm_100a, measured with
-// tools/dfma_peak.cu), 4096 rounds, 8 resident CTAs/SM.
+// FP64 FMA-pipe peak: 8 independent DFMA chains per thread, 4096 rounds, 8 resident CTAs/SM.  Multiplier and addend are
+// kernel parameters (uniform operands): on sm_100a a DFMA with at most two distinct 64-bit REGISTER sources retires at
+// 63.6 lanes/clk/SM (36.98 TFLOP/s at 1965 MHz), one with three distinct register sources at only 53-54 lanes/clk/SM
+// (register-file read bandwidth) - measured with tools/dfma_forms.cu, profiles/r1_dfma_operand_forms.txt.
 constexpr int kPeakIters = 4096;
 constexpr int kPeakChains = 8;
-__global__ void __launch_bounds__(256) fp64_peak_kernel(double* sink, const double* coef) {
+__global__ void __launch_bounds__(256) fp64_peak_kernel(double* sink, double m, double b) {
     double x[kPeakChains];
-    // opaque per-thread values: they live in regular registers; one multiplier and one addend shared by all chains keeps
-    // the operand-reuse cache hot (eight distinct addend registers cost ~15 % in register-bank conflicts)
-    const double m = coef[threadIdx.x & 1], b = coef[2 + (threadIdx.x & 1)];
 #pragma unroll
     for (int c = 0; c < kPeakChains; ++c) x[c] = 1.0 + c + threadIdx.x * 1e-9;
 #pragma unroll 1
@@ -260,20 +258,14 @@ int launch_cheb_eval(int64_t N, int n, int npts, const double* a, const double* 
 
 int launch_fp64_peak(int launches, double* tflops, double* ms_per_launch, cudaStream_t st) {
     double* buf = nullptr;
-    FAOP_CUDA_OK(cudaMalloc(&buf, 16 * sizeof(double)));
-    double h[16];
-    h[0] = 0.0;
-    for (int i = 1; i < 16; ++i) h[i] = 1e-7 * i;
-    h[1] = 0.999999; h[2] = 0.999998;
-    // layout: [0] sink, [1..2] multipliers, [3..10] addends
-    FAOP_CUDA_OK(cudaMemcpyAsync(buf, h, sizeof h, cudaMemcpyHostToDevice, st));
+    FAOP_CUDA_OK(cudaMalloc(&buf, sizeof(double)));
     cudaEvent_t e0, e1;
     FAOP_CUDA_OK(cudaEventCreate(&e0));
     FAOP_CUDA_OK(cudaEventCreate(&e1));
     const int blocks = kSMs * 8 * 4, threads = 256;  // 8 resident CTAs/SM x 4 waves
-    for (int w = 0; w < 2; ++w) { fp64_peak_kernel<<<blocks, threads, 0, st>>>(buf, buf + 1); count_launch(); }
+    for (int w = 0; w < 2; ++w) { fp64_peak_kernel<<<blocks, threads, 0, st>>>(buf, 0.999999, 1e-7); count_launch(); }
     FAOP_CUDA_OK(cudaEventRecord(e0, st));
-    for (int i = 0; i < launches; ++i) { fp64_peak_kernel<<<blocks, threads, 0, st>>>(buf, buf + 1); count_launch(); }
+    for (int i = 0; i < launches; ++i) { fp64_peak_kernel<<<blocks, threads, 0, st>>>(buf, 0.999999, 1e-7); count_launch(); }
     FAOP_CUDA_OK(cudaEventRecord(e1, st));
     FAOP_CUDA_OK(cudaEventSynchronize(e1));
     float ms = 0;
