@@ -13,12 +13,12 @@ class FastAmericanOptionSolverA(FastAmericanOptionSolver):
     _SOLVER = "A"
 
     def K12(self, tau, B):
-        """reference :24-25 — recovered from D = phi(d+)/(sigma sqrt tau) +- Phi(+-d+) + q K12"""
-        return self.quadrature_sum(self.K12_integrand, tau, B, self.quadrature_num)
+        """reference :24-25 — the quadrature runs in the CUDA evaluation kernel (faop_alo_eval_points_batch, I1)"""
+        return np.float64(self._eval([tau], [B])["I1"].item())
 
     def K3(self, tau, B):
-        """reference :34-35"""
-        return self.quadrature_sum(self.K3_integrand, tau, B, self.quadrature_num)
+        """reference :34-35 (I2 of the evaluation kernel)"""
+        return np.float64(self._eval([tau], [B])["I2"].item())
 
     def K12_integrand(self, tau, B_tau, u, B_u):
         """reference :27-32 (host scalar helper)"""

@@ -34,11 +34,13 @@ except Exception:  # matplotlib is optional here; plotting is outside the hot pa
 
 
 def _Phi(x):
-    return 0.5 * math.erfc(-x / math.sqrt(2.0))
+    """standard normal cdf of a scalar, evaluated by the device math (faop_dev_math_batch kind 4)"""
+    return float(_batch.dev_math_batch(4, [float(x)]).item())
 
 
 def _phi(x):
-    return math.exp(-0.5 * x * x) / math.sqrt(2.0 * math.pi)
+    """standard normal pdf of a scalar: exp on the device (kind 0)"""
+    return float(_batch.dev_math_batch(0, [-0.5 * float(x) * float(x)]).item()) / math.sqrt(2.0 * math.pi)
 
 
 class FastAmericanOptionSolver(ABC):

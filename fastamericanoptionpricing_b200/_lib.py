@@ -31,7 +31,7 @@ _SIGNATURES = {
     "faop_workspace_bytes": (ctypes.c_int, [_P(FaopCfg), c_i64, _P(c_sz)]),
     "faop_alo_price_batch": (ctypes.c_int, [_P(FaopCfg), c_i64] + [c_vp] * 19),
     "faop_alo_surface_batch": (ctypes.c_int, [_P(FaopCfg), _P(FaopSurface), c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
-    "faop_alo_eval_points_batch": (ctypes.c_int, [_P(FaopCfg), c_i64, c_i32] + [c_vp] * 18),
+    "faop_alo_eval_points_batch": (ctypes.c_int, [_P(FaopCfg), c_i64, c_i32] + [c_vp] * 20),
     "faop_alo_interp_boundary_batch": (ctypes.c_int, [_P(FaopCfg), c_i64, c_i32] + [c_vp] * 10),
     "faop_alo_price_known_boundary_batch": (ctypes.c_int, [_P(FaopCfg), c_i64] + [c_vp] * 13),
     "faop_qd_boundary_batch": (ctypes.c_int, [c_i64] + [c_vp] * 8),
@@ -57,11 +57,23 @@ class FaopError(RuntimeError):
     pass
 
 
+def _try_build():
+    """Compile csrc/ with nvcc when the shared library is absent and a CUDA toolkit is at hand (a fresh checkout);
+    failure is not masked — load() still raises if the library does not appear."""
+    import shutil
+    import subprocess
+    nvcc = shutil.which("nvcc") or ("/usr/local/cuda/bin/nvcc" if os.path.exists("/usr/local/cuda/bin/nvcc") else None)
+    if nvcc and shutil.which("make"):
+        subprocess.call(["make", "-s", "-j8", "-C", os.path.join(_HERE, "csrc"), "NVCC=" + nvcc])
+
+
 def load():
     """Load libfaop.so (once).  Raises FaopError if the CUDA extension has not been built."""
     global _lib
     if _lib is not None:
         return _lib
+    if not os.path.exists(LIB_PATH):
+        _try_build()
     if not os.path.exists(LIB_PATH):
         raise FaopError(
             "libfaop.so not found at %s — build it with `python -c 'import __graft_entry__ as g; g.build()'` "

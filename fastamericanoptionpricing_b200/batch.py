@@ -160,7 +160,8 @@ def collocation_tau(T, n):
 def eval_points_batch(B, tau_pts, B_pts, r, q, sigma, K, T, is_put, cfg: AloConfig = AloConfig(), device=None):
     """N_func, D_func, Nprime_func, Dprime_func, compute_f_and_fprime and the damped update at arbitrary
     (tau, Q) points (N x p) on a given boundary B (N x (n+1)); FastAmericanOptionSolverBase.py:144-165, 267-279.
-    Returns dict(N, D, Nprime, Dprime, f, fprime, Bnew), each N x p."""
+    Returns dict(N, D, Nprime, Dprime, f, fprime, Bnew, I1, I2), each N x p (I1, I2: the two quadrature integrals,
+    K12/K3 for Solver A, the D-/N-integrals for Solver B)."""
     lib = _lib.load()
     dev = _device(device)
     with torch.cuda.device(dev):
@@ -174,13 +175,13 @@ def eval_points_batch(B, tau_pts, B_pts, r, q, sigma, K, T, is_put, cfg: AloConf
         if tp.shape != bp.shape:
             raise ValueError("tau_pts and B_pts must have the same shape")
         p = tp.shape[1]
-        outs = [torch.empty((N, p), dtype=torch.float64, device=dev) for _ in range(7)]
+        outs = [torch.empty((N, p), dtype=torch.float64, device=dev) for _ in range(9)]
         tab = tables_for(cfg, dev)
         c = cfg.c()
         check(lib.faop_alo_eval_points_batch(ctypes.byref(c), N, p, _ptr(r), _ptr(q), _ptr(sigma), _ptr(K), _ptr(T),
                                              _ptr(is_put), _ptr(tab), _ptr(Bd), _ptr(tp), _ptr(bp),
                                              *[_ptr(o) for o in outs], _stream(dev)), "faop_alo_eval_points_batch")
-        return dict(zip(("N", "D", "Nprime", "Dprime", "f", "fprime", "Bnew"), outs))
+        return dict(zip(("N", "D", "Nprime", "Dprime", "f", "fprime", "Bnew", "I1", "I2"), outs))
 
 
 def eval_nodes_batch(B, r, q, sigma, K, T, is_put, cfg: AloConfig = AloConfig(), device=None):

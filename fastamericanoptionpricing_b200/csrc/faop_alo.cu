@@ -150,6 +150,7 @@ __global__ void __launch_bounds__(kGenWarps * 32) alo_eval_points_kernel(AloArgs
             const int64_t at = opt * a.npts + p;
             const double tau = a.pts_tau[at], Q = a.pts_B[at];
             NodeOut no;
+            double i1 = 0.0, i2 = 0.0;   // quadrature_sum returns 0 at tau == 0 (:382-383)
             if (tau == 0) {  // compute_f_and_fprime: tau == 0 -> [B_at_zero, 1]
                 no.Nv = no.Dv = no.Np = no.Dp = nan("");
                 no.f = o.X;
@@ -171,6 +172,8 @@ __global__ void __launch_bounds__(kGenWarps * 32) alo_eval_points_kernel(AloArgs
                 a2 = warp_sum(a2);
                 if (DERIV) { a3 = warp_sum(a3); a4 = warp_sum(a4); }
                 no = alo_node<SOLVER, DERIV>(o, c, Q, L, lnXK, o.K * exp(-tau * (o.r - o.q)), a1, a2, a3, a4);
+                i1 = c.tau * a1;
+                i2 = (SOLVER == 0) ? c.tau * c.cinv * kInvSqrt2Pi * a2 : c.tau * a2;
             }
             if (lane == 0) {
                 if (eo.Nv) eo.Nv[at] = no.Nv;
@@ -179,6 +182,8 @@ __global__ void __launch_bounds__(kGenWarps * 32) alo_eval_points_kernel(AloArgs
                 if (eo.Dp) eo.Dp[at] = no.Dp;
                 if (eo.f) eo.f[at] = no.f;
                 if (eo.fp) eo.fp[at] = no.fp;
+                if (eo.I1) eo.I1[at] = i1;
+                if (eo.I2) eo.I2[at] = i2;
                 if (eo.Bnew) {  // iterate_once_foreach_tau (:144-165)
                     double fp = DERIV ? no.fp : 0.0;
                     eo.Bnew[at] = (tau == 0) ? o.X : Q + a.cfg.eta * (Q - no.f) / (fp - 1.0);

@@ -180,7 +180,7 @@ int faop_alo_eval_points_batch(const faop_cfg* cfg, int64_t N, int32_t npts, con
                                const double* sigma, const double* K, const double* T, const uint8_t* is_put,
                                const void* tables_dev, const double* B, const double* pts_tau, const double* pts_B,
                                double* Nv, double* Dv, double* Np, double* Dp, double* f, double* fp, double* Bnew,
-                               void* cuda_stream) {
+                               double* I1, double* I2, void* cuda_stream) {
     AloArgs a;
     int rc = fill_args(a, cfg, N, r, q, sigma, K, T, nullptr, nullptr, is_put, tables_dev);
     if (rc) return rc;
@@ -189,7 +189,7 @@ int faop_alo_eval_points_batch(const faop_cfg* cfg, int64_t N, int32_t npts, con
     if (!B || !pts_tau || !pts_B) return FAOP_EINVAL;
     a.seeds_in = B;
     a.npts = npts; a.pts_tau = pts_tau; a.pts_B = pts_B;
-    EvalOut eo = {Nv, Dv, Np, Dp, f, fp, Bnew};
+    EvalOut eo = {Nv, Dv, Np, Dp, f, fp, Bnew, I1, I2};
     return launch_alo_eval_nodes(a, eo, (cudaStream_t)cuda_stream);
 }
 

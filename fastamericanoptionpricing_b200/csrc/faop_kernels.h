@@ -24,6 +24,7 @@ struct AloArgs {
 
 struct EvalOut {
     double *Nv, *Dv, *Np, *Dp, *f, *fp, *Bnew;
+    double *I1, *I2;   // the two quadrature integrals: A: K12, K3 (A.py:24-44); B: the D- and N-integrals (B.py:25-39)
 };
 
 int launch_qd_seed(const AloArgs& a, cudaStream_t st);

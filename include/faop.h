@@ -109,13 +109,15 @@ int faop_alo_surface_batch(const faop_cfg* cfg, const faop_surface* surf, int64_
  * FastAmericanOptionSolver.compute_f_and_fprime / N_func / D_func / Nprime_func / Dprime_func /
  * iterate_once_foreach_tau (FastAmericanOptionSolverBase.py:144-165, 267-279 and the A/B files).
  * pts_tau, pts_B and all outputs are N x npts (outputs nullable).  f' is the analytic derivative when
- * cfg->use_derivative, else 1 (as the reference returns); tau == 0 gives f = B_at_zero, f' = 1.       */
+ * cfg->use_derivative, else 1 (as the reference returns); tau == 0 gives f = B_at_zero, f' = 1.
+ * I1, I2 (nullable) are the two quadrature integrals themselves: Solver A K12 and K3 (FastAmericanOptionSolverA.py:24-44),
+ * Solver B the D- and N-integrals (FastAmericanOptionSolverB.py:25-39).                                              */
 int faop_alo_eval_points_batch(const faop_cfg* cfg, int64_t N, int32_t npts,
                                const double* r, const double* q, const double* sigma, const double* K,
                                const double* T, const uint8_t* is_put, const void* tables_dev,
                                const double* B, const double* pts_tau, const double* pts_B,
                                double* Nv, double* Dv, double* Np, double* Dp, double* f, double* fp,
-                               double* Bnew, void* cuda_stream);
+                               double* Bnew, double* I1, double* I2, void* cuda_stream);
 
 /* B(u) at `npts` arbitrary u per option from the Chebyshev interpolant of ln(B/X)^2:
  * compute_integration_terms (FastAmericanOptionSolverBase.py:167-195).  u, Bu are N x npts.         */

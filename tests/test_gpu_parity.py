@@ -410,6 +410,16 @@ def test_dropin_classes(capsys):
             assert abs(s_.D_func(tau_i, B_i) / st["D"][i][node] - 1) <= 1e-10
             f, fp = s_.compute_f_and_fprime(tau_i, B_i)
             assert abs(f / st["f"][i][node] - 1) <= 1e-10 and abs(fp - st["fp"][i][node]) <= 2e-8 * np.max(np.abs(st["fp"][i][:12]))
+        if str(st["solver"][i]) == "A":      # K12 / K3 (A.py:24-44) recovered from the reference's N and D at node 5
+            from scipy.stats import norm
+            tau_i, B_i = s_.shared_tau[5], s_.shared_B[5]
+            dp, dm = s_.dplus(tau_i, B_i / s_.K), s_.dminus(tau_i, B_i / s_.K)
+            svt = s_.sigma * np.sqrt(tau_i)
+            sign = 1.0 if st["in_is_put"][i] else -1.0
+            K12_ref = (st["D"][i][5] - norm.pdf(dp) / svt - sign * norm.cdf(sign * dp)) / s_.q
+            K3_ref = (st["N"][i][5] - norm.pdf(dm) / svt) / s_.r
+            assert abs(s_.K12(tau_i, B_i) / K12_ref - 1) <= 1e-8 and abs(s_.K3(tau_i, B_i) / K3_ref - 1) <= 1e-8
+            assert abs(s_.CDF_pos_dplus(tau_i, B_i / s_.K) - norm.cdf(dp)) <= 1e-14 and abs(s_.PDF_dminus(tau_i, B_i / s_.K) - norm.pdf(dm)) <= 1e-14
         assert s_.compute_f_and_fprime(0, s_.shared_B[12]) == [s_.B_at_zero(), 1]
         K, T = s_.K, s_.T
         assert abs(s_.american_value_with_known_boundary(T, 0.8 * K, s_.r, s_.q, s_.sigma, K) - st["v"][i][0]) <= PRICE_ABS_TOL
