@@ -2,31 +2,84 @@
 // (generic: any n <= 64, l, m <= 128, Solver A/B, with/without derivative), price integral.
 // Replaces FastAmericanOptionSolver.solve (FastAmericanOptionSolverBase.py:49-165) for a batch.
 #include "faop_alo.cuh"
+#include "faop_fastmath.cuh"
 #include "faop_kernels.h"
 
 namespace faop {
 
-// ---------------------------------------------------------------- QD seed: one thread per (option, node)
-// set_initial_guess (FastAmericanOptionSolverBase.py:258-265) -> QDplus.compute_exercise_boundary per node.
-// Thread index is node-major (idx = node * N + option): a warp works on one node of 32 consecutive options, so its lanes
-// take similar Newton iteration counts and the option parameters load coalesced.
-__global__ void __launch_bounds__(256) qd_seed_kernel(AloArgs a) {
-    const int nn = a.tl.n + 1;
-    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= a.N * nn) return;
-    int node = (int)(idx / a.N);
-    int64_t opt = idx - (int64_t)node * a.N;
-    double r = a.r[opt], q = a.q[opt], sg = a.sigma[opt], K = a.K[opt], T = a.T[opt];
-    bool put = a.is_put[opt] != 0;
-    double out;
-    if (q == 0 && !put) {
-        out = nan("");
-    } else {
-        double c = a.tables[a.tl.off_c + node];
-        double tau = (c + 1) * (c + 1) * T / 4;  // to_orig_point, FastAmericanOptionSolverBase.py:239-240
-        out = qd_boundary(tau, r, q, sg, K, put);
+// ---------------------------------------------------------------- QD seed: one thread per option
+// set_initial_guess (FastAmericanOptionSolverBase.py:258-265) -> QDplus.compute_exercise_boundary per node
+// (QDplusAmericanOptionSolver.py:69-76, residual :110-125).  The reference starts MINPACK hybr from x0 = K at every node;
+// here a thread walks its option's nodes from the smallest tau upwards and starts Newton at the previous node's root
+// (the QD residual has a single root, so the limit is the same; ~5 instead of ~8 evaluations per node), with the
+// fast exp / erfcx of faop_fastmath.cuh (their 1e-14 relative error moves the root by the same order).
+FAOP_D double seed_cdf(double x, double E) {  // Phi(x) from E = exp(-x^2/2)
+    double xa[1] = {fabs(x) * kInvSqrt2}, G[1];
+    half_erfcx_n<1, false>(xa, G);
+    double ec = E * G[0];
+    return (x <= 0.0) ? ec : 1.0 - ec;
+}
+
+__global__ void __launch_bounds__(128) qd_seed_kernel(AloArgs a) {
+    const int n = a.tl.n, nn = n + 1;
+    int64_t opt = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (opt >= a.N) return;
+    const double r = a.r[opt], q = a.q[opt], sg = a.sigma[opt], K = a.K[opt], T = a.T[opt];
+    const bool put = a.is_put[opt] != 0;
+    double* out = a.seeds_out + opt * nn;
+    if (q == 0 && !put) {  // European shortcut: no boundary is solved
+        for (int j = 0; j <= n; ++j) out[j] = nan("");
+        return;
     }
-    a.seeds_out[opt * nn + node] = out;
+    const double s2 = sg * sg;
+    const double Nn1 = 2 * (r - q) / s2 - 1.0, M4 = 4.0 * (2 * r / s2), invK = 1.0 / K;
+    double S = K;   // x0 = K for the first (smallest-tau) node, QDplusAmericanOptionSolver.py:73
+    for (int j = n; j >= 0; --j) {
+        const double c = a.tables[a.tl.off_c + j];
+        const double tau = (c + 1) * (c + 1) * T / 4;  // to_orig_point, FastAmericanOptionSolverBase.py:239-240
+        if (tau == 0) {
+            out[j] = b_at_zero(r, q, K, put);
+            continue;
+        }
+        double ee[2] = {-r * tau, -q * tau}, ed[2];
+        fast_exp_n<2, false>(ee, ed);
+        const double dr = ed[0], dq = ed[1];
+        const double h = 1.0 - dr;
+        const double disc = sqrt(Nn1 * Nn1 + M4 / h);
+        const double qQD = put ? -0.5 * Nn1 - 0.5 * disc : -0.5 * Nn1 + 0.5 * disc;   // :127-134
+        const double svt = sg * sqrt(tau), rsvt = 1.0 / svt, drift = (r - q) * tau;
+        double prev = 1.79e308;
+        for (int it = 0; it < 100; ++it) {
+            const double d1 = (log(S * invK) + drift) * rsvt + 0.5 * svt;
+            const double d2 = d1 - svt;
+            double ex[2] = {-0.5 * d1 * d1, -0.5 * d2 * d2}, E[2];
+            fast_exp_n<2, false>(ex, E);
+            double F, dF;
+            if (put) {
+                const double P1 = seed_cdf(-d1, E[0]), P2 = seed_cdf(-d2, E[1]);
+                const double p = K * dr * P2 - S * dq * P1;
+                const double g = 1 - dq * P1;
+                F = g * S + qQD * (K - S - p);                                   // :124
+                dF = (1 - qQD) * g + dq * E[0] * kInvSqrt2Pi * rsvt;             // :207-208
+            } else {
+                const double P1 = seed_cdf(d1, E[0]), P2 = seed_cdf(d2, E[1]);
+                const double cv = S * dq * P1 - K * dr * P2;
+                const double g = 1 - dq * P1;
+                F = g * S - qQD * (S - K - cv);                                  // :122
+                dF = (1 - qQD) * g - dq * E[0] * kInvSqrt2Pi * rsvt;
+            }
+            double Sn = S - F / dF;
+            if (!(Sn > 0) || !(Sn < 1.79e308)) Sn = 0.5 * S;
+            if (Sn > 2.0 * S) Sn = 2.0 * S;
+            const double d = fabs(Sn - S);
+            // converged (the next Newton step would be ~d^2), or stalled at the rounding floor of a flat residual
+            const bool done = d <= 1e-10 * fabs(Sn) || (d >= 0.5 * prev && prev <= 1e-7 * fabs(Sn));
+            prev = d;
+            S = Sn;
+            if (done) break;
+        }
+        out[j] = S;
+    }
 }
 
 // One Jacobi sweep's quadrature: for every active node i the reduced sums s1..s4 land in shared memory.
@@ -256,10 +309,9 @@ static size_t generic_smem(const TableLayout& tl) {
 }
 
 int launch_qd_seed(const AloArgs& a, cudaStream_t st) {
-    int64_t total = a.N * (a.tl.n + 1);
-    if (total == 0) return 0;
-    int64_t blocks = (total + 255) / 256;
-    qd_seed_kernel<<<(unsigned)blocks, 256, 0, st>>>(a);
+    if (a.N == 0) return 0;
+    int64_t blocks = (a.N + 127) / 128;
+    qd_seed_kernel<<<(unsigned)blocks, 128, 0, st>>>(a);
     count_launch();
     return launch_status();
 }

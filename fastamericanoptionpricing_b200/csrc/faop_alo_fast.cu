@@ -40,42 +40,28 @@ struct FastWarpSmem {
     double tau[16], disc[16];
     double sN[16], sD[16];
     double par[8];   // X, 1/X, ln(X/K)
+    double red[8 * 36];   // transpose buffer of the per-group reduction, row pitch 36 = 4 (mod 16): conflict-free both ways
 };
 
 struct FastSmem {
     // followed in dynamic shared memory by: small tables (tl.small doubles), M (NC*NN*32 doubles), FastWarpSmem[kFastWarps]
 };
 
-// Reduce 8 per-lane values over the 32 lanes with a transposing butterfly.  On return every lane of the 4-lane group
-// g = lane >> 2 holds the total of value index g in v[0].
-FAOP_D double transpose_reduce8(double (&v)[8], int lane) {
-    {   // xor 16: keep 4
-        const bool up = lane & 16;
+// Reduce 8 per-lane values over the 32 lanes through a shared-memory transpose: every lane stores its 8 partial sums
+// (row v, column lane), then lane l sums the 8 entries {l&3, (l&3)+4, ...} of row v = l>>2 and two xor-shuffles finish
+// the row.  On return every lane of the 4-lane group l>>2 holds the total of value index l>>2.  Costs 8 STS + 8 LDS +
+// 9 DADD + 2 shuffles per 4 nodes, about half the issue slots of the select-and-shuffle butterfly it replaces.
+FAOP_D double transpose_reduce8(const double (&v)[8], double* red, int lane) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            double send = up ? v[j] : v[j + 4];
-            double keep = up ? v[j + 4] : v[j];
-            v[j] = keep + __shfl_xor_sync(kFull, send, 16);
-        }
-    }
-    {   // xor 8: keep 2
-        const bool up = lane & 8;
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-            double send = up ? v[j] : v[j + 2];
-            double keep = up ? v[j + 2] : v[j];
-            v[j] = keep + __shfl_xor_sync(kFull, send, 8);
-        }
-    }
-    {   // xor 4: keep 1
-        const bool up = lane & 4;
-        double send = up ? v[0] : v[1];
-        double keep = up ? v[1] : v[0];
-        v[0] = keep + __shfl_xor_sync(kFull, send, 4);
-    }
-    v[0] += __shfl_xor_sync(kFull, v[0], 2);
-    v[0] += __shfl_xor_sync(kFull, v[0], 1);
-    return v[0];
+    for (int k = 0; k < 8; ++k) red[k * 36 + lane] = v[k];
+    __syncwarp();
+    const double* row = red + (lane >> 2) * 36 + (lane & 3);
+    double s0 = row[0] + row[4], s1 = row[8] + row[12], s2 = row[16] + row[20], s3 = row[24] + row[28];
+    double t = (s0 + s1) + (s2 + s3);
+    t += __shfl_xor_sync(kFull, t, 1);
+    t += __shfl_xor_sync(kFull, t, 2);
+    __syncwarp();   // the buffer is rewritten by the next group
+    return t;
 }
 
 template <int kFastWarps>
@@ -226,7 +212,7 @@ __global__ void __launch_bounds__(kFastWarps * 32, 1) alo_fast_A12_kernel(AloArg
                             acc[4 * pr + 2 * p + 1] = fma(cisw[p], E[2 * p], wh * cdf);  // -> K12 = tau * sum
                         }
                     }
-                    const double tot = transpose_reduce8(acc, lane);
+                    const double tot = transpose_reduce8(acc, ws.red, lane);
                     // lanes 8 ii .. 8 ii + 3 hold the K3 sum of node grp*4+ii, lanes 8 ii + 4 .. 8 ii + 7 its K12 sum
                     if ((lane & 3) == 0) {
                         const int node = grp * kGroup + (lane >> 3);
@@ -287,7 +273,7 @@ static int launch_fast_t(const AloArgs& a, cudaStream_t st) {
     return launch_status();
 }
 
-// cfg.kernel: 0 = default (16 warps/CTA, <= 128 registers/thread); tuning variants 2 / 3 / 4 = 12 / 20 / 24 warps per CTA
+// cfg.kernel: 0 = default (16 warps/CTA, <= 128 registers/thread); tuning variants 2 / 3 = 12 / 20 warps per CTA
 int launch_alo_fast(const AloArgs& a, cudaStream_t st) {
     const bool match = a.cfg.solver == 0 && !a.cfg.use_derivative && a.tl.n == NC && a.tl.LP == 32 && a.tl.has_matrix &&
                        a.iter_errs == nullptr;
@@ -295,7 +281,6 @@ int launch_alo_fast(const AloArgs& a, cudaStream_t st) {
     if (a.N == 0) return 0;
     if (a.cfg.kernel == 2) return launch_fast_t<12>(a, st);
     if (a.cfg.kernel == 3) return launch_fast_t<20>(a, st);
-    if (a.cfg.kernel == 4) return launch_fast_t<24>(a, st);
     return launch_fast_t<16>(a, st);
 }
 
