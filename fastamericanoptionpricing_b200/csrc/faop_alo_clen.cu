@@ -1,0 +1,286 @@
+// faop_alo_clen.cu — specialised boundary + price kernel for the configurations whose interpolation matrix does not fit
+// in shared memory: Solver A or B without derivative, n <= 28 collocation nodes (n a multiple of 4), l <= 64 quadrature
+// points.  BASELINE.json configs[2] (C3: FastAmericanOptionSolverB, n = 24, l = 64, m = 128) runs here.
+//
+// Same structure as faop_alo_fast.cu (one option per warp, lane = quadrature index, 4 nodes per shared-memory transpose
+// reduction, fast exp / erfcx / sqrt with constant-bank coefficients), except that
+//   * H(u) is evaluated by Clenshaw from the DCT-I coefficients a_k of the current iterate (refitted once per iteration
+//     by lanes 0..n, ChebyshevInterpolation.py:43-51), read from shared memory as broadcast loads;
+//   * two point slots advance in lock step: with l > 32 (PPL = 2) the lane's two quadrature points k and k+32 of one
+//     node, with l <= 32 (PPL = 1) the points of two consecutive nodes;
+//   * e^{qu}, e^{ru} are recomputed per point (no room to keep n*l of them per warp).
+// Solver B per point: E+ = exp(qu - d+^2/2), E- = exp(ru - d-^2/2), e^{qu}, e^{ru}, erfcx(|d+|/sqrt2)/2, erfcx(|d-|/sqrt2)/2
+//   D-sum += w h e^{qu} Phi(om d+),  N-sum += w h e^{ru} Phi(om d-)           (FastAmericanOptionSolverB.py:25-39)
+#include "faop_alo_fast.cuh"
+#include "faop_kernels.h"
+
+namespace faop {
+
+constexpr int kClenWarps = 16;
+constexpr int kClenMaxNodes = 32;   // n + 1 <= 32: one lane per node in the closing pass
+
+struct ClenWarpSmem {
+    NodePack node[kClenMaxNodes];
+    double B[kClenMaxNodes], L[kClenMaxNodes], H[kClenMaxNodes], A[kClenMaxNodes];
+    double tau[kClenMaxNodes], disc[kClenMaxNodes], opc[kClenMaxNodes];
+    double sN[kClenMaxNodes], sD[kClenMaxNodes];
+    double par[8];
+    double red[8 * 36];
+};
+
+// Two Clenshaw recurrences in lock step (ChebyshevInterpolation.py:31-41), coefficients broadcast from shared memory.
+FAOP_D void clenshaw2(int n, const double* A, const double (&z)[2], double (&out)[2]) {
+    double b0[2], b1[2] = {0.0, 0.0}, b2[2] = {0.0, 0.0};
+    const double an = A[n] * 0.5;
+    const double z2[2] = {2.0 * z[0], 2.0 * z[1]};
+    b0[0] = an;
+    b0[1] = an;
+#pragma unroll 4
+    for (int k = n - 1; k >= 0; --k) {
+        const double ak = A[k];
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            b2[c] = b1[c];
+            b1[c] = b0[c];
+            b0[c] = fma(z2[c], b1[c], ak - b2[c]);
+        }
+    }
+    out[0] = 0.5 * (b0[0] - b2[0]);
+    out[1] = 0.5 * (b0[1] - b2[1]);
+}
+
+template <int SOLVER, int PPL>
+__global__ void __launch_bounds__(kClenWarps * 32, 1) alo_clen_kernel(AloArgs a) {
+    extern __shared__ double smem[];
+    const TableLayout tl = a.tl;
+    const int n = tl.n, nn = n + 1;
+    ClenWarpSmem* s_w = reinterpret_cast<ClenWarpSmem*>(smem + tl.small);
+    stage_tables(smem, a.tables, tl.small);
+    const CtaTables tb(smem, tl);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    ClenWarpSmem& ws = s_w[warp];
+
+    // lane constants of the l-point rule: PPL quadrature points per lane
+    double h[PPL], rh[PPL], sgk[PPL], g[PPL], wh[PPL];
+#pragma unroll
+    for (int p = 0; p < PPL; ++p) {
+        const int k = lane + 32 * p;
+        h[p] = tb.hl[k]; rh[p] = tb.rhl[k]; sgk[p] = tb.sgl[k];
+        g[p] = sgk[p] * sgk[p];
+        wh[p] = tb.wl[k] * h[p];
+    }
+    WarpSmem gw(ws.B, kClenMaxNodes);
+    gw.B = ws.B; gw.L = ws.L; gw.H = ws.H; gw.A = ws.A;
+
+    const int64_t stride = (int64_t)gridDim.x * kClenWarps;
+    for (int64_t opt = (int64_t)blockIdx.x * kClenWarps + warp; opt < a.N; opt += stride) {
+        double om, oq, orr;
+        int sgn;
+        bool degenerate;
+        {
+            const Opt o = load_option(a, opt);
+            if (o.q == 0 && !o.put) {  // European shortcut, FastAmericanOptionSolverBase.py:50-53
+                double e = euro_value(o.T - o.t, o.S, o.r, o.q, o.sg, o.K, false);
+                if (lane == 0) {
+                    a.price[opt] = e;
+                    if (a.european) a.european[opt] = e;
+                    if (a.iters) a.iters[opt] = 0;
+                    if (a.err) a.err[opt] = 1e6;
+                }
+                if (a.B && lane < nn) a.B[opt * nn + lane] = nan("");
+                continue;
+            }
+            if (lane < nn) {
+                const double c = tb.c[lane];
+                const double tau = (c + 1) * (c + 1) * o.T / 4;   // to_orig_point, FastAmericanOptionSolverBase.py:239-240
+                ws.tau[lane] = tau;
+                ws.opc[lane] = 1.0 + c;
+                ws.node[lane] = make_node_pack(o, tau);
+                ws.disc[lane] = o.K * exp(-tau * (o.r - o.q));
+                ws.B[lane] = (lane == n) ? o.X : a.seeds_in[opt * nn + lane];   // tau = 0 node pinned to X (see faop_alo_fast.cu)
+            }
+            if (lane == 0) {
+                ws.par[0] = o.X;
+                ws.par[1] = 1.0 / o.X;
+                ws.par[2] = log(o.X / o.K);
+            }
+            om = o.om; oq = o.q; orr = o.r;
+            sgn = o.put ? 0 : (int)0x80000000;
+            degenerate = !(o.T > 0);
+        }
+        __syncwarp();
+
+        int count = 0;
+        double err = 1.0;
+        while (err > a.cfg.iter_tol && count < a.cfg.max_iters) {
+            ++count;
+            // ---- L_j, H_j and the DCT-I fit a_k = (2/n) sum'' H_j cos(j k pi/n)
+            if (lane < nn) {
+                const double L = (lane == n) ? 0.0 : log(ws.B[lane] * ws.par[1]);
+                ws.L[lane] = L;
+                ws.node[lane].L = L;
+                ws.H[lane] = L * L;
+            }
+            __syncwarp();
+            if (lane < nn) {
+                double ans = 0.0;
+                int idx = 0;
+                const int n2 = 2 * n;
+                for (int j = 0; j <= n; ++j) {
+                    double term = ws.H[j] * tb.cs[idx];
+                    if (j == 0 || j == n) term *= 0.5;
+                    ans += term;
+                    idx += lane;
+                    if (idx >= n2) idx -= n2;
+                }
+                ws.A[lane] = ans * (2.0 / n);
+            }
+            __syncwarp();
+
+            if (!degenerate) {
+#pragma unroll 1
+                for (int grp = 0; grp < n / 4; ++grp) {
+                    double acc[8];
+#pragma unroll
+                    for (int k8 = 0; k8 < 8; ++k8) acc[k8] = 0.0;
+                    // slot pairs: PPL == 2 -> (node, k) and (node, k+32); PPL == 1 -> (node, k) and (node+1, k)
+#pragma unroll
+                    for (int pr = 0; pr < (PPL == 2 ? 4 : 2); ++pr) {
+                        int nd_i[2];
+                        double hh[2], rhh[2], gg[2], whh[2], z[2];
+#pragma unroll
+                        for (int c = 0; c < 2; ++c) {
+                            nd_i[c] = (PPL == 2) ? grp * 4 + pr : grp * 4 + 2 * pr + c;
+                            const int p = (PPL == 2) ? c : 0;
+                            hh[c] = h[p]; rhh[c] = rh[p]; gg[c] = g[p]; whh[c] = wh[p];
+                            z[c] = fma(ws.opc[nd_i[c]], sgk[p], -1.0);   // to_cheby_point(u_ik) = (1+c_i) sqrt(g_k) - 1
+                        }
+                        double Hu[2], root[2];
+                        clenshaw2(n, ws.A, z, Hu);
+                        sqrt_clamped_n<2>(Hu, root);
+                        double ex[8], xa[4], xs[4];
+#pragma unroll
+                        for (int c = 0; c < 2; ++c) {
+                            const NodePack& nd = ws.node[nd_i[c]];
+                            const double lnz = fma(om, root[c], nd.L);
+                            const double xp = fma(lnz, nd.cinv2 * rhh[c], nd.apc2 * hh[c]);   // d+ / sqrt2
+                            const double xm = fma(-nd.ssu2, hh[c], xp);                        // d- / sqrt2
+                            const double aq = nd.qtau * gg[c], ar = nd.rtau * gg[c];           // q u, r u
+                            ex[4 * c] = fma(-xp, xp, aq);
+                            ex[4 * c + 1] = fma(-xm, xm, ar);
+                            ex[4 * c + 2] = aq;
+                            ex[4 * c + 3] = ar;
+                            xs[2 * c] = xp; xs[2 * c + 1] = xm;
+                            xa[2 * c] = fabs(xp); xa[2 * c + 1] = fabs(xm);
+                        }
+                        double E[8], G[4];
+                        if (SOLVER == 0) {
+                            // Solver A needs e^{qu} but not e^{ru}, and one erfcx: reuse the B layout, skip the spare chains
+                            double ex6[6] = {ex[0], ex[1], ex[2], ex[4], ex[5], ex[6]}, E6[6];
+                            fast_exp_n<6, true>(ex6, E6);
+                            E[0] = E6[0]; E[1] = E6[1]; E[2] = E6[2]; E[4] = E6[3]; E[5] = E6[4]; E[6] = E6[5];
+                            double xa2[2] = {xa[0], xa[2]}, G2[2];
+                            half_erfcx_n<2, true>(xa2, G2);
+                            G[0] = G2[0]; G[2] = G2[1];
+                        } else {
+                            fast_exp_n<8, true>(ex, E);
+                            half_erfcx_n<4, true>(xa, G);
+                        }
+#pragma unroll
+                        for (int c = 0; c < 2; ++c) {
+                            const int slot = (PPL == 2) ? pr : 2 * pr + c;   // node index within the group
+                            const double wk = whh[c] * rhh[c];               // w_k
+                            if (SOLVER == 0) {
+                                // K12 += w h [+-e^{qu}Phi(+-d+)] + cis w e^{qu}phi(d+) sqrt(2pi);  K3 += w e^{ru}phi(d-) sqrt(2pi)
+                                const double ec = E[4 * c] * G[2 * c];
+                                const bool neg = (__double2hiint(xs[2 * c]) ^ sgn) < 0;
+                                double cdf = neg ? ec : E[4 * c + 2] - ec;
+                                cdf = __hiloint2double(__double2hiint(cdf) ^ sgn, __double2loint(cdf));
+                                acc[2 * slot] = fma(wk, E[4 * c + 1], acc[2 * slot]);
+                                acc[2 * slot + 1] = fma(ws.node[nd_i[c]].cis * wk, E[4 * c], fma(whh[c], cdf, acc[2 * slot + 1]));
+                            } else {
+                                // put: Phi(+d), call: Phi(-d)  ->  Phi(om d)
+                                const double ecp = E[4 * c] * G[2 * c], ecm = E[4 * c + 1] * G[2 * c + 1];
+                                const bool negp = (__double2hiint(xs[2 * c]) ^ sgn) < 0;
+                                const bool negm = (__double2hiint(xs[2 * c + 1]) ^ sgn) < 0;
+                                const double cdfp = negp ? ecp : E[4 * c + 2] - ecp;   // e^{qu} Phi(om d+)
+                                const double cdfm = negm ? ecm : E[4 * c + 3] - ecm;   // e^{ru} Phi(om d-)
+                                acc[2 * slot] = fma(whh[c], cdfm, acc[2 * slot]);          // -> N integral
+                                acc[2 * slot + 1] = fma(whh[c], cdfp, acc[2 * slot + 1]);  // -> D integral
+                            }
+                        }
+                    }
+                    const double tot = transpose_reduce8(acc, ws.red, lane);
+                    if ((lane & 3) == 0) {
+                        const int node = grp * 4 + (lane >> 3);
+                        if (lane & 4) ws.sD[node] = tot; else ws.sN[node] = tot;
+                    }
+                }
+            }
+            __syncwarp();
+            // ---- close N, D, f and the damped update at the nodes (lanes 0..n)
+            double dd = 0.0;
+            if (lane < nn) {
+                const double Bj = ws.B[lane];
+                double Bn;
+                const double tau = ws.tau[lane];
+                if (tau == 0) {
+                    Bn = ws.par[0];
+                } else {
+                    const NodePack nd = ws.node[lane];
+                    const double LK = nd.L + ws.par[2];
+                    const double xpK = fma(LK, nd.cinv2, nd.apc2);
+                    const double xmK = xpK - nd.ssu2;
+                    const double Ep = fast_exp(-xpK * xpK), Em = fast_exp(-xmK * xmK);
+                    double Nv, Dv;
+                    if (SOLVER == 0) {
+                        Nv = Em * nd.cis + orr * (tau * nd.cis * ws.sN[lane]);                                            // A.py:5-10
+                        Dv = Ep * nd.cis + om * fast_half_erfcx_cdf(om * xpK, Ep) + oq * (tau * ws.sD[lane]);             // A.py:13-19
+                    } else {
+                        Nv = fast_half_erfcx_cdf(om * xmK, Em) + orr * (tau * ws.sN[lane]);                               // B.py:5-13
+                        Dv = fast_half_erfcx_cdf(om * xpK, Ep) + oq * (tau * ws.sD[lane]);                                // B.py:15-23
+                    }
+                    const double f = ws.disc[lane] * Nv / Dv;
+                    Bn = Bj + a.cfg.eta * (Bj - f) / (0.0 - 1.0);
+                }
+                dd = fabs(Bj - Bn);
+                ws.B[lane] = Bn;
+            }
+            err = sqrt(warp_sum(dd * dd));
+            __syncwarp();
+        }
+        if (a.B && lane < nn) a.B[opt * nn + lane] = ws.B[lane];
+        double eur;
+        const Opt o = load_option(a, opt);
+        const double v = price_integral(gw, tb, tl, o, lane, &eur);
+        if (lane == 0) {
+            a.price[opt] = v;
+            if (a.european) a.european[opt] = eur;
+            if (a.iters) a.iters[opt] = count;
+            if (a.err) a.err[opt] = err;
+        }
+        __syncwarp();
+    }
+}
+
+template <int SOLVER, int PPL>
+static int launch_clen_t(const AloArgs& a, cudaStream_t st) {
+    const size_t sm = sizeof(double) * (size_t)a.tl.small + sizeof(ClenWarpSmem) * kClenWarps;
+    FAOP_CUDA_OK(cudaFuncSetAttribute(alo_clen_kernel<SOLVER, PPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    int64_t ctas = (a.N + kClenWarps - 1) / kClenWarps;
+    int grid = (int)(ctas < kSMs ? ctas : kSMs);
+    alo_clen_kernel<SOLVER, PPL><<<grid, kClenWarps * 32, sm, st>>>(a);
+    count_launch();
+    return launch_status();
+}
+
+int launch_alo_clen(const AloArgs& a, cudaStream_t st) {
+    const int n = a.tl.n;
+    const bool match = !a.cfg.use_derivative && n % 4 == 0 && n + 1 <= kClenMaxNodes && a.tl.LP <= 64 && a.iter_errs == nullptr;
+    if (!match) return -1000;
+    if (a.N == 0) return 0;
+    if (a.cfg.solver == 0) return a.tl.LP == 64 ? launch_clen_t<0, 2>(a, st) : launch_clen_t<0, 1>(a, st);
+    return a.tl.LP == 64 ? launch_clen_t<1, 2>(a, st) : launch_clen_t<1, 1>(a, st);
+}
+
+}  // namespace faop

@@ -142,6 +142,8 @@ int faop_alo_price_batch(const faop_cfg* cfg, int64_t N, const double* r, const 
     if (cfg->kernel != 1 && !iter_errs) {  // the per-iteration error history is a generic-kernel feature
         rc = launch_alo_fast(a, st);
         if (rc != -1000) return rc;
+        rc = launch_alo_clen(a, st);
+        if (rc != -1000) return rc;
     }
     return launch_alo_generic(a, st);
 }

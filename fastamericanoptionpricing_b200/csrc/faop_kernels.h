@@ -34,6 +34,8 @@ int launch_alo_price_known(const AloArgs& a, cudaStream_t st);
 int launch_alo_interp(const AloArgs& a, double* Bu, cudaStream_t st);
 // specialised kernels (faop_alo_fast.cu); returns -1000 when no specialisation matches the config
 int launch_alo_fast(const AloArgs& a, cudaStream_t st);
+// Clenshaw-based specialised kernels (faop_alo_clen.cu): Solver A/B, no derivative, n % 4 == 0, n <= 28, l <= 64
+int launch_alo_clen(const AloArgs& a, cudaStream_t st);
 
 int launch_qd_boundary(int64_t N, const double* r, const double* q, const double* sigma, const double* K,
                        const double* tau, const uint8_t* is_put, double* B, cudaStream_t st);
