@@ -80,7 +80,8 @@ int faop_workspace_bytes(const faop_cfg* cfg, int64_t N, size_t* bytes);
  * integral (:92-103).  q == 0 calls take the European shortcut (:50-53): iters = 0, err = 1e6,
  * boundary rows NaN.
  *   t        nullable (t = 0)
- *   B0_in    nullable: N x (n+1) borrowed seed boundary (stage-wise parity); skips the seed kernel
+ *   B0_in    nullable: N x (n+1) borrowed seed boundary (stage-wise parity); skips the seed kernel.  Its last column
+ *            (tau = 0) is B_at_zero in every reference seed; the specialised kernels impose that value
  *   B, B0_out nullable: N x (n+1) row-major, node i at tau_i = T (1+cos(i pi/n))^2/4, last node tau=0
  *   iters, err nullable: realised iteration count and final ||B_old-B_new||_2 per option
  *   iter_errs nullable: N x max_iters, the per-iteration errors of self.iter_records (:130), NaN padded       */
