@@ -275,6 +275,7 @@ int faop_measure_fp64_peak(int launches, double* tflops, double* ms_per_launch, 
 struct faop_ctx {
     int device;
     cudaStream_t stream;
+    cudaStream_t stream2;   // second lane of the chunk pipeline: copies of one chunk overlap the kernels of the other
     void* dev;          // one growing device arena
     size_t dev_bytes;
     void* tables_dev;   // cached table blob
@@ -293,6 +294,8 @@ int faop_ctx_create(int device, faop_ctx** out) {
     memset(&c->tables_cfg, 0, sizeof c->tables_cfg);
     cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { delete c; return (int)e; }
+    e = cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { cudaStreamDestroy(c->stream); delete c; return (int)e; }
     *out = c;
     return 0;
 }
@@ -303,6 +306,7 @@ int faop_ctx_destroy(faop_ctx* c) {
     if (c->dev) cudaFree(c->dev);
     if (c->tables_dev) cudaFree(c->tables_dev);
     cudaStreamDestroy(c->stream);
+    cudaStreamDestroy(c->stream2);
     delete c;
     return 0;
 }
@@ -364,28 +368,41 @@ int faop_alo_price_batch_host(faop_ctx* c, const faop_cfg* cfg, int64_t N, const
     double* d_S = (double*)take(vec); double* d_price = (double*)take(vec); double* d_eur = (double*)take(vec);
     double* d_err = (double*)take(vec); uint8_t* d_put = (uint8_t*)take(vec); int32_t* d_it = (int32_t*)take(vec);
     double* d_B0 = (double*)take(mat); double* d_B = (double*)take(mat);
-    cudaStream_t st = c->stream;
-    const size_t vb = (size_t)N * sizeof(double);
-    FAOP_CUDA_OK(cudaMemcpyAsync(d_r, r, vb, cudaMemcpyHostToDevice, st));
-    FAOP_CUDA_OK(cudaMemcpyAsync(d_q, q, vb, cudaMemcpyHostToDevice, st));
-    FAOP_CUDA_OK(cudaMemcpyAsync(d_s, sigma, vb, cudaMemcpyHostToDevice, st));
-    FAOP_CUDA_OK(cudaMemcpyAsync(d_K, K, vb, cudaMemcpyHostToDevice, st));
-    FAOP_CUDA_OK(cudaMemcpyAsync(d_T, T, vb, cudaMemcpyHostToDevice, st));
-    if (t) FAOP_CUDA_OK(cudaMemcpyAsync(d_t, t, vb, cudaMemcpyHostToDevice, st));
-    FAOP_CUDA_OK(cudaMemcpyAsync(d_S, S, vb, cudaMemcpyHostToDevice, st));
-    FAOP_CUDA_OK(cudaMemcpyAsync(d_put, is_put, (size_t)N, cudaMemcpyHostToDevice, st));
-    if (B0_in) FAOP_CUDA_OK(cudaMemcpyAsync(d_B0, B0_in, (size_t)N * nn * sizeof(double), cudaMemcpyHostToDevice, st));
-    rc = faop_alo_price_batch(cfg, N, d_r, d_q, d_s, d_K, d_T, t ? d_t : nullptr, d_S, d_put, c->tables_dev,
-                              B0_in ? d_B0 : nullptr, d_price, european ? d_eur : nullptr, B ? d_B : nullptr,
-                              B0_in ? nullptr : d_B0, iters ? d_it : nullptr, err ? d_err : nullptr, nullptr, nullptr, st);
-    if (rc) return rc;
-    FAOP_CUDA_OK(cudaMemcpyAsync(price, d_price, vb, cudaMemcpyDeviceToHost, st));
-    if (european) FAOP_CUDA_OK(cudaMemcpyAsync(european, d_eur, vb, cudaMemcpyDeviceToHost, st));
-    if (err) FAOP_CUDA_OK(cudaMemcpyAsync(err, d_err, vb, cudaMemcpyDeviceToHost, st));
-    if (iters) FAOP_CUDA_OK(cudaMemcpyAsync(iters, d_it, (size_t)N * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-    if (B) FAOP_CUDA_OK(cudaMemcpyAsync(B, d_B, (size_t)N * nn * sizeof(double), cudaMemcpyDeviceToHost, st));
-    if (B0_out) FAOP_CUDA_OK(cudaMemcpyAsync(B0_out, d_B0, (size_t)N * nn * sizeof(double), cudaMemcpyDeviceToHost, st));
-    FAOP_CUDA_OK(cudaStreamSynchronize(st));
+    // Chunk pipeline over two streams: while one chunk's kernels run, the other's inputs go up and results come back
+    // (asynchronous when the caller's arrays are pinned).  Chunks are slices of the same arena.
+    int nchunks = (int)(N / 262144);
+    if (nchunks < 1) nchunks = 1;
+    if (nchunks > 4) nchunks = 4;
+    const int64_t per = ((N + nchunks - 1) / nchunks + 255) & ~(int64_t)255;
+    int idx = 0;
+    for (int64_t off = 0; off < N; off += per, ++idx) {
+        const int64_t cnt = (N - off < per) ? N - off : per;
+        cudaStream_t st = (idx & 1) ? c->stream2 : c->stream;
+        const size_t vb = (size_t)cnt * sizeof(double), mb = (size_t)cnt * nn * sizeof(double);
+        FAOP_CUDA_OK(cudaMemcpyAsync(d_r + off, r + off, vb, cudaMemcpyHostToDevice, st));
+        FAOP_CUDA_OK(cudaMemcpyAsync(d_q + off, q + off, vb, cudaMemcpyHostToDevice, st));
+        FAOP_CUDA_OK(cudaMemcpyAsync(d_s + off, sigma + off, vb, cudaMemcpyHostToDevice, st));
+        FAOP_CUDA_OK(cudaMemcpyAsync(d_K + off, K + off, vb, cudaMemcpyHostToDevice, st));
+        FAOP_CUDA_OK(cudaMemcpyAsync(d_T + off, T + off, vb, cudaMemcpyHostToDevice, st));
+        if (t) FAOP_CUDA_OK(cudaMemcpyAsync(d_t + off, t + off, vb, cudaMemcpyHostToDevice, st));
+        FAOP_CUDA_OK(cudaMemcpyAsync(d_S + off, S + off, vb, cudaMemcpyHostToDevice, st));
+        FAOP_CUDA_OK(cudaMemcpyAsync(d_put + off, is_put + off, (size_t)cnt, cudaMemcpyHostToDevice, st));
+        if (B0_in) FAOP_CUDA_OK(cudaMemcpyAsync(d_B0 + off * nn, B0_in + off * nn, mb, cudaMemcpyHostToDevice, st));
+        rc = faop_alo_price_batch(cfg, cnt, d_r + off, d_q + off, d_s + off, d_K + off, d_T + off, t ? d_t + off : nullptr,
+                                  d_S + off, d_put + off, c->tables_dev, B0_in ? d_B0 + off * nn : nullptr, d_price + off,
+                                  european ? d_eur + off : nullptr, B ? d_B + off * nn : nullptr,
+                                  B0_in ? nullptr : d_B0 + off * nn, iters ? d_it + off : nullptr, err ? d_err + off : nullptr,
+                                  nullptr, nullptr, st);
+        if (rc) return rc;
+        FAOP_CUDA_OK(cudaMemcpyAsync(price + off, d_price + off, vb, cudaMemcpyDeviceToHost, st));
+        if (european) FAOP_CUDA_OK(cudaMemcpyAsync(european + off, d_eur + off, vb, cudaMemcpyDeviceToHost, st));
+        if (err) FAOP_CUDA_OK(cudaMemcpyAsync(err + off, d_err + off, vb, cudaMemcpyDeviceToHost, st));
+        if (iters) FAOP_CUDA_OK(cudaMemcpyAsync(iters + off, d_it + off, (size_t)cnt * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        if (B) FAOP_CUDA_OK(cudaMemcpyAsync(B + off * nn, d_B + off * nn, mb, cudaMemcpyDeviceToHost, st));
+        if (B0_out) FAOP_CUDA_OK(cudaMemcpyAsync(B0_out + off * nn, d_B0 + off * nn, mb, cudaMemcpyDeviceToHost, st));
+    }
+    FAOP_CUDA_OK(cudaStreamSynchronize(c->stream));
+    FAOP_CUDA_OK(cudaStreamSynchronize(c->stream2));
     return 0;
 }
 
