@@ -37,6 +37,8 @@ _SIGNATURES = {
     "faop_qd_boundary_batch": (ctypes.c_int, [c_i64] + [c_vp] * 8),
     "faop_qd_residual_batch": (ctypes.c_int, [c_i64] + [c_vp] * 9),
     "faop_qd_price_batch": (ctypes.c_int, [c_i64] + [c_vp] * 10),
+    "faop_bjerksund_stensland_batch": (ctypes.c_int, [c_i64] + [c_vp] * 12),
+    "faop_bs_phi_batch": (ctypes.c_int, [c_i64] + [c_vp] * 10),
     "faop_european_batch": (ctypes.c_int, [c_i64] + [c_vp] * 9),
     "faop_european_greeks_batch": (ctypes.c_int, [c_i64] + [c_vp] * 10),
     "faop_cheb_fit_batch": (ctypes.c_int, [c_i64, c_i32, c_vp, c_vp, c_vp]),

@@ -303,6 +303,35 @@ def qd_price_batch(tau, S, r, q, sigma, K, is_put, device=None):
         return P, Bd
 
 
+def bjerksund_stensland_batch(S, r, q, sigma, K, T, is_put=None, Kb=None, Tb=None, device=None):
+    """BksdStld(r, q, sigma, K, T).price(S) (BjerksundStenslandSolver.py:15-21).  Returns (price, boundary X).
+    Kb / Tb: the module globals the reference's computeExerciseBoundary reads (:40, :42); default K, T."""
+    lib = _lib.load()
+    arrs = [S, r, q, sigma, K, T] + ([Kb] if Kb is not None else []) + ([Tb] if Tb is not None else [])
+    dev, N, ts = _common(arrs, device)
+    S, r, q, sigma, K, T = ts[:6]
+    Kb_t = ts[6] if Kb is not None else None
+    Tb_t = ts[6 + (Kb is not None)] if Tb is not None else None
+    with torch.cuda.device(dev):
+        ip = None if is_put is None else _u8(is_put, dev, N)
+        P, X = (torch.empty(N, dtype=torch.float64, device=dev) for _ in range(2))
+        check(lib.faop_bjerksund_stensland_batch(N, _ptr(r), _ptr(q), _ptr(sigma), _ptr(K), _ptr(T), _ptr(S), _ptr(ip),
+                                                 _ptr(Kb_t), _ptr(Tb_t), _ptr(P), _ptr(X), _stream(dev)),
+              "faop_bjerksund_stensland_batch")
+        return P, X
+
+
+def bs_phi_batch(S, T, gamma, H, X, r, q, sigma, device=None):
+    """BksdStld.phi (BjerksundStenslandSolver.py:26-33)."""
+    lib = _lib.load()
+    dev, N, (S, T, gamma, H, X, r, q, sigma) = _common([S, T, gamma, H, X, r, q, sigma], device)
+    with torch.cuda.device(dev):
+        out = torch.empty(N, dtype=torch.float64, device=dev)
+        check(lib.faop_bs_phi_batch(N, _ptr(S), _ptr(T), _ptr(gamma), _ptr(H), _ptr(X), _ptr(r), _ptr(q), _ptr(sigma),
+                                    _ptr(out), _stream(dev)), "faop_bs_phi_batch")
+        return out
+
+
 def european_batch(tau, S, r, q, sigma, K, is_put, device=None):
     """EuropeanOption.european_put_value / european_call_value (EuropeanOptionSolver.py:7-22)."""
     lib = _lib.load()

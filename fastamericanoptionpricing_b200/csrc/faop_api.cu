@@ -240,6 +240,17 @@ int faop_qd_price_batch(int64_t N, const double* r, const double* q, const doubl
     if (N < 0 || (N > 0 && (!r || !q || !sigma || !K || !tau || !S || !is_put || !price))) return FAOP_EINVAL;
     return launch_qd_price(N, r, q, sigma, K, tau, S, is_put, price, boundary, (cudaStream_t)cuda_stream);
 }
+int faop_bjerksund_stensland_batch(int64_t N, const double* r, const double* q, const double* sigma, const double* K,
+                                   const double* T, const double* S, const uint8_t* is_put, const double* Kb,
+                                   const double* Tb, double* price, double* boundary, void* cuda_stream) {
+    if (N < 0 || (N > 0 && (!r || !q || !sigma || !K || !T || !S || !price))) return FAOP_EINVAL;
+    return launch_bjerksund_stensland(N, r, q, sigma, K, T, S, is_put, Kb, Tb, price, boundary, (cudaStream_t)cuda_stream);
+}
+int faop_bs_phi_batch(int64_t N, const double* S, const double* T, const double* gamma, const double* H, const double* X,
+                      const double* r, const double* q, const double* sigma, double* out, void* cuda_stream) {
+    if (N < 0 || (N > 0 && (!S || !T || !gamma || !H || !X || !r || !q || !sigma || !out))) return FAOP_EINVAL;
+    return launch_bs_phi(N, S, T, gamma, H, X, r, q, sigma, out, (cudaStream_t)cuda_stream);
+}
 int faop_european_batch(int64_t N, const double* tau, const double* S, const double* r, const double* q,
                         const double* sigma, const double* K, const uint8_t* is_put, double* price, void* cuda_stream) {
     if (N < 0 || (N > 0 && (!tau || !S || !r || !q || !sigma || !K || !is_put || !price))) return FAOP_EINVAL;

@@ -44,6 +44,11 @@ int launch_qd_residual(int64_t N, const double* r, const double* q, const double
 int launch_qd_price(int64_t N, const double* r, const double* q, const double* sigma, const double* K,
                     const double* tau, const double* S, const uint8_t* is_put, double* price, double* boundary,
                     cudaStream_t st);
+int launch_bjerksund_stensland(int64_t N, const double* r, const double* q, const double* sigma, const double* K,
+                               const double* T, const double* S, const uint8_t* is_put, const double* Kb, const double* Tb,
+                               double* price, double* boundary, cudaStream_t st);
+int launch_bs_phi(int64_t N, const double* S, const double* T, const double* gamma, const double* H, const double* X,
+                  const double* r, const double* q, const double* sigma, double* out, cudaStream_t st);
 int launch_european(int64_t N, const double* tau, const double* S, const double* r, const double* q,
                     const double* sigma, const double* K, const uint8_t* is_put, double* price, cudaStream_t st);
 int launch_european_greeks(int64_t N, const double* tau, const double* S, const double* r, const double* q,

@@ -175,6 +175,7 @@ __global__ void __launch_bounds__(256) dev_math_kernel(int kind, int64_t N, cons
         case 8: { double a[1] = {v}, o[1]; half_erfcx_n<1, true>(a, o); r = o[0]; break; }       // erfcx(v)/2, degree 14
         case 9: { double a[1] = {v}, o[1]; fast_exp_n<1, true>(a, o); r = o[0]; break; }         // e^v, degree 8
         case 10: r = fast_log(v); break;
+        case 11: r = norm_cdf(v); break;                                        // Phi(v), the library-accuracy form
         case 7: { double a[2] = {v, v - 1.0}, o[2]; fast_exp_n<2>(a, o); r = o[0] + o[1]; break; }  // e^v + e^(v-1)
         default: r = nan("");
     }
@@ -222,11 +223,74 @@ int launch_qd_residual(int64_t N, const double* r, const double* q, const double
     count_launch();
     return launch_status();
 }
+// ---------------------------------------------------------------- Bjerksund-Stensland (1993) flat-boundary call
+// BksdStld (BjerksundStenslandSolver.py:4-43).  phi (:26-33):
+FAOP_D double bs_phi(double S, double T, double gamma, double H, double X, double r, double b, double sg) {
+    const double s2 = sg * sg, svt = sg * sqrt(T);
+    const double lamb = -r + gamma * b + 0.5 * gamma * (gamma - 1) * s2;
+    const double kappa = 2 * b / s2 + (2 * gamma - 1.0);
+    const double drift = (b + (gamma - 0.5) * s2) * T;
+    const double d1 = -(log(S / H) + drift) / svt;
+    const double d2 = -(log(X * X / (S * H)) + drift) / svt;
+    return exp(lamb * T) * pow(S, gamma) * (norm_cdf(d1) - pow(X / S, kappa) * norm_cdf(d2));
+}
+// price (:15-21), computeAlpha (:23-24), computeExerciseBoundary (:38-43).  The reference reads the module globals
+// `K` and `T` at :40 and :42 (it only runs as __main__); Kb / Tb carry those two values (nullable = the option's own
+// strike and maturity).  is_put (nullable = all calls) prices a put by the symmetry the reference's __main__ uses (:53):
+// put(S, K, r, q) = call(S' = K, K' = S, r' = q, q' = r).  No S >= X branch, as upstream.
+__global__ void __launch_bounds__(128) bjerksund_stensland_kernel(int64_t N, const double* r_, const double* q_,
+                                                                  const double* sigma_, const double* K_, const double* T_,
+                                                                  const double* S_, const uint8_t* is_put, const double* Kb_,
+                                                                  const double* Tb_, double* price, double* boundary) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    double r = r_[i], q = q_[i], sg = sigma_[i], K = K_[i], T = T_[i], S = S_[i];
+    if (is_put && is_put[i]) {
+        double t = r; r = q; q = t;
+        t = S; S = K; K = t;
+    }
+    const double Kb = Kb_ ? Kb_[i] : K, Tb = Tb_ ? Tb_[i] : T;
+    const double b = r - q, s2 = sg * sg;
+    const double hb = b / s2 - 0.5;
+    const double beta = (0.5 - b / s2) + sqrt(hb * hb + 2.0 * r / s2);                  // :13
+    const double B0 = fmax(K, r / (r - b) * Kb);                                        // :40
+    const double Binf = beta / (beta - 1) * K;                                          // :41
+    const double h = -(b * Tb + 2 * sg * sqrt(T)) * (K * K / ((Binf - B0) * B0));       // :42
+    const double X = B0 + (Binf - B0) * (1 - exp(h));                                   // :43
+    if (boundary) boundary[i] = X;
+    const double alpha = (X - K) * pow(X, -beta);                                       // :24
+    price[i] = alpha * pow(S, beta) - alpha * bs_phi(S, T, beta, X, X, r, b, sg) + bs_phi(S, T, 1.0, X, X, r, b, sg) -
+               bs_phi(S, T, 1.0, K, X, r, b, sg) - K * bs_phi(S, T, 0.0, X, X, r, b, sg) + K * bs_phi(S, T, 0.0, K, X, r, b, sg);
+}
+// BksdStld.phi as a stand-alone component (:26-33)
+__global__ void __launch_bounds__(256) bs_phi_kernel(int64_t N, const double* S, const double* T, const double* gamma,
+                                                     const double* H, const double* X, const double* r, const double* q,
+                                                     const double* sigma, double* out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    out[i] = bs_phi(S[i], T[i], gamma[i], H[i], X[i], r[i], r[i] - q[i], sigma[i]);
+}
+
 int launch_qd_price(int64_t N, const double* r, const double* q, const double* sigma, const double* K,
                     const double* tau, const double* S, const uint8_t* is_put, double* price, double* boundary,
                     cudaStream_t st) {
     if (N == 0) return 0;
     qd_price_kernel<<<blocks_for(N, 128), 128, 0, st>>>(N, r, q, sigma, K, tau, S, is_put, price, boundary);
+    count_launch();
+    return launch_status();
+}
+int launch_bjerksund_stensland(int64_t N, const double* r, const double* q, const double* sigma, const double* K,
+                               const double* T, const double* S, const uint8_t* is_put, const double* Kb, const double* Tb,
+                               double* price, double* boundary, cudaStream_t st) {
+    if (N == 0) return 0;
+    bjerksund_stensland_kernel<<<blocks_for(N, 128), 128, 0, st>>>(N, r, q, sigma, K, T, S, is_put, Kb, Tb, price, boundary);
+    count_launch();
+    return launch_status();
+}
+int launch_bs_phi(int64_t N, const double* S, const double* T, const double* gamma, const double* H, const double* X,
+                  const double* r, const double* q, const double* sigma, double* out, cudaStream_t st) {
+    if (N == 0) return 0;
+    bs_phi_kernel<<<blocks_for(N, 256), 256, 0, st>>>(N, S, T, gamma, H, X, r, q, sigma, out);
     count_launch();
     return launch_status();
 }

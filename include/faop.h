@@ -149,6 +149,16 @@ int faop_qd_residual_batch(int64_t N, const double* r, const double* q, const do
 int faop_qd_price_batch(int64_t N, const double* r, const double* q, const double* sigma,
                         const double* K, const double* tau, const double* S, const uint8_t* is_put,
                         double* price, double* boundary, void* cuda_stream);
+/* BksdStld.price(S) (BjerksundStenslandSolver.py:15-21): Bjerksund-Stensland 1993 flat-boundary American CALL with
+ * computeExerciseBoundary (:38-43) and computeAlpha (:23-24).  The reference reads the module globals `K`, `T` at :40/:42
+ * (it only runs as __main__); Kb, Tb carry them (nullable: the option's own K, T).  is_put nullable (= all calls); a put
+ * is priced by the symmetry of the reference's __main__ (:53): call with S<->K, r<->q.  boundary (the trigger X) nullable. */
+int faop_bjerksund_stensland_batch(int64_t N, const double* r, const double* q, const double* sigma, const double* K,
+                                   const double* T, const double* S, const uint8_t* is_put, const double* Kb,
+                                   const double* Tb, double* price, double* boundary, void* cuda_stream);
+/* BksdStld.phi(S, T, gamma, H, X) (BjerksundStenslandSolver.py:26-33). */
+int faop_bs_phi_batch(int64_t N, const double* S, const double* T, const double* gamma, const double* H, const double* X,
+                      const double* r, const double* q, const double* sigma, double* out, void* cuda_stream);
 /* EuropeanOption.european_put_value / european_call_value (EuropeanOptionSolver.py:7-22). */
 int faop_european_batch(int64_t N, const double* tau, const double* S, const double* r, const double* q,
                         const double* sigma, const double* K, const uint8_t* is_put,
@@ -199,7 +209,8 @@ int64_t faop_launch_count(void);
 /* Unit-test hook for the device math the specialised kernel is built from (csrc/faop_fastmath.cuh):
  * kind 0 = fast_exp, 1 = mills_half (Phi(-y)/exp(-y^2/2)), 2 = fast_sqrt_pos, 3 = fast_rcp, 4 = Phi via fast path,
  * 5 = erfcx(x)/2 (x >= 0), 6 = sqrt(max(0, x)), 7 = e^x + e^(x-1) (two interleaved chains),
- * 8 = erfcx(x)/2 degree-14 variant, 9 = e^x degree-8 variant (the quadrature-point versions), 10 = fast_log. */
+ * 8 = erfcx(x)/2 degree-14 variant, 9 = e^x degree-8 variant (the quadrature-point versions), 10 = fast_log,
+ * 11 = Phi(x) as the leaf kernels compute it (erfc based). */
 int faop_dev_math_batch(int32_t kind, int64_t N, const double* x, double* out, void* cuda_stream);
 /* FP64 FMA-pipe peak microbenchmark (the roofline denominator; MEASURED_PEAKS.json has no FP64
  * figure): launches `launches` saturating DFMA kernels, returns measured TFLOP/s (2 flops/DFMA). */

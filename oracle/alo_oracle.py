@@ -75,6 +75,52 @@ def european_option_theta(tau, s0, r, q, vol, strike):
         - vol * s0 * np.exp(-q * tau) * norm_pdf(d1) / (2 * np.sqrt(tau))
 
 
+# --------------------------------------------------------------------------- Bjerksund-Stensland (1993) call
+def bs_beta(r, q, sigma):
+    """BjerksundStenslandSolver.py:11-13."""
+    b = r - q
+    s2 = np.power(sigma, 2.0)
+    return (0.5 - b / s2) + np.sqrt(np.power(b / s2 - 0.5, 2.0) + 2.0 * r / s2)
+
+
+def bs_boundary(r, q, sigma, K, T, Kb=None, Tb=None):
+    """BjerksundStenslandSolver.py:38-43 (computeExerciseBoundary).  The reference reads the MODULE GLOBALS `K` and `T`
+    at :40 and :42 (it only runs as __main__); Kb / Tb are those two values, defaulting to the object's own strike and
+    maturity (the evident intent)."""
+    Kb = K if Kb is None else Kb
+    Tb = T if Tb is None else Tb
+    b = r - q
+    beta = bs_beta(r, q, sigma)
+    with np.errstate(all="ignore"):
+        B0 = np.maximum(K, (r / (r - b) * Kb))
+        Binf = beta / (beta - 1) * K
+        h = -(b * Tb + 2 * sigma * np.sqrt(T)) * (np.power(K, 2.0) / ((Binf - B0) * B0))
+        return B0 + (Binf - B0) * (1 - np.exp(h))
+
+
+def bs_phi(S, T, gamma, H, X, r, q, sigma):
+    """BjerksundStenslandSolver.py:26-33."""
+    b = r - q
+    s2 = np.power(sigma, 2.0)
+    with np.errstate(all="ignore"):
+        lamb = -r + gamma * b + 0.5 * gamma * (gamma - 1) * s2
+        kappa = 2 * b / s2 + (2 * gamma - 1.0)
+        d1 = -(np.log(S / H) + (b + (gamma - 0.5) * s2) * T) / (sigma * np.sqrt(T))
+        d2 = -(np.log(X * X / (S * H)) + (b + (gamma - 0.5) * s2) * T) / (sigma * np.sqrt(T))
+        return np.exp(lamb * T) * np.power(S, gamma) * (ndtr(d1) - np.power(X / S, kappa) * ndtr(d2))
+
+
+def bs_price(S, r, q, sigma, K, T, Kb=None, Tb=None):
+    """BjerksundStenslandSolver.py:15-21 (price) with computeAlpha (:23-24).  No S >= X early-exercise branch, as upstream."""
+    S, r, q, sigma, K, T = (np.asarray(a, dtype=float) for a in (S, r, q, sigma, K, T))
+    X = bs_boundary(r, q, sigma, K, T, Kb, Tb)
+    beta = bs_beta(r, q, sigma)
+    with np.errstate(all="ignore"):
+        alpha = (X - K) * np.power(X, -beta)
+        ph = lambda g, H: bs_phi(S, T, g, H, X, r, q, sigma)  # noqa: E731
+        return alpha * np.power(S, beta) - alpha * ph(beta, X) + ph(1, X) - ph(1, K) - K * ph(0, X) + K * ph(0, K)
+
+
 # --------------------------------------------------------------------------- Chebyshev
 def cheb_points(n):
     """ChebyshevInterpolation.py:15-17: cos(i pi / n), i = 0..n."""

@@ -35,7 +35,11 @@ class _N:
     def __call__(self, *a, **k): return _N()
 for _sub in ("pyplot", "cm", "colors"):
     _m = types.ModuleType("matplotlib." + _sub)
-    _m.__getattr__ = lambda k: _N()
+    def _ga(k):
+        if k.startswith("__"):      # inspect / importlib probe dunders (e.g. __file__) on every module in sys.modules
+            raise AttributeError(k)
+        return _N()
+    _m.__getattr__ = _ga
     sys.modules["matplotlib." + _sub] = _m
     globals()[_sub] = _m
 '''
@@ -401,8 +405,50 @@ def gen_stage(pool):
     print("stage: %d" % len(jobs))
 
 
+def _bs_module(Kg, Tg):
+    """The reference module executed with the globals `K`, `T` that computeExerciseBoundary reads
+    (BjerksundStenslandSolver.py:40,42); its __main__ block is not run."""
+    import types
+    src = open(os.path.join(REF, "BjerksundStenslandSolver.py")).read()
+    mod = types.ModuleType("BjerksundStenslandSolver_ref")
+    mod.__dict__.update(K=Kg, T=Tg)
+    exec(compile(src, "BjerksundStenslandSolver.py", "exec"), mod.__dict__)
+    return mod
+
+
+def gen_bs(pool, count=1024):
+    g = np.random.default_rng(77)
+    r = g.uniform(0.005, 0.10, count)
+    q = g.uniform(0.005, 0.10, count)
+    sig = g.uniform(0.08, 0.6, count)
+    K = g.uniform(50.0, 150.0, count)
+    T = g.uniform(0.05, 5.0, count)
+    S = K * g.uniform(0.5, 1.4, count)
+    # globals as the object's own strike / maturity (what the class means) ...
+    price = np.empty(count); X = np.empty(count); alpha = np.empty(count); phis = np.empty((count, 6))
+    for i in range(count):
+        m = _bs_module(float(K[i]), float(T[i]))
+        o = m.BksdStld(float(r[i]), float(q[i]), float(sig[i]), float(K[i]), float(T[i]))
+        price[i] = o.price(float(S[i]))
+        X[i] = o.computeExerciseBoundary()
+        alpha[i] = o.computeAlpha(X[i])
+        phis[i] = [o.phi(S[i], T[i], o.beta, X[i], X[i]), o.phi(S[i], T[i], 1, X[i], X[i]), o.phi(S[i], T[i], 1, K[i], X[i]),
+                   o.phi(S[i], T[i], 0, X[i], X[i]), o.phi(S[i], T[i], 0, K[i], X[i]), o.beta]
+    # ... and foreign globals (the __main__ put-by-symmetry line has K_global = 100 != self.K = 80, :52-53)
+    Kg = g.uniform(50.0, 150.0, 128); Tg = g.uniform(0.05, 5.0, 128)
+    price_g = np.array([_bs_module(float(Kg[i]), float(Tg[i])).BksdStld(float(r[i]), float(q[i]), float(sig[i]), float(K[i]),
+                                                                         float(T[i])).price(float(S[i])) for i in range(128)])
+    # the module's own __main__ numbers (:46-57)
+    m = _bs_module(100, 3.0)
+    main_call = m.BksdStld(0.04, 0.04, 0.2, 100, 3.0).price(80)
+    main_put = m.BksdStld(0.04, 0.04, 0.2, 80, 3.0).price(100)
+    np.savez(os.path.join(OUT, "ref_bs.npz"), r=r, q=q, sigma=sig, K=K, T=T, S=S, price=price, X=X, alpha=alpha, phis=phis,
+             Kg=Kg, Tg=Tg, price_g=price_g, main_call=main_call, main_put=main_put, versions=np.array(VERSIONS))
+    print("bs: %d, main call %r put %r, nan %d" % (count, main_call, main_put, np.isnan(price).sum()))
+
+
 GENS = dict(c1=gen_c1, european=gen_european, cheb=gen_cheb, qd=gen_qd, stage=gen_stage, misc=gen_misc, cn=gen_cn,
-            c3=gen_c3, c2=gen_c2)
+            c3=gen_c3, c2=gen_c2, bs=gen_bs)
 
 
 def main():

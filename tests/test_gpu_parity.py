@@ -532,3 +532,39 @@ def test_stress_ranges_vs_c_oracle():
                     sane_out = ((out["B"] > 1e-3 * b["K"][:, None]) & (out["B"] < 1e3 * b["K"][:, None])).all(axis=1)
                 bad_out = ~(np.isfinite(out["price"]) & (out["err"] < 1e-2) & sane_out)
                 assert (bad_ref[~short] != bad_out[~short]).mean() <= 2e-3, (tag, (bad_ref != bad_out).sum())
+
+
+def test_bjerksund_stensland():
+    """faop_bjerksund_stensland_batch / faop_bs_phi_batch and the BksdStld drop-in against the reference run with the
+    module globals its computeExerciseBoundary reads (tests/golden/ref_bs.npz).  pow / exp of O(100) magnitudes: 1e-12 relative."""
+    from fastamericanoptionpricing_b200.BjerksundStenslandSolver import BksdStld
+    z = load_golden("ref_bs.npz")
+    a = [z[k] for k in ("S", "r", "q", "sigma", "K", "T")]
+    P, X = batch.bjerksund_stensland_batch(*a)
+    scale = 1 + np.abs(z["price"])
+    assert np.max(np.abs(P.cpu().numpy() - z["price"]) / scale) <= 1e-11
+    assert np.max(np.abs(X.cpu().numpy() / z["X"] - 1)) <= 1e-13
+    Pg, _ = batch.bjerksund_stensland_batch(*[x[:128] for x in a], Kb=z["Kg"], Tb=z["Tg"])
+    assert np.max(np.abs(Pg.cpu().numpy() - z["price_g"]) / scale[:128]) <= 1e-11
+    S, r, q, sg, K, T = a
+    ph = z["phis"]
+    beta = ph[:, 5]
+    for col, (gam, H) in enumerate(((beta, z["X"]), (1.0, z["X"]), (1.0, K), (0.0, z["X"]), (0.0, K))):
+        got = batch.bs_phi_batch(S, T, np.broadcast_to(gam, S.shape).copy(), H, z["X"], r, q, sg).cpu().numpy()
+        assert np.max(np.abs(got - ph[:, col]) / (1 + np.abs(ph[:, col]))) <= 1e-11, col
+    # the module's own __main__ (BjerksundStenslandSolver.py:46-57): call, and put by symmetry with the global K = 100
+    call = BksdStld(0.04, 0.04, 0.2, 100, 3.0)
+    assert abs(call.price(80) - 4.342423011041589) <= 1e-11 and abs(call.beta - ph[0, 5]) >= 0   # beta is host-side
+    put = BksdStld(0.04, 0.04, 0.2, 80, 3.0)
+    put.boundary_K = 100
+    assert abs(put.price(100) - 23.062019527897103) <= 1e-11
+    # is_put flag = the same symmetry on the device
+    Pp, _ = batch.bjerksund_stensland_batch(K, q, r, sg, S, T)          # call(S'=K, K'=S, r'=q, q'=r)
+    Pq, _ = batch.bjerksund_stensland_batch(S, r, q, sg, K, T, is_put=np.ones(len(S), dtype=np.uint8))
+    assert torch.equal(Pp, Pq)
+    i = 5
+    o1 = BksdStld(r[i], q[i], sg[i], K[i], T[i])
+    assert abs(o1.computeExerciseBoundary() / z["X"][i] - 1) <= 1e-13 and abs(o1.computeAlpha(z["X"][i]) / z["alpha"][i] - 1) <= 1e-13
+    assert abs(o1.phi(S[i], T[i], 1, K[i], z["X"][i]) - ph[i, 2]) <= 1e-11 * (1 + abs(ph[i, 2]))
+    assert abs(BksdStld.cdf(0.3) - 0.6179114221889526) <= 1e-15
+    assert np.max(np.abs(o1.price(S[:7]) - np.array([o.item() for o in [batch.bjerksund_stensland_batch(S[j], r[i], q[i], sg[i], K[i], T[i])[0].cpu() for j in range(7)]]))) == 0

@@ -204,3 +204,16 @@ def test_cn_oracle():
     a = [0.04, 0.04, 0.2, 100.0, 3.0, 80.0]
     p2 = co.cn_put_batch(*a, n_space=200, max_dt=1 / 12.0, mode=2)
     assert abs(p2[0] - 23.209084798867803) <= 5e-4
+
+
+def test_bjerksund_stensland_golden():
+    """BksdStld (BjerksundStenslandSolver.py:4-43) run with the globals it reads (own K/T, foreign K/T, and the
+    module's own __main__ numbers, SURVEY 4: call 4.342423011041589, put 23.062019527897103)."""
+    z = load_golden("ref_bs.npz")
+    a = [z[k] for k in ("S", "r", "q", "sigma", "K", "T")]
+    assert np.max(np.abs(o.bs_price(*a) - z["price"]) / (1 + np.abs(z["price"]))) <= 1e-14
+    assert np.max(np.abs(o.bs_boundary(*a[1:]) / z["X"] - 1)) <= 1e-15
+    pg = o.bs_price(*[x[:128] for x in a], z["Kg"], z["Tg"])
+    assert np.max(np.abs(pg - z["price_g"]) / (1 + np.abs(z["price_g"]))) <= 1e-14
+    assert o.bs_price(80, .04, .04, .2, 100, 3.0, 100, 3.0) == 4.342423011041589 == float(z["main_call"])
+    assert o.bs_price(100, .04, .04, .2, 80, 3.0, 100, 3.0) == 23.062019527897103 == float(z["main_put"])
