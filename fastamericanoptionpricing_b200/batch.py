@@ -235,17 +235,31 @@ def price_known_boundary_batch(B, r, q, sigma, K, T, S, is_put, t=None, cfg: Alo
         return price, eur
 
 
-def surface_batch(surface: dict, first, count, cfg: AloConfig, want_iters=False, device=None, workspace_mb=512):
+def surface_batch(surface: dict, first, count, cfg: AloConfig, want_iters=False, device=None, workspace_mb=512,
+                  dedup=False, out=None):
     """Config-5 implied-surface sweep; options are decoded from the flat index on the device
-    (workloads.c5_surface defines the index order).  Returns price (and iters)."""
+    (workloads.c5_surface defines the index order).  Returns price (and iters).
+    dedup=True: one boundary solve per (T, sigma) group shared by all strikes (faop_alo_surface_dedup_batch);
+    prices agree with the plain sweep to rounding.  out: optional preallocated price tensor (count,)."""
     lib = _lib.load()
     dev = _device(device)
     with torch.cuda.device(dev):
         s = FaopSurface(surface["K0"], surface["K1"], surface["T0"], surface["T1"], surface["V0"], surface["V1"],
                         surface["S"], surface["r"], surface["q"], surface["nK"], surface["nT"], surface["nV"],
                         int(surface.get("is_put", 1)))
-        price = torch.empty(count, dtype=torch.float64, device=dev)
+        price = torch.empty(count, dtype=torch.float64, device=dev) if out is None else out
         iters = torch.empty(count, dtype=torch.int32, device=dev) if want_iters else None
+        if dedup:
+            tab = tables_for(cfg, dev)
+            c = cfg.c()
+            nb = ctypes.c_size_t()
+            check(lib.faop_alo_surface_dedup_workspace_bytes(ctypes.byref(c), ctypes.byref(s), int(first), int(count),
+                                                             ctypes.byref(nb)), "faop_alo_surface_dedup_workspace_bytes")
+            ws = torch.empty(max(nb.value, 256), dtype=torch.uint8, device=dev)
+            check(lib.faop_alo_surface_dedup_batch(ctypes.byref(c), ctypes.byref(s), int(first), int(count), _ptr(tab),
+                                                   _ptr(price), _ptr(iters), _ptr(ws), ws.numel(), _stream(dev)),
+                  "faop_alo_surface_dedup_batch")
+            return (price, iters) if want_iters else price
         ws = torch.empty(workspace_mb << 20, dtype=torch.uint8, device=dev)
         tab = tables_for(cfg, dev)
         c = cfg.c()

@@ -125,6 +125,10 @@ __global__ void __launch_bounds__(kGenWarps * 32) alo_generic_kernel(AloArgs a) 
     for (int64_t opt = (int64_t)blockIdx.x * kGenWarps + warp; opt < a.N; opt += stride) {
         const Opt o = load_option(a, opt);
         if (o.q == 0 && !o.put) {  // European shortcut, FastAmericanOptionSolverBase.py:50-53
+            if (a.snap) {
+                if (lane == 0) a.nsnap[opt] = -1;
+                continue;
+            }
             double e = euro_value(o.T - o.t, o.S, o.r, o.q, o.sg, o.K, false);
             if (lane == 0) {
                 a.price[opt] = e;
@@ -142,6 +146,8 @@ __global__ void __launch_bounds__(kGenWarps * 32) alo_generic_kernel(AloArgs a) 
         const double lnXK = log(o.X / o.K);
         int count = 0;
         double err = 1.0;
+        int ns = 0;                  // snapshot mode only
+        double best = 1.79e308;
         while (err > a.cfg.iter_tol && count < a.cfg.max_iters) {
             ++count;
             fit_boundary(w, tb, n, o.X, lane);
@@ -164,6 +170,15 @@ __global__ void __launch_bounds__(kGenWarps * 32) alo_generic_kernel(AloArgs a) 
             err = sqrt(warp_sum(ss));  // norm1_error is the 2-norm over all n+1 nodes (:230-233)
             if (a.iter_errs && lane == 0) a.iter_errs[opt * a.cfg.max_iters + (count - 1)] = err;  // iter_records (:130)
             __syncwarp();
+            if (a.snap && err <= a.snap_tol_hi && err < best) {
+                best = err;
+                snap_append(a, opt, ns, err, count, w, tb, n, o.X, lane);
+            }
+        }
+        if (a.snap) {
+            if (!(ns > 0 && best == err)) snap_append(a, opt, ns, 0.0, count, w, tb, n, o.X, lane);
+            if (lane == 0) a.nsnap[opt] = ns;
+            continue;
         }
         if (a.iter_errs) for (int j = count + lane; j < a.cfg.max_iters; j += 32) a.iter_errs[opt * a.cfg.max_iters + j] = nan("");
         if (a.B) for (int j = lane; j <= n; j += 32) a.B[opt * nn + j] = w.B[j];

@@ -241,6 +241,25 @@ FAOP_D void setup_nodes(const WarpSmem& w, const CtaTables& tb, int n, const Opt
     }
 }
 
+// Snapshot mode: append [err, count, a_0..a_n] of the boundary currently in w.B (see AloArgs::snap).  Overwrites w.L/H/A.
+// The catch-all row (err == 0) always lands: if the table is full it replaces the last row.
+FAOP_D void snap_append(const AloArgs& a, int64_t opt, int& ns, double err, int count, const WarpSmem& w,
+                        const CtaTables& tb, int n, double X, int lane) {
+    if (ns >= a.snap_cap) {
+        if (err != 0.0) return;
+        ns = a.snap_cap - 1;
+    }
+    fit_boundary(w, tb, n, X, lane);
+    double* dst = a.snap + ((int64_t)opt * a.snap_cap + ns) * (n + 3);
+    if (lane == 0) {
+        dst[0] = err;
+        dst[1] = (double)count;
+    }
+    for (int k = lane; k <= n; k += 32) dst[2 + k] = w.A[k];
+    ++ns;
+    __syncwarp();
+}
+
 // Price integral on the boundary currently in w.B: american_value_with_known_boundary
 // (FastAmericanOptionSolverBase.py:92-103).  Returns price; *eur gets the European value.
 FAOP_D double price_integral(const WarpSmem& w, const CtaTables& tb, const TableLayout& tl, const Opt& o, int lane,

@@ -276,7 +276,7 @@ static int launch_clen_t(const AloArgs& a, cudaStream_t st) {
 
 int launch_alo_clen(const AloArgs& a, cudaStream_t st) {
     const int n = a.tl.n;
-    const bool match = !a.cfg.use_derivative && n % 4 == 0 && n + 1 <= kClenMaxNodes && a.tl.LP <= 64 && a.iter_errs == nullptr;
+    const bool match = !a.cfg.use_derivative && n % 4 == 0 && n + 1 <= kClenMaxNodes && a.tl.LP <= 64 && a.iter_errs == nullptr && a.snap == nullptr;
     if (!match) return -1000;
     if (a.N == 0) return 0;
     if (a.cfg.solver == 0) return a.tl.LP == 64 ? launch_clen_t<0, 2>(a, st) : launch_clen_t<0, 1>(a, st);

@@ -31,7 +31,7 @@ struct FastWarpSmem {
     double red[8 * 36];   // transpose buffer of the per-group reduction, row pitch 36 = 4 (mod 16): conflict-free both ways
 };
 
-template <int kFastWarps>
+template <int kFastWarps, bool SNAP = false>
 __global__ void __launch_bounds__(kFastWarps * 32, 1) alo_fast_A12_kernel(AloArgs a) {
     extern __shared__ double smem[];
     const TableLayout tl = a.tl;
@@ -66,6 +66,10 @@ __global__ void __launch_bounds__(kFastWarps * 32, 1) alo_fast_A12_kernel(AloArg
         {
             const Opt o = load_option(a, opt);
             if (o.q == 0 && !o.put) {  // European shortcut, FastAmericanOptionSolverBase.py:50-53
+                if (SNAP) {
+                    if (lane == 0) a.nsnap[opt] = -1;
+                    continue;
+                }
                 double e = euro_value(o.T - o.t, o.S, o.r, o.q, o.sg, o.K, false);
                 if (lane == 0) {
                     a.price[opt] = e;
@@ -103,6 +107,8 @@ __global__ void __launch_bounds__(kFastWarps * 32, 1) alo_fast_A12_kernel(AloArg
 
         int count = 0;
         double err = 1.0;
+        int ns = 0;                  // snapshot mode only
+        double best = 1.79e308;
         while (err > a.cfg.iter_tol && count < a.cfg.max_iters) {
             ++count;
             // ---- L_j = ln(B_j/X), H_j = L_j^2 (FastAmericanOptionSolverBase.py:184), broadcast through shared memory
@@ -205,6 +211,16 @@ __global__ void __launch_bounds__(kFastWarps * 32, 1) alo_fast_A12_kernel(AloArg
             }
             err = sqrt(warp_sum(dd * dd));         // norm1_error is the 2-norm over all n+1 nodes (:230-233)
             __syncwarp();
+            if (SNAP && err <= a.snap_tol_hi && err < best) {
+                best = err;
+                snap_append(a, opt, ns, err, count, gw, tb, NC, ws.par[0], lane);
+            }
+        }
+        if (SNAP) {
+            if (!(ns > 0 && best == err)) snap_append(a, opt, ns, 0.0, count, gw, tb, NC, ws.par[0], lane);
+            if (lane == 0) a.nsnap[opt] = ns;
+            __syncwarp();
+            continue;
         }
         if (a.B && lane < NN) a.B[opt * NN + lane] = ws.B[lane];
         double eur;
@@ -220,13 +236,13 @@ __global__ void __launch_bounds__(kFastWarps * 32, 1) alo_fast_A12_kernel(AloArg
     }
 }
 
-template <int kFastWarps>
+template <int kFastWarps, bool SNAP = false>
 static int launch_fast_t(const AloArgs& a, cudaStream_t st) {
     const size_t sm = sizeof(double) * (size_t)(a.tl.small + NC * NC * 32) + sizeof(FastWarpSmem) * kFastWarps;
-    FAOP_CUDA_OK(cudaFuncSetAttribute(alo_fast_A12_kernel<kFastWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    FAOP_CUDA_OK(cudaFuncSetAttribute(alo_fast_A12_kernel<kFastWarps, SNAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     int64_t ctas = (a.N + kFastWarps - 1) / kFastWarps;
     int grid = (int)(ctas < kSMs ? ctas : kSMs);
-    alo_fast_A12_kernel<kFastWarps><<<grid, kFastWarps * 32, sm, st>>>(a);
+    alo_fast_A12_kernel<kFastWarps, SNAP><<<grid, kFastWarps * 32, sm, st>>>(a);
     count_launch();
     return launch_status();
 }
@@ -237,6 +253,7 @@ int launch_alo_fast(const AloArgs& a, cudaStream_t st) {
                        a.iter_errs == nullptr;
     if (!match) return -1000;
     if (a.N == 0) return 0;
+    if (a.snap) return launch_fast_t<16, true>(a, st);
     if (a.cfg.kernel == 2) return launch_fast_t<12>(a, st);
     if (a.cfg.kernel == 3) return launch_fast_t<20>(a, st);
     return launch_fast_t<16>(a, st);

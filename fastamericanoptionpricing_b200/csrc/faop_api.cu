@@ -178,6 +178,102 @@ int faop_alo_surface_batch(const faop_cfg* cfg, const faop_surface* surf, int64_
     return 0;
 }
 
+// ---- deduplicated surface sweep (faop_surface.cu) ------------------------------------------------------------------
+static int surf_snap_cap(const faop_cfg* cfg) { return cfg->max_iters + 1 < 48 ? cfg->max_iters + 1 : 48; }
+
+static int surf_plan(const faop_cfg* cfg, const faop_surface* surf, int64_t first, int64_t count, SurfArgs& a) {
+    memset(&a, 0, sizeof a);
+    a.cfg = *cfg;
+    a.tl = table_layout(cfg->n_colloc, cfg->n_quad, cfg->n_price_quad);
+    a.s = *surf;
+    a.stepK = surf->nK > 1 ? (surf->K1 - surf->K0) / (surf->nK - 1) : 0.0;
+    a.stepT = surf->nT > 1 ? (surf->T1 - surf->T0) / (surf->nT - 1) : 0.0;
+    a.stepV = surf->nV > 1 ? (surf->V1 - surf->V0) / (surf->nV - 1) : 0.0;
+    a.first = first;
+    a.count = count;
+    const int64_t G = (int64_t)surf->nT * surf->nV;
+    a.iK_lo = (int)(first / G);
+    a.iK_hi = (int)((first + (count > 0 ? count - 1 : 0)) / G);
+    if (a.iK_hi == a.iK_lo && count > 0) {   // inside one strike row: only the groups the range touches
+        a.g_lo = (int)(first % G);
+        a.g_cnt = (int)count;
+    } else {
+        a.g_lo = 0;
+        a.g_cnt = (int)G;
+    }
+    a.snap_cap = surf_snap_cap(cfg);
+    return 0;
+}
+
+static size_t surf_ws_bytes(const SurfArgs& a) {
+    const size_t G = (size_t)a.g_cnt, nn = (size_t)a.tl.n + 1;
+    // r q sigma K T | is_put (one 8-byte slot each) | seeds | snapshot rows | row counts
+    return sizeof(double) * (G * 6 + G * nn + G * (size_t)a.snap_cap * (nn + 2)) + sizeof(int32_t) * ((G + 1) & ~(size_t)1);
+}
+
+int faop_alo_surface_dedup_workspace_bytes(const faop_cfg* cfg, const faop_surface* surf, int64_t first, int64_t count,
+                                           size_t* bytes) {
+    int rc = check_cfg(cfg);
+    if (rc) return rc;
+    if (!surf || !bytes || first < 0 || count < 0 || surf->nK < 1 || surf->nT < 1 || surf->nV < 1) return FAOP_EINVAL;
+    if (first + count > (int64_t)surf->nK * surf->nT * surf->nV) return FAOP_EINVAL;
+    SurfArgs a;
+    surf_plan(cfg, surf, first, count, a);
+    *bytes = (surf_ws_bytes(a) + 255) & ~(size_t)255;
+    return 0;
+}
+
+int faop_alo_surface_dedup_batch(const faop_cfg* cfg, const faop_surface* surf, int64_t first, int64_t count,
+                                 const void* tables_dev, double* price, int32_t* iters, void* workspace,
+                                 size_t workspace_bytes, void* cuda_stream) {
+    int rc = check_cfg(cfg);
+    if (rc) return rc;
+    if (!surf || first < 0 || count < 0 || surf->nK < 1 || surf->nT < 1 || surf->nV < 1) return FAOP_EINVAL;
+    if (first + count > (int64_t)surf->nK * surf->nT * surf->nV) return FAOP_EINVAL;
+    if (cfg->use_derivative) return FAOP_ERANGE;    // f' = N'/D - D'N/D^2 is not scale-free in the reference's form
+    if (count == 0) return 0;
+    if (!price || !workspace || !tables_dev) return FAOP_EINVAL;
+    SurfArgs sa;
+    surf_plan(cfg, surf, first, count, sa);
+    if (workspace_bytes < surf_ws_bytes(sa)) return FAOP_EINVAL;
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    const size_t G = (size_t)sa.g_cnt, nn = (size_t)sa.tl.n + 1;
+    double* w = (double*)workspace;
+    double *d_r = w, *d_q = w + G, *d_s = w + 2 * G, *d_K = w + 3 * G, *d_T = w + 4 * G;
+    uint8_t* d_put = (uint8_t*)(w + 5 * G);
+    double* d_seed = w + 6 * G;
+    double* d_snap = d_seed + G * nn;
+    int32_t* d_ns = (int32_t*)(d_snap + G * (size_t)sa.snap_cap * (nn + 2));
+    sa.tables = (const double*)tables_dev;
+    sa.snap = d_snap;
+    sa.nsnap = d_ns;
+    sa.price = price;
+    sa.iters = iters;
+    rc = launch_surface_groups(sa, d_r, d_q, d_s, d_K, d_T, d_put, st);
+    if (rc) return rc;
+    // one boundary solve per group at K = 1, stopping at the tightest threshold any strike of the range has
+    double Klo = surf->K0 + sa.stepK * sa.iK_lo, Khi = surf->K0 + sa.stepK * sa.iK_hi;
+    if (sa.iK_hi == surf->nK - 1 && surf->nK > 1) Khi = surf->K1;
+    if (sa.iK_lo == surf->nK - 1 && surf->nK > 1) Klo = surf->K1;
+    const double Kmin = Klo < Khi ? Klo : Khi, Kmax = Klo < Khi ? Khi : Klo;
+    AloArgs a;
+    rc = fill_args(a, cfg, (int64_t)G, d_r, d_q, d_s, d_K, d_T, nullptr, nullptr, d_put, tables_dev);
+    if (rc) return rc;
+    a.cfg.iter_tol = cfg->iter_tol / Kmax * (1.0 - 1e-12);     // never above any strike's own tol / K
+    a.snap_tol_hi = cfg->iter_tol / Kmin * (1.0 + 1e-12);      // never below
+    a.snap = d_snap;
+    a.nsnap = d_ns;
+    a.snap_cap = sa.snap_cap;
+    a.seeds_out = d_seed;
+    rc = launch_qd_seed(a, st);
+    if (rc) return rc;
+    a.seeds_in = d_seed;
+    rc = cfg->kernel != 1 ? launch_alo_fast(a, st) : -1000;
+    if (rc == -1000) rc = launch_alo_generic(a, st);
+    if (rc) return rc;
+    return launch_surface_price(sa, st);
+}
+
 int faop_alo_eval_points_batch(const faop_cfg* cfg, int64_t N, int32_t npts, const double* r, const double* q,
                                const double* sigma, const double* K, const double* T, const uint8_t* is_put,
                                const void* tables_dev, const double* B, const double* pts_tau, const double* pts_B,

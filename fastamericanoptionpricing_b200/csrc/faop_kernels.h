@@ -20,6 +20,13 @@ struct AloArgs {
     // eval / interpolation kernels: npts points per option at arbitrary (tau, B) / u
     int npts;
     const double *pts_tau, *pts_B;
+    // snapshot mode (deduplicated surface sweep, faop_surface.cu): instead of pricing, the solve records every iterate
+    // whose error is a new minimum <= snap_tol_hi as a row [err, count, a_0..a_n] (a = DCT-I fit of ln(B/X)^2) and the
+    // final iterate as a catch-all row with err = 0; cfg.iter_tol is the LOWEST tolerance any sharing option needs.
+    double* snap;            // N x snap_cap x (n+3)
+    int32_t* nsnap;          // rows written per option; -1 = European shortcut (q == 0 call)
+    int snap_cap;
+    double snap_tol_hi;
 };
 
 struct EvalOut {
@@ -56,6 +63,25 @@ int launch_european_greeks(int64_t N, const double* tau, const double* S, const 
 int launch_cheb_fit(int64_t N, int n, const double* y, double* a, cudaStream_t st);
 int launch_cheb_eval(int64_t N, int n, int npts, const double* a, const double* z, double* out, cudaStream_t st);
 
+// deduplicated surface sweep (faop_surface.cu)
+struct SurfArgs {
+    faop_cfg cfg;
+    TableLayout tl;
+    faop_surface s;
+    double stepK, stepT, stepV;
+    int64_t first, count;    // flat option range to price
+    int g_lo, g_cnt;         // groups (iT*nV + iV) solved: [g_lo, g_lo + g_cnt)
+    int iK_lo, iK_hi;        // strike rows touched by the range
+    const double* tables;
+    const double* snap;
+    const int32_t* nsnap;
+    int snap_cap;
+    double* price;
+    int32_t* iters;
+};
+int launch_surface_groups(const SurfArgs& a, double* r, double* q, double* sigma, double* K, double* T, uint8_t* is_put,
+                          cudaStream_t st);
+int launch_surface_price(const SurfArgs& a, cudaStream_t st);
 int launch_surface_decode(const faop_surface& s, int64_t first, int64_t count, double* r, double* q, double* sigma,
                           double* K, double* T, double* S, uint8_t* is_put, cudaStream_t st);
 int launch_dev_math(int kind, int64_t N, const double* x, double* out, cudaStream_t st);

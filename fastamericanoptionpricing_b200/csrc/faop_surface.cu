@@ -1,0 +1,158 @@
+// faop_surface.cu — deduplicated implied-surface sweep (BASELINE.json configs[4]).
+//
+// The early-exercise boundary is homogeneous of degree one in the strike: B(tau; K) = K b(tau), with b depending on
+// (r, q, sigma, T, type) only — the QD residual (QDplusAmericanOptionSolver.py:110-125) and f = K e^{-(r-q)tau} N/D
+// (FastAmericanOptionSolverBase.py:267-279) both scale with K, so every Jacobi iterate does.  All strikes of a surface
+// that share (T, sigma) therefore share ONE boundary solve at K = 1 and differ only in
+//   * how many sweeps the reference would have run: its stopping rule ||B_old - B_new||_2 <= iter_tol (:119) is absolute,
+//     i.e. K e_j <= tol for the normalised error e_j, so a strike stops at the first iterate with e_j <= tol / K.  The
+//     solve (snapshot mode of the boundary kernels) records every iterate that is a new error minimum below tol / K_min
+//     and runs on until tol / K_max; each strike picks the first recorded iterate that satisfies its own threshold;
+//   * the m-point price integral (american_value_with_known_boundary, :92-103), evaluated here.
+// Price kernel: one CTA per (T, sigma) group, one thread per strike.  Everything that does not depend on the strike is
+// tabulated once per group in shared memory: sqrt(H(u_k)) for every recorded iterate (Clenshaw on the stored Chebyshev
+// coefficients), the discounted weights and the d+- coefficients of the m quadrature points.  Per strike and point the
+// work left is two FMAs and two Phi evaluations.
+#include "faop_alo.cuh"
+#include "faop_fastmath.cuh"
+#include "faop_kernels.h"
+
+namespace faop {
+
+constexpr int kSurfThreads = 256;
+
+FAOP_D double lin_at(int i, int n, double lo, double hi, double step) {   // numpy.linspace arithmetic
+    return (i == n - 1 && n > 1) ? hi : __dadd_rn(__dmul_rn((double)i, step), lo);
+}
+
+// Group parameters (K = 1) for the seed and boundary kernels: group g = iT * nV + iV.
+__global__ void __launch_bounds__(256) surface_groups_kernel(SurfArgs a, double* r, double* q, double* sigma, double* K,
+                                                             double* T, uint8_t* is_put) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= a.g_cnt) return;
+    const int g = a.g_lo + j;
+    const int iV = g % a.s.nV, iT = g / a.s.nV;
+    r[j] = a.s.r;
+    q[j] = a.s.q;
+    K[j] = 1.0;
+    T[j] = lin_at(iT, a.s.nT, a.s.T0, a.s.T1, a.stepT);
+    sigma[j] = lin_at(iV, a.s.nV, a.s.V0, a.s.V1, a.stepV);
+    is_put[j] = (uint8_t)(a.s.is_put != 0);
+}
+
+// Phi(-om d) for the pair (d-, d+): Phi(y) = E G(|y|) for y <= 0, 1 - E G(|y|) otherwise, with x = y / sqrt2,
+// E = exp(-x^2), G = erfcx(|x|)/2 (full-accuracy fits of faop_fastmath.cuh).
+FAOP_D void phi_pair(double y0, double y1, double& P0, double& P1) {
+    const double x[2] = {y0 * kInvSqrt2, y1 * kInvSqrt2};
+    double ex[2] = {-x[0] * x[0], -x[1] * x[1]}, xa[2] = {fabs(x[0]), fabs(x[1])}, E[2], G[2];
+    fast_exp_n<2, false>(ex, E);
+    half_erfcx_n<2, false>(xa, G);
+    const double c0 = E[0] * G[0], c1 = E[1] * G[1];
+    P0 = (y0 <= 0.0) ? c0 : 1.0 - c0;
+    P1 = (y1 <= 0.0) ? c1 : 1.0 - c1;
+}
+
+__global__ void __launch_bounds__(kSurfThreads) surface_price_kernel(SurfArgs a) {
+    extern __shared__ double smem[];
+    const TableLayout tl = a.tl;
+    const int n = tl.n, MP = tl.MP, cap = a.snap_cap;
+    double* s_A = smem;            // w h tau r e^{-r tau h^2}        (times K per strike)
+    double* s_Bq = s_A + MP;       // w h tau q S e^{-q tau h^2}
+    double* s_inv = s_Bq + MP;     // 1 / (sigma sqrt(tau) h)
+    double* s_apch = s_inv + MP;   // ((r-q) + sigma^2/2) sqrt(tau) h / sigma
+    double* s_ssuh = s_apch + MP;  // sigma sqrt(tau) h
+    double* s_e = s_ssuh + MP;     // [cap] recorded errors
+    double* s_cnt = s_e + cap;     // [cap] sweep counts
+    double* s_root = s_cnt + cap;  // [cap][MP] sqrt(max(0, H(u_k)))
+    const double* g_wm = a.tables + tl.off_wm;
+    const double* g_hm = a.tables + tl.off_hm;
+    const double* g_sgm = a.tables + tl.off_sgm;
+    const bool put = a.s.is_put != 0;
+    const double om = put ? 1.0 : -1.0;
+    const double r = a.s.r, q = a.s.q, S = a.s.S;
+    const double x0 = b_at_zero(r, q, 1.0, put);
+    const int64_t rowlen = (int64_t)a.s.nT * a.s.nV;
+
+    for (int j = blockIdx.x; j < a.g_cnt; j += gridDim.x) {
+        const int g = a.g_lo + j;
+        const int iV = g % a.s.nV, iT = g / a.s.nV;
+        const double T = lin_at(iT, a.s.nT, a.s.T0, a.s.T1, a.stepT);
+        const double sg = lin_at(iV, a.s.nV, a.s.V0, a.s.V1, a.stepV);
+        const int ns = a.nsnap[j];
+        const double* snap = a.snap + (int64_t)j * cap * (n + 3);
+        const double sqt = sqrt(T), ssu = sg * sqt, cinv = 1.0 / ssu, apc = ((r - q) + 0.5 * sg * sg) * sqt / sg;
+        __syncthreads();   // previous group's tables are no longer read
+        for (int k = threadIdx.x; k < MP; k += kSurfThreads) {
+            const double h = g_hm[k], wh = g_wm[k] * h * T, h2 = h * h;
+            s_A[k] = wh * r * exp(-r * T * h2);
+            s_Bq[k] = wh * q * S * exp(-q * T * h2);
+            s_inv[k] = cinv / h;
+            s_apch[k] = apc * h;
+            s_ssuh[k] = ssu * h;
+        }
+        for (int e = threadIdx.x; e < ns; e += kSurfThreads) {
+            s_e[e] = snap[e * (n + 3)];
+            s_cnt[e] = snap[e * (n + 3) + 1];
+        }
+        for (int e = threadIdx.x; e < ns * MP; e += kSurfThreads) {
+            const int sidx = e / MP, k = e - sidx * MP;
+            // z = sqrt(4 u / T) - 1 with u = T g_k (t = 0): 2 sqrt(g_k) - 1 (to_cheby_point, Base.py:235-237)
+            const double z = fma(2.0, g_sgm[k], -1.0);
+            const double Hu = clenshaw(n, snap + sidx * (n + 3) + 2, z);
+            s_root[e] = sqrt(Hu < 0.0 ? 0.0 : Hu);    // NaN propagates
+        }
+        __syncthreads();
+        for (int iK = a.iK_lo + threadIdx.x; iK <= a.iK_hi; iK += kSurfThreads) {
+            const int64_t flat = (int64_t)iK * rowlen + g;
+            if (flat < a.first || flat >= a.first + a.count) continue;
+            const double K = lin_at(iK, a.s.nK, a.s.K0, a.s.K1, a.stepK);
+            const double eur = euro_value(T, S, r, q, sg, K, put);
+            double v = eur;
+            int its = 0;
+            if (ns >= 0 && T != 0) {       // ns < 0: European shortcut; tau == 0: quadrature_sum returns 0
+                int sidx = ns - 1;
+                for (int e = 0; e < ns - 1; ++e)
+                    if (s_e[e] * K <= a.cfg.iter_tol) { sidx = e; break; }   // first recorded iterate the strike accepts
+                its = (int)s_cnt[sidx];
+                const double* root = s_root + sidx * MP;
+                const double LS = log(S / (K * x0));
+                double accA = 0.0, accB = 0.0;
+                for (int k = 0; k < MP; ++k) {
+                    const double lnz = fma(om, root[k], LS);
+                    const double dp = fma(lnz, s_inv[k], s_apch[k]);
+                    const double dm = dp - s_ssuh[k];
+                    double Pm, Pp;
+                    phi_pair(-om * dm, -om * dp, Pm, Pp);
+                    accA = fma(s_A[k], Pm, accA);
+                    accB = fma(s_Bq[k], Pp, accB);
+                }
+                v = eur + om * (K * accA - accB);      // v_integrand_12, Base.py:211-219
+            } else if (ns >= 0) {
+                its = (int)s_cnt[ns - 1];
+            }
+            a.price[flat - a.first] = v;
+            if (a.iters) a.iters[flat - a.first] = its;
+        }
+    }
+}
+
+int launch_surface_groups(const SurfArgs& a, double* r, double* q, double* sigma, double* K, double* T, uint8_t* is_put,
+                          cudaStream_t st) {
+    if (a.g_cnt == 0) return 0;
+    surface_groups_kernel<<<(a.g_cnt + 255) / 256, 256, 0, st>>>(a, r, q, sigma, K, T, is_put);
+    count_launch();
+    return launch_status();
+}
+
+int launch_surface_price(const SurfArgs& a, cudaStream_t st) {
+    if (a.g_cnt == 0 || a.count == 0) return 0;
+    const size_t sm = sizeof(double) * (size_t)(5 * a.tl.MP + 2 * a.snap_cap + a.snap_cap * a.tl.MP);
+    if (sm > 48 * 1024)
+        FAOP_CUDA_OK(cudaFuncSetAttribute(surface_price_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    const int grid = a.g_cnt < kSMs * 8 ? a.g_cnt : kSMs * 8;
+    surface_price_kernel<<<grid, kSurfThreads, sm, st>>>(a);
+    count_launch();
+    return launch_status();
+}
+
+}  // namespace faop

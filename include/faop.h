@@ -105,6 +105,20 @@ int faop_alo_surface_batch(const faop_cfg* cfg, const faop_surface* surf, int64_
                            const void* tables_dev, double* price, int32_t* iters /* nullable */,
                            void* workspace, size_t workspace_bytes, void* cuda_stream);
 
+/* The same sweep with the boundary solves deduplicated: the early-exercise boundary is homogeneous of
+ * degree one in the strike, so all strikes sharing (T, sigma) share one solve at K = 1; the reference's ABSOLUTE
+ * stopping rule (FastAmericanOptionSolverBase.py:119) is honoured per strike (a strike takes the first iterate whose
+ * error, scaled by K, is <= iter_tol), then every option gets its own price integral (:92-103).  Same index order,
+ * outputs and argument meaning as faop_alo_surface_batch; prices agree with it to rounding (<= 1e-9 absolute).
+ * Not available with use_derivative (FAOP_ERANGE).  Exact while a group records < 48 iterates between the loosest and
+ * the tightest threshold (always, unless the sweep contracts slower than ~0.98 per iteration).
+ * Workspace: faop_alo_surface_dedup_workspace_bytes for the same (first, count).                                      */
+int faop_alo_surface_dedup_workspace_bytes(const faop_cfg* cfg, const faop_surface* surf, int64_t first, int64_t count,
+                                           size_t* bytes);
+int faop_alo_surface_dedup_batch(const faop_cfg* cfg, const faop_surface* surf, int64_t first, int64_t count,
+                                 const void* tables_dev, double* price, int32_t* iters /* nullable */,
+                                 void* workspace, size_t workspace_bytes, void* cuda_stream);
+
 /* N, D, N', D', f, f' (and the damped update B_new) at `npts` arbitrary (tau, Q) points per option on a GIVEN
  * boundary B (N x (n+1)) — one Jacobi sweep's internals:
  * FastAmericanOptionSolver.compute_f_and_fprime / N_func / D_func / Nprime_func / Dprime_func /

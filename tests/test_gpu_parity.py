@@ -568,3 +568,57 @@ def test_bjerksund_stensland():
     assert abs(o1.phi(S[i], T[i], 1, K[i], z["X"][i]) - ph[i, 2]) <= 1e-11 * (1 + abs(ph[i, 2]))
     assert abs(BksdStld.cdf(0.3) - 0.6179114221889526) <= 1e-15
     assert np.max(np.abs(o1.price(S[:7]) - np.array([o.item() for o in [batch.bjerksund_stensland_batch(S[j], r[i], q[i], sg[i], K[i], T[i])[0].cpu() for j in range(7)]]))) == 0
+
+
+def _surface_arrays(s, first, count):
+    i = np.arange(first, first + count, dtype=np.int64)
+    iV, iT, iK = i % s["nV"], (i // s["nV"]) % s["nT"], i // (s["nV"] * s["nT"])
+    n = len(i)
+    return [np.full(n, s["r"]), np.full(n, s["q"]), np.linspace(s["V0"], s["V1"], s["nV"])[iV],
+            np.linspace(s["K0"], s["K1"], s["nK"])[iK], np.linspace(s["T0"], s["T1"], s["nT"])[iT], np.full(n, s["S"]),
+            np.full(n, bool(s.get("is_put", 1)))]
+
+
+@pytest.mark.parametrize("cfgk", [dict(wl.C5_CFG), dict(wl.C5_CFG, kernel=1), dict(solver="A", n=10, l=20, m=40, iter_tol=1e-5, max_iters=30),
+                                  dict(solver="B", n=12, l=24, m=48, iter_tol=1e-6, max_iters=60)])
+def test_surface_dedup_matches_plain_sweep(cfgk):
+    """one boundary solve per (T, sigma) shared by all strikes (B = K b) with the reference's absolute
+    stopping rule honoured per strike == every option solved on its own: same sweep counts, prices to 1e-9 (observed
+    ~1e-12), also against the C oracle, for puts and calls, whole surfaces and ragged sub-ranges."""
+    from oracle import c_oracle as co
+    cfg = AloConfig(**cfgk)
+    for is_put, q in ((1, 0.01), (0, 0.05), (1, 0.07), (0, 0.0)):
+        surf = dict(K0=50.0, K1=150.0, T0=1.0 / 52, T1=3.0, V0=0.12, V1=0.60, S=100.0, r=0.04, q=q, nK=37, nT=11, nV=7,
+                    is_put=is_put)
+        total = surf["nK"] * surf["nT"] * surf["nV"]
+        plain, it0 = batch.surface_batch(surf, 0, total, cfg, want_iters=True)
+        got, it1 = batch.surface_batch(surf, 0, total, cfg, want_iters=True, dedup=True)
+        fin = torch.isfinite(plain)
+        assert torch.equal(fin, torch.isfinite(got)) and fin.float().mean() > 0.95
+        assert (plain - got)[fin].abs().max().item() <= PRICE_ABS_TOL, (cfgk, is_put, (plain - got)[fin].abs().max().item())
+        assert (it0 != it1).float().mean().item() <= 2e-3, (cfgk, is_put)
+        if q != 0.0 or is_put:
+            assert it0.unique().numel() >= 2        # the absolute rule really splits the strikes of a group
+        a = _surface_arrays(surf, 0, total)
+        ref = co.alo_price_batch(cfg.solver, *a, n=cfg.n, l=cfg.l, m=cfg.m, iter_tol=cfg.iter_tol, max_iters=cfg.max_iters)
+        ps = np.isfinite(ref["price"]) & ((ref["err"] < 1e-2) | (ref["iters"] == 0))
+        assert np.abs(got.cpu().numpy() - ref["price"])[ps].max() <= PRICE_ABS_TOL
+        # ragged ranges: inside one strike row, across a row edge, the tail
+        G = surf["nT"] * surf["nV"]
+        for first, count in ((5, 40), (3 * G + 20, G - 30), (2 * G - 9, 3 * G + 17), (total - 61, 61), (G, G), (7, 1)):
+            part, itp = batch.surface_batch(surf, first, count, cfg, want_iters=True, dedup=True)
+            d = (part - got[first:first + count])[fin[first:first + count]].abs()
+            assert d.numel() == 0 or d.max().item() <= PRICE_ABS_TOL, (first, count)   # thresholds of the sub-range differ
+            assert (itp != it1[first:first + count]).float().mean().item() <= 0.02
+
+
+def test_surface_dedup_c5_slice():
+    """Full-size C5 geometry: a slab of whole strike rows from the deduplicated sweep against the same flat range solved
+    option by option."""
+    cfg = AloConfig(**wl.C5_CFG)
+    surf = dict(K0=50.0, K1=150.0, T0=1.0 / 52, T1=3.0, V0=0.10, V1=0.60, S=100.0, r=0.04, q=0.01, nK=1000, nT=1000, nV=100)
+    first, count = 499 * 100_000, 200_000
+    got, it1 = batch.surface_batch(surf, first, count, cfg, want_iters=True, dedup=True)
+    plain, it0 = batch.surface_batch(surf, first, count, cfg, want_iters=True)
+    assert torch.isfinite(got).all() and (got - plain).abs().max().item() <= PRICE_ABS_TOL
+    assert (it0 != it1).float().mean().item() <= 1e-4

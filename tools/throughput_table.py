@@ -38,6 +38,10 @@ surf = dict(K0=50.0, K1=150.0, T0=1.0 / 52, T1=3.0, V0=0.10, V1=0.60, S=100.0, r
 N5 = 4_000_000
 ms, out = timeit(lambda: batch.surface_batch(surf, 48_000_000, N5, AloConfig(**wl.C5_CFG), want_iters=True), reps=2)
 rows.append(("C5 surface slice [48M, 52M) decoded on device", N5, ms, N5 / ms * 1e3, float(out[1].double().mean()), int(torch.isnan(out[0]).sum())))
+N5d = 100_000_000
+buf = torch.empty(N5d, dtype=torch.float64, device="cuda")
+ms, out = timeit(lambda: batch.surface_batch(surf, 0, N5d, AloConfig(**wl.C5_CFG), dedup=True, out=buf), reps=3)
+rows.append(("C5 full 100M surface, boundary solves deduplicated", N5d, ms, N5d / ms * 1e3, float("nan"), int(torch.isnan(out).sum())))
 print("%-55s %10s %10s %14s %8s %6s" % ("config", "options", "ms", "options/s", "mean_it", "nan"))
 for r in rows:
     print("%-55s %10d %10.1f %14.0f %8.2f %6d" % r)
