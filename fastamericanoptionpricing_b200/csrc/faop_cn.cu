@@ -80,40 +80,57 @@ __device__ __forceinline__ MaxAff shfl_down_map(const MaxAff& m, int d) {
     return {__shfl_down_sync(kFullMask, m.A, d), __shfl_down_sync(kFullMask, m.B, d), __shfl_down_sync(kFullMask, m.C, d)};
 }
 
+// Everything that depends only on (option, dt) is computed once per distinct dt (normally once per option): the scaled
+// rows Q_i = alpha_i/den_i, O_i = (1-beta_i)/den_i, R_i = gamma_i/den_i of the elimination, and the A-components (products
+// of Q resp. R) of every composed map the two scans form — thread-local, per shuffle level, per warp.  A time step then
+// only moves the B (and, projected, C) components: one FMA per composition.  Q, R, X, the payoff and D live in registers,
+// O in shared memory; three barriers per step (halo exchange, forward warp totals, backward warp totals + closure data).
 template <int NPT, bool PROJ>
 __global__ void __launch_bounds__(kCnThreads, (NPT <= 8 ? 2 : 1)) cn_scan_kernel(CnArgs a) {
     constexpr int NS = kCnThreads * NPT;  // padded node slots
+    constexpr double kNegBig = -1.79e308;
     extern __shared__ double sm[];
-    double* s_alpha = sm;                // [j * T + t] for node t*NPT + j
-    double* s_gamma = s_alpha + NS;
-    double* s_omb = s_gamma + NS;        // 1 - beta
-    double* s_rden = s_omb + NS;         // 1 / (1 + beta + alpha c'_{i-1})
-    double* s_seq = s_rden + NS;         // natural-order scratch (c' recurrence, closure, fallback back-substitution)
-    double* s_edgeL = s_seq + NS;        // first X of every thread
-    double* s_edgeR = s_edgeL + kCnThreads;
-    double* s_wmap = s_edgeR + kCnThreads;   // warp totals: up to 3 doubles per warp
-    double* s_misc = s_wmap + 3 * kCnWarps;  // [0] X_{N-1}, [1] flag: some R_i < 0 outside thread 0
+    double* s_Q = sm;                    // [j * T + t] for node t*NPT + j
+    double* s_R = s_Q + NS;
+    double* s_O = s_R + NS;
+    double* s_seq = s_O + NS;            // natural-order scratch (c' recurrence, fallback back-substitution)
+    double* s_G = s_seq + NS;            // payoff K - S_i, [j * T + t]
+    double* s_eL = s_G + NS;             // [warp] X of the warp's first node / last node (halo of the neighbours)
+    double* s_eR = s_eL + kCnWarps;
+    double* s_fwA = s_eR + kCnWarps;     // forward warp totals: A (per dt) and B (per step)
+    double* s_fwB = s_fwA + kCnWarps;
+    double* s_bwA = s_fwB + kCnWarps;    // backward warp totals: A (per dt), B and C (per step)
+    double* s_bwB = s_bwA + kCnWarps;
+    double* s_bwC = s_bwB + kCnWarps;
+    double* s_clo = s_bwC + kCnWarps;    // D_{N-4}, D_{N-3}, D_{N-2}
+    double* s_misc = s_clo + 4;          // [0] flag: some R_i < 0 outside thread 0
 
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const int n = a.n_space;
     for (int64_t opt = blockIdx.x; opt < a.N; opt += gridDim.x) {
-        const double r = a.r[opt], q = a.q[opt], sg = a.sigma[opt], K = a.K[opt];
-        const double dS = grid_point(1, n, K) - grid_point(0, n, K);
-        double X[NPT], g[NPT];
+        double X[NPT], Q[NPT], R[NPT];
 #pragma unroll
         for (int j = 0; j < NPT; ++j) {
+            const double K = a.K[opt];
             int i = t * NPT + j;
             double S = grid_point(i < n ? i : n - 1, n, K);
-            g[j] = K - S;                         // payoff (applyConstraint, :106-107)
+            s_G[j * kCnThreads + t] = K - S;      // payoff (applyConstraint, :106-107); read by this thread only
             X[j] = (i < n) ? fmax(K - S, 0.0) : 0.0;   // setInitialCondition, :48-52
+            Q[j] = R[j] = 0.0;
         }
+        double Af[5], Ab[5], excA = 0.0, nxtA = 0.0, cR3 = 0.0, cR4 = 0.0, cinv = 0.0;
         const int nsteps = a.n_steps[opt];
         double dt_prev = -1.0;
+        __syncthreads();                          // the previous option's output pass is done with s_seq
+        if (lane == 0) s_eL[warp] = X[0];
+        if (lane == 31) s_eR[warp] = X[NPT - 1];
         for (int st = 0; st < nsteps; ++st) {
             const double dt = a.dts[opt * a.max_steps + st];
             if (dt != dt_prev) {
                 // ---- coefficients for this dt (setCoeff, :55-79) and the c' recurrence of the elimination
-                __syncthreads();
+                const double r = a.r[opt], q = a.q[opt], sg = a.sigma[opt], K = a.K[opt];   // cold path: not kept in registers
+                const double dS = grid_point(1, n, K) - grid_point(0, n, K);
+                if (t == 0) s_misc[1] = K - 3.0 * K;            // payoff at the last node (floor of X_{N-1})
 #pragma unroll
                 for (int j = 0; j < NPT; ++j) {
                     int i = t * NPT + j;
@@ -126,9 +143,9 @@ __global__ void __launch_bounds__(kCnThreads, (NPT <= 8 ? 2 : 1)) cn_scan_kernel
                         be = 0.5 * dt * (r + aa * aa);
                         ga = 0.25 * dt * (aa * aa + m);
                     }
-                    s_alpha[j * kCnThreads + t] = al;
-                    s_gamma[j * kCnThreads + t] = ga;
-                    s_omb[j * kCnThreads + t] = 1.0 - be;
+                    s_Q[j * kCnThreads + t] = al;
+                    s_R[j * kCnThreads + t] = ga;
+                    s_O[j * kCnThreads + t] = 1.0 - be;
                     s_seq[i] = 1.0 + be;          // diagonal, natural order, for the sequential recurrence below
                 }
                 __syncthreads();
@@ -137,132 +154,147 @@ __global__ void __launch_bounds__(kCnThreads, (NPT <= 8 ? 2 : 1)) cn_scan_kernel
                     double cp = 0.0;
                     int neg = 0;
                     for (int i = 0; i < n - 1; ++i) {
-                        int tt = i / NPT, jj = i - tt * NPT;
-                        double al = s_alpha[jj * kCnThreads + tt], ga = s_gamma[jj * kCnThreads + tt];
+                        int tt = i / NPT, jj = i - tt * NPT, at = jj * kCnThreads + tt;
+                        double al = s_Q[at], ga = s_R[at];
                         double den = s_seq[i] + al * cp;
                         double rd = 1.0 / den;
-                        s_rden[jj * kCnThreads + tt] = rd;
-                        cp = -ga * rd;
-                        if (ga * rd < 0.0 && tt > 0) neg = 1;
+                        double Ri = ga * rd;
+                        s_Q[at] = al * rd;
+                        s_R[at] = Ri;
+                        s_O[at] = s_O[at] * rd;
+                        cp = -Ri;
+                        if (Ri < 0.0 && tt > 0) neg = 1;
                     }
                     for (int i = n - 1; i < NS; ++i) {
-                        int tt = i / NPT, jj = i - tt * NPT;
-                        s_rden[jj * kCnThreads + tt] = 0.0;
+                        int tt = i / NPT, jj = i - tt * NPT, at = jj * kCnThreads + tt;
+                        s_Q[at] = 0.0; s_R[at] = 0.0; s_O[at] = 0.0;
                     }
-                    s_misc[1] = (double)neg;
+                    s_misc[0] = (double)neg;
                 }
                 __syncthreads();
+                // ---- step-invariant A-components of the composed maps
+                double aF = 1.0, aB = 1.0;
+#pragma unroll
+                for (int j = 0; j < NPT; ++j) {
+                    Q[j] = s_Q[j * kCnThreads + t];
+                    R[j] = s_R[j * kCnThreads + t];
+                    aF *= Q[j];
+                    if (t * NPT + j <= n - 2) aB *= R[j];
+                }
+#pragma unroll
+                for (int lv = 0; lv < 5; ++lv) {
+                    const int d = 1 << lv;
+                    Af[lv] = aF;                                   // multiplier of the incoming B at this level
+                    double o = __shfl_up_sync(kFullMask, aF, d);
+                    if (lane >= d) aF *= o;
+                    Ab[lv] = aB;
+                    o = __shfl_down_sync(kFullMask, aB, d);
+                    if (lane + d < 32) aB *= o;
+                }
+                excA = __shfl_up_sync(kFullMask, aF, 1);           // inclusive A of the lane below
+                nxtA = __shfl_down_sync(kFullMask, aB, 1);         // inclusive A of the lane above
+                if (lane == 31) s_fwA[warp] = aF;
+                if (lane == 0) s_bwA[warp] = aB;
+                {   // closure of the 4-term last row: X_{N-2..N-4} are affine in x = X_{N-1} with slopes m2, m3, m4
+                    auto Rat = [&](int i) { int tt = i / NPT, jj = i - tt * NPT; return s_R[jj * kCnThreads + tt]; };
+                    const double m2 = Rat(n - 2);
+                    cR3 = Rat(n - 3);
+                    cR4 = Rat(n - 4);
+                    const double m3 = cR3 * m2, m4 = cR4 * m3;
+                    cinv = 1.0 / (2.0 - m4 + 4.0 * m3 - 5.0 * m2);
+                }
                 dt_prev = dt;
             }
-            // ---- right-hand side b_i = alpha X_{i-1} + (1-beta) X_i + gamma X_{i+1}
-            s_edgeL[t] = X[0];
-            s_edgeR[t] = X[NPT - 1];
-            __syncthreads();
-            const double xl = (t > 0) ? s_edgeR[t - 1] : 0.0;
-            const double xr = (t < kCnThreads - 1) ? s_edgeL[t + 1] : 0.0;
-            double P[NPT], Q[NPT], R[NPT];
-#pragma unroll
-            for (int j = 0; j < NPT; ++j) {
-                const double al = s_alpha[j * kCnThreads + t], ga = s_gamma[j * kCnThreads + t];
-                const double ob = s_omb[j * kCnThreads + t], rd = s_rden[j * kCnThreads + t];
-                const double xm = (j == 0) ? xl : X[j - 1];
-                const double xp = (j == NPT - 1) ? xr : X[j + 1];
-                const double b = al * xm + ob * X[j] + ga * xp;
-                P[j] = b * rd;        // d'_i = P_i + Q_i d'_{i-1}
-                Q[j] = al * rd;
-                R[j] = ga * rd;       // X_i  = d'_i + R_i X_{i+1}
-            }
-            // ---- forward elimination as a prefix scan of affine maps
-            Aff loc = {1.0, 0.0};
-#pragma unroll
-            for (int j = 0; j < NPT; ++j) loc = compose(Aff{Q[j], P[j]}, loc);
-            Aff inc = loc;  // inclusive scan over lanes: inc_l = loc_l o ... o loc_0
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                Aff o = shfl_up_map(inc, d);
-                if (lane >= d) inc = compose(inc, o);
-            }
-            if (lane == 31) { s_wmap[2 * warp] = inc.A; s_wmap[2 * warp + 1] = inc.B; }
-            __syncthreads();
-            double din = 0.0;  // d' entering this warp
-            for (int w = 0; w < warp; ++w) din = s_wmap[2 * w] * din + s_wmap[2 * w + 1];
-            Aff exc = shfl_up_map(inc, 1);
-            double dprev = (lane == 0) ? din : apply(exc, din);
+            __syncthreads();   // halo values (and, after a dt change, the warp-level A's) are visible
+            // ---- right-hand side, already scaled by 1/den: P_i = Q_i X_{i-1} + O_i X_i + R_i X_{i+1}
+            double xl = __shfl_up_sync(kFullMask, X[NPT - 1], 1);
+            double xr = __shfl_down_sync(kFullMask, X[0], 1);
+            if (lane == 0) xl = (warp > 0) ? s_eR[warp - 1] : 0.0;
+            if (lane == 31) xr = (warp < kCnWarps - 1) ? s_eL[warp + 1] : 0.0;
             double D[NPT];
 #pragma unroll
             for (int j = 0; j < NPT; ++j) {
-                dprev = Q[j] * dprev + P[j];
-                D[j] = dprev;
+                const double xm = (j == 0) ? xl : X[j - 1];
+                const double xp = (j == NPT - 1) ? xr : X[j + 1];
+                D[j] = fma(R[j], xp, fma(s_O[j * kCnThreads + t], X[j], Q[j] * xm));   // P_j for now
             }
-            // ---- close the last row: X_{N-2}, X_{N-3}, X_{N-4} as affine functions of x = X_{N-1}
+            // ---- forward elimination d'_i = P_i + Q_i d'_{i-1}: prefix scan of the B-components
+            double b = D[0];
+#pragma unroll
+            for (int j = 1; j < NPT; ++j) b = fma(Q[j], b, D[j]);
+#pragma unroll
+            for (int lv = 0; lv < 5; ++lv) {
+                const int d = 1 << lv;
+                const double o = __shfl_up_sync(kFullMask, b, d);
+                if (lane >= d) b = fma(Af[lv], o, b);
+            }
+            if (lane == 31) s_fwB[warp] = b;
+            __syncthreads();
+            double din = 0.0;  // d' entering this warp
+            for (int w = 0; w < warp; ++w) din = fma(s_fwA[w], din, s_fwB[w]);
+            const double eb = __shfl_up_sync(kFullMask, b, 1);
+            double dprev = (lane == 0) ? din : fma(excA, din, eb);
 #pragma unroll
             for (int j = 0; j < NPT; ++j) {
-                int i = t * NPT + j;
-                if (i >= n - 4 && i <= n - 2) { s_seq[2 * (i - (n - 4))] = D[j]; s_seq[2 * (i - (n - 4)) + 1] = R[j]; }
+                dprev = fma(Q[j], dprev, D[j]);
+                D[j] = dprev;
             }
-            __syncthreads();
-            if (t == 0) {
-                double p2 = s_seq[4], m2 = s_seq[5];
-                double p3 = s_seq[2] + s_seq[3] * p2, m3 = s_seq[3] * m2;
-                double p4 = s_seq[0] + s_seq[1] * p3, m4 = s_seq[1] * m3;
-                double x = (p4 - 4.0 * p3 + 5.0 * p2) / (2.0 - m4 + 4.0 * m3 - 5.0 * m2);
-                if (PROJ) x = fmax(x, K - 3.0 * K);
-                s_misc[0] = x;
+#pragma unroll
+            for (int j = 0; j < NPT; ++j) {
+                const int i = t * NPT + j;
+                if (i >= n - 4 && i <= n - 2) s_clo[i - (n - 4)] = D[j];
             }
-            __syncthreads();
-            const double xlast = s_misc[0];
-            const bool fallback = PROJ && s_misc[1] != 0.0;
+            const bool fallback = PROJ && s_misc[0] != 0.0;
             if (!fallback) {
-                // ---- (projected) back-substitution as a suffix scan; padding nodes carry the identity map
-                double xin;
-                if (PROJ) {
-                    MaxAff locb = {1.0, 0.0, -1.79e308};
+                // ---- (projected) back-substitution X_i = max(D_i + R_i X_{i+1}, g_i): suffix scan of (B, C)
+                double B = 0.0, C = kNegBig;
 #pragma unroll
-                    for (int j = NPT - 1; j >= 0; --j) {
-                        int i = t * NPT + j;
-                        if (i <= n - 2) locb = compose(MaxAff{R[j], D[j], g[j]}, locb);
+                for (int j = NPT - 1; j >= 0; --j) {
+                    if (t * NPT + j <= n - 2) {
+                        if (PROJ) C = fmax(fma(R[j], C, D[j]), s_G[j * kCnThreads + t]);
+                        B = fma(R[j], B, D[j]);
                     }
-                    MaxAff incb = locb;  // inclusive suffix scan: incb_l = locb_l o ... o locb_31
+                }
 #pragma unroll
-                    for (int d = 1; d < 32; d <<= 1) {
-                        MaxAff o = shfl_down_map(incb, d);
-                        if (lane + d < 32) incb = compose(incb, o);
+                for (int lv = 0; lv < 5; ++lv) {
+                    const int d = 1 << lv;
+                    const double oB = __shfl_down_sync(kFullMask, B, d);
+                    double oC = 0.0;
+                    if (PROJ) oC = __shfl_down_sync(kFullMask, C, d);
+                    if (lane + d < 32) {
+                        if (PROJ) C = fmax(fma(Ab[lv], oC, B), C);
+                        B = fma(Ab[lv], oB, B);
                     }
-                    if (lane == 0) { s_wmap[3 * warp] = incb.A; s_wmap[3 * warp + 1] = incb.B; s_wmap[3 * warp + 2] = incb.C; }
-                    __syncthreads();
-                    double v = xlast;
-                    for (int w = kCnWarps - 1; w > warp; --w) v = fmax(s_wmap[3 * w] * v + s_wmap[3 * w + 1], s_wmap[3 * w + 2]);
-                    MaxAff nxt = shfl_down_map(incb, 1);
-                    xin = (lane == 31) ? v : apply(nxt, v);
-                } else {
-                    Aff locb = {1.0, 0.0};
-#pragma unroll
-                    for (int j = NPT - 1; j >= 0; --j) {
-                        int i = t * NPT + j;
-                        if (i <= n - 2) locb = compose(Aff{R[j], D[j]}, locb);
-                    }
-                    Aff incb = locb;
-#pragma unroll
-                    for (int d = 1; d < 32; d <<= 1) {
-                        Aff o = {__shfl_down_sync(kFullMask, incb.A, d), __shfl_down_sync(kFullMask, incb.B, d)};
-                        if (lane + d < 32) incb = compose(incb, o);
-                    }
-                    if (lane == 0) { s_wmap[3 * warp] = incb.A; s_wmap[3 * warp + 1] = incb.B; }
-                    __syncthreads();
-                    double v = xlast;
-                    for (int w = kCnWarps - 1; w > warp; --w) v = s_wmap[3 * w] * v + s_wmap[3 * w + 1];
-                    Aff nxt = {__shfl_down_sync(kFullMask, incb.A, 1), __shfl_down_sync(kFullMask, incb.B, 1)};
-                    xin = (lane == 31) ? v : apply(nxt, v);
+                }
+                if (lane == 0) {
+                    s_bwB[warp] = B;
+                    if (PROJ) s_bwC[warp] = C;
+                }
+                __syncthreads();
+                // last row: x = X_{N-1} from D_{N-4..N-2}
+                const double p2 = s_clo[2];
+                const double p3 = fma(cR3, p2, s_clo[1]);
+                const double p4 = fma(cR4, p3, s_clo[0]);
+                double v = (p4 - 4.0 * p3 + 5.0 * p2) * cinv;
+                if (PROJ) v = fmax(v, s_misc[1]);
+                for (int w = kCnWarps - 1; w > warp; --w) {
+                    const double y = fma(s_bwA[w], v, s_bwB[w]);
+                    v = PROJ ? fmax(y, s_bwC[w]) : y;
+                }
+                const double nB = __shfl_down_sync(kFullMask, B, 1);
+                double nC = 0.0;
+                if (PROJ) nC = __shfl_down_sync(kFullMask, C, 1);
+                double xin = v;
+                if (lane != 31) {
+                    xin = fma(nxtA, v, nB);
+                    if (PROJ) xin = fmax(xin, nC);
                 }
 #pragma unroll
                 for (int j = NPT - 1; j >= 0; --j) {
-                    int i = t * NPT + j;
-                    double xn;
-                    if (i <= n - 2) {
-                        xn = R[j] * xin + D[j];
-                        if (PROJ) xn = fmax(xn, g[j]);
-                    } else {
-                        xn = xin;   // i == n-1 holds X_{N-1}; slots beyond mirror it (never read back)
+                    double xn = xin;          // i == n-1 holds X_{N-1}; slots beyond mirror it (never read back)
+                    if (t * NPT + j <= n - 2) {
+                        xn = fma(R[j], xin, D[j]);
+                        if (PROJ) xn = fmax(xn, s_G[j * kCnThreads + t]);
                     }
                     X[j] = xn;
                     xin = xn;
@@ -273,16 +305,19 @@ __global__ void __launch_bounds__(kCnThreads, (NPT <= 8 ? 2 : 1)) cn_scan_kernel
 #pragma unroll
                 for (int j = 0; j < NPT; ++j) {
                     int i = t * NPT + j;
-                    if (i <= n - 2) { s_seq[i] = D[j]; }
+                    if (i <= n - 2) s_seq[i] = D[j];
                 }
                 __syncthreads();
                 if (t == 0) {
-                    double x = xlast;
+                    const double p2 = s_clo[2];
+                    const double p3 = fma(cR3, p2, s_clo[1]);
+                    const double p4 = fma(cR4, p3, s_clo[0]);
+                    const double K = a.K[opt];
+                    double x = fmax((p4 - 4.0 * p3 + 5.0 * p2) * cinv, s_misc[1]);
                     s_seq[n - 1] = x;
                     for (int i = n - 2; i >= 0; --i) {
                         int tt = i / NPT, jj = i - tt * NPT;
-                        double Ri = s_gamma[jj * kCnThreads + tt] * s_rden[jj * kCnThreads + tt];
-                        x = fmax(Ri * x + s_seq[i], K - grid_point(i, n, K));
+                        x = fmax(fma(s_R[jj * kCnThreads + tt], x, s_seq[i]), K - grid_point(i, n, K));
                         s_seq[i] = x;
                     }
                 }
@@ -293,7 +328,8 @@ __global__ void __launch_bounds__(kCnThreads, (NPT <= 8 ? 2 : 1)) cn_scan_kernel
                     X[j] = s_seq[i < n ? i : n - 1];
                 }
             }
-            __syncthreads();   // s_edge*, s_wmap, s_seq are reused by the next step
+            if (lane == 0) s_eL[warp] = X[0];
+            if (lane == 31) s_eR[warp] = X[NPT - 1];
         }
         // ---- output: X (optional) and np.interp(S0, S, X) (:32-34)
         __syncthreads();
@@ -306,8 +342,7 @@ __global__ void __launch_bounds__(kCnThreads, (NPT <= 8 ? 2 : 1)) cn_scan_kernel
             }
         }
         __syncthreads();
-        if (t == 0) a.price[opt] = interp_uniform(a.S0[opt], n, K, [&](int i) { return s_seq[i]; });
-        __syncthreads();
+        if (t == 0) a.price[opt] = interp_uniform(a.S0[opt], n, a.K[opt], [&](int i) { return s_seq[i]; });
     }
 }
 
@@ -377,7 +412,7 @@ __global__ void __launch_bounds__(64) cn_sor_kernel(CnArgs a) {
 template <int NPT, bool PROJ>
 static int launch_scan(const CnArgs& a, cudaStream_t st) {
     constexpr int NS = kCnThreads * NPT;
-    size_t sm = sizeof(double) * (size_t)(5 * NS + 2 * kCnThreads + 3 * kCnWarps + 8);
+    size_t sm = sizeof(double) * (size_t)(5 * NS + 7 * kCnWarps + 8);
     FAOP_CUDA_OK(cudaFuncSetAttribute(cn_scan_kernel<NPT, PROJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     int64_t grid = a.N < (int64_t)kSMs * 8 ? a.N : (int64_t)kSMs * 8;
     cn_scan_kernel<NPT, PROJ><<<(unsigned)grid, kCnThreads, sm, st>>>(a);
