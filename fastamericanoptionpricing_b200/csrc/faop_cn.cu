@@ -85,6 +85,9 @@ __device__ __forceinline__ MaxAff shfl_down_map(const MaxAff& m, int d) {
 // of Q resp. R) of every composed map the two scans form — thread-local, per shuffle level, per warp.  A time step then
 // only moves the B (and, projected, C) components: one FMA per composition.  Q, R, X, the payoff and D live in registers,
 // O in shared memory; three barriers per step (halo exchange, forward warp totals, backward warp totals + closure data).
+// max without fmax's NaN canonicalisation (one DSETP + two selects): the operands here are never NaN unless the inputs are
+__device__ __forceinline__ double dmax(double x, double y) { return x > y ? x : y; }
+
 template <int NPT, bool PROJ>
 __global__ void __launch_bounds__(kCnThreads, (NPT <= 8 ? 2 : 1)) cn_scan_kernel(CnArgs a) {
     constexpr int NS = kCnThreads * NPT;  // padded node slots
@@ -128,6 +131,7 @@ __global__ void __launch_bounds__(kCnThreads, (NPT <= 8 ? 2 : 1)) cn_scan_kernel
             const double dt = a.dts[opt * a.max_steps + st];
             if (dt != dt_prev) {
                 // ---- coefficients for this dt (setCoeff, :55-79) and the c' recurrence of the elimination
+                __syncthreads();   // nobody still reads the previous dt's rows or s_seq
                 const double r = a.r[opt], q = a.q[opt], sg = a.sigma[opt], K = a.K[opt];   // cold path: not kept in registers
                 const double dS = grid_point(1, n, K) - grid_point(0, n, K);
                 if (t == 0) s_misc[1] = K - 3.0 * K;            // payoff at the last node (floor of X_{N-1})
@@ -184,10 +188,12 @@ __global__ void __launch_bounds__(kCnThreads, (NPT <= 8 ? 2 : 1)) cn_scan_kernel
 #pragma unroll
                 for (int lv = 0; lv < 5; ++lv) {
                     const int d = 1 << lv;
-                    Af[lv] = aF;                                   // multiplier of the incoming B at this level
+                    // multiplier of the incoming B at this level; 0 where the lane has no partner, so that the
+                    // per-step update is an unconditional FMA
+                    Af[lv] = (lane >= d) ? aF : 0.0;
                     double o = __shfl_up_sync(kFullMask, aF, d);
                     if (lane >= d) aF *= o;
-                    Ab[lv] = aB;
+                    Ab[lv] = (lane + d < 32) ? aB : 0.0;
                     o = __shfl_down_sync(kFullMask, aB, d);
                     if (lane + d < 32) aB *= o;
                 }
@@ -225,8 +231,7 @@ __global__ void __launch_bounds__(kCnThreads, (NPT <= 8 ? 2 : 1)) cn_scan_kernel
 #pragma unroll
             for (int lv = 0; lv < 5; ++lv) {
                 const int d = 1 << lv;
-                const double o = __shfl_up_sync(kFullMask, b, d);
-                if (lane >= d) b = fma(Af[lv], o, b);
+                b = fma(Af[lv], __shfl_up_sync(kFullMask, b, d), b);
             }
             if (lane == 31) s_fwB[warp] = b;
             __syncthreads();
@@ -251,7 +256,7 @@ __global__ void __launch_bounds__(kCnThreads, (NPT <= 8 ? 2 : 1)) cn_scan_kernel
 #pragma unroll
                 for (int j = NPT - 1; j >= 0; --j) {
                     if (t * NPT + j <= n - 2) {
-                        if (PROJ) C = fmax(fma(R[j], C, D[j]), s_G[j * kCnThreads + t]);
+                        if (PROJ) C = dmax(fma(R[j], C, D[j]), s_G[j * kCnThreads + t]);
                         B = fma(R[j], B, D[j]);
                     }
                 }
@@ -261,10 +266,8 @@ __global__ void __launch_bounds__(kCnThreads, (NPT <= 8 ? 2 : 1)) cn_scan_kernel
                     const double oB = __shfl_down_sync(kFullMask, B, d);
                     double oC = 0.0;
                     if (PROJ) oC = __shfl_down_sync(kFullMask, C, d);
-                    if (lane + d < 32) {
-                        if (PROJ) C = fmax(fma(Ab[lv], oC, B), C);
-                        B = fma(Ab[lv], oB, B);
-                    }
+                    if (PROJ && lane + d < 32) C = dmax(fma(Ab[lv], oC, B), C);
+                    B = fma(Ab[lv], oB, B);
                 }
                 if (lane == 0) {
                     s_bwB[warp] = B;
@@ -276,10 +279,10 @@ __global__ void __launch_bounds__(kCnThreads, (NPT <= 8 ? 2 : 1)) cn_scan_kernel
                 const double p3 = fma(cR3, p2, s_clo[1]);
                 const double p4 = fma(cR4, p3, s_clo[0]);
                 double v = (p4 - 4.0 * p3 + 5.0 * p2) * cinv;
-                if (PROJ) v = fmax(v, s_misc[1]);
+                if (PROJ) v = dmax(v, s_misc[1]);
                 for (int w = kCnWarps - 1; w > warp; --w) {
                     const double y = fma(s_bwA[w], v, s_bwB[w]);
-                    v = PROJ ? fmax(y, s_bwC[w]) : y;
+                    v = PROJ ? dmax(y, s_bwC[w]) : y;
                 }
                 const double nB = __shfl_down_sync(kFullMask, B, 1);
                 double nC = 0.0;
@@ -287,14 +290,14 @@ __global__ void __launch_bounds__(kCnThreads, (NPT <= 8 ? 2 : 1)) cn_scan_kernel
                 double xin = v;
                 if (lane != 31) {
                     xin = fma(nxtA, v, nB);
-                    if (PROJ) xin = fmax(xin, nC);
+                    if (PROJ) xin = dmax(xin, nC);
                 }
 #pragma unroll
                 for (int j = NPT - 1; j >= 0; --j) {
                     double xn = xin;          // i == n-1 holds X_{N-1}; slots beyond mirror it (never read back)
                     if (t * NPT + j <= n - 2) {
                         xn = fma(R[j], xin, D[j]);
-                        if (PROJ) xn = fmax(xn, s_G[j * kCnThreads + t]);
+                        if (PROJ) xn = dmax(xn, s_G[j * kCnThreads + t]);
                     }
                     X[j] = xn;
                     xin = xn;
@@ -313,11 +316,11 @@ __global__ void __launch_bounds__(kCnThreads, (NPT <= 8 ? 2 : 1)) cn_scan_kernel
                     const double p3 = fma(cR3, p2, s_clo[1]);
                     const double p4 = fma(cR4, p3, s_clo[0]);
                     const double K = a.K[opt];
-                    double x = fmax((p4 - 4.0 * p3 + 5.0 * p2) * cinv, s_misc[1]);
+                    double x = dmax((p4 - 4.0 * p3 + 5.0 * p2) * cinv, s_misc[1]);
                     s_seq[n - 1] = x;
                     for (int i = n - 2; i >= 0; --i) {
                         int tt = i / NPT, jj = i - tt * NPT;
-                        x = fmax(fma(s_R[jj * kCnThreads + tt], x, s_seq[i]), K - grid_point(i, n, K));
+                        x = dmax(fma(s_R[jj * kCnThreads + tt], x, s_seq[i]), K - grid_point(i, n, K));
                         s_seq[i] = x;
                     }
                 }
