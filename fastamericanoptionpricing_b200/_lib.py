@@ -33,6 +33,8 @@ _SIGNATURES = {
     "faop_alo_surface_batch": (ctypes.c_int, [_P(FaopCfg), _P(FaopSurface), c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
     "faop_alo_surface_dedup_workspace_bytes": (ctypes.c_int, [_P(FaopCfg), _P(FaopSurface), c_i64, c_i64, _P(c_sz)]),
     "faop_alo_surface_dedup_batch": (ctypes.c_int, [_P(FaopCfg), _P(FaopSurface), c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
+    "faop_alo_ladder_workspace_bytes": (ctypes.c_int, [_P(FaopCfg), c_i64, _P(c_sz)]),
+    "faop_alo_ladder_batch": (ctypes.c_int, [_P(FaopCfg), c_i64] + [c_vp] * 6 + [c_i32, c_vp, c_dbl, c_dbl] + [c_vp] * 4 + [c_sz, c_vp]),
     "faop_alo_eval_points_batch": (ctypes.c_int, [_P(FaopCfg), c_i64, c_i32] + [c_vp] * 20),
     "faop_alo_interp_boundary_batch": (ctypes.c_int, [_P(FaopCfg), c_i64, c_i32] + [c_vp] * 10),
     "faop_alo_price_known_boundary_batch": (ctypes.c_int, [_P(FaopCfg), c_i64] + [c_vp] * 13),

@@ -268,6 +268,33 @@ def surface_batch(surface: dict, first, count, cfg: AloConfig, want_iters=False,
         return (price, iters) if want_iters else price
 
 
+def ladder_batch(r, q, sigma, T, S, is_put, K, cfg: AloConfig = AloConfig(), want_iters=False, device=None, out=None):
+    """Strike ladder: G scenarios (r, q, sigma, T, S, is_put) x the strikes K[0..nK) -> price[G, nK] (and iters).
+    One boundary solve per scenario is shared by all of its strikes (the boundary scales with K); each price is what
+    FastAmericanOptionSolver(r, q, sigma, K_k, T, type).solve(0, S) returns, to rounding (faop_alo_ladder_batch)."""
+    lib = _lib.load()
+    dev, G, (r, q, sigma, T, S) = _common([r, q, sigma, T, S], device)
+    with torch.cuda.device(dev):
+        ip = _u8(is_put, dev, G)
+        Kh = np.ascontiguousarray(np.atleast_1d(K.detach().cpu().numpy() if isinstance(K, torch.Tensor) else np.asarray(K, dtype=np.float64)),
+                                  dtype=np.float64).reshape(-1)
+        nK = Kh.shape[0]
+        Kd = _f64(K, dev)
+        price = torch.empty((G, nK), dtype=torch.float64, device=dev) if out is None else out
+        iters = torch.empty((G, nK), dtype=torch.int32, device=dev) if want_iters else None
+        if G == 0 or nK == 0:
+            return (price, iters) if want_iters else price
+        tab = tables_for(cfg, dev)
+        c = cfg.c()
+        nb = ctypes.c_size_t()
+        check(lib.faop_alo_ladder_workspace_bytes(ctypes.byref(c), G, ctypes.byref(nb)), "faop_alo_ladder_workspace_bytes")
+        ws = torch.empty(max(nb.value, 256), dtype=torch.uint8, device=dev)
+        check(lib.faop_alo_ladder_batch(ctypes.byref(c), G, _ptr(r), _ptr(q), _ptr(sigma), _ptr(T), _ptr(S), _ptr(ip), nK,
+                                        _ptr(Kd), float(Kh.min()), float(Kh.max()), _ptr(tab), _ptr(price), _ptr(iters),
+                                        _ptr(ws), ws.numel(), _stream(dev)), "faop_alo_ladder_batch")
+        return (price, iters) if want_iters else price
+
+
 # ------------------------------------------------------------------------------------------ leaf kernels
 def _common(arrs, device):
     dev = _device(device)

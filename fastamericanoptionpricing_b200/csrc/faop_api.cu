@@ -274,6 +274,64 @@ int faop_alo_surface_dedup_batch(const faop_cfg* cfg, const faop_surface* surf, 
     return launch_surface_price(sa, st);
 }
 
+// Strike ladder: G scenarios x nK strikes, one boundary solve per scenario (same machinery as the deduplicated surface).
+static size_t ladder_ws_bytes(const faop_cfg* cfg, int64_t G) {
+    const size_t nn = (size_t)cfg->n_colloc + 1, cap = (size_t)surf_snap_cap(cfg);
+    return sizeof(double) * ((size_t)G * (1 + nn + cap * (nn + 2))) + sizeof(int32_t) * (((size_t)G + 1) & ~(size_t)1);
+}
+int faop_alo_ladder_workspace_bytes(const faop_cfg* cfg, int64_t G, size_t* bytes) {
+    int rc = check_cfg(cfg);
+    if (rc) return rc;
+    if (!bytes || G < 0) return FAOP_EINVAL;
+    *bytes = (ladder_ws_bytes(cfg, G) + 255) & ~(size_t)255;
+    return 0;
+}
+int faop_alo_ladder_batch(const faop_cfg* cfg, int64_t G, const double* r, const double* q, const double* sigma,
+                          const double* T, const double* S, const uint8_t* is_put, int32_t nK, const double* K,
+                          double K_min, double K_max, const void* tables_dev, double* price, int32_t* iters,
+                          void* workspace, size_t workspace_bytes, void* cuda_stream) {
+    int rc = check_cfg(cfg);
+    if (rc) return rc;
+    if (G < 0 || nK < 0 || G > 0x7fffffff) return FAOP_EINVAL;
+    if (cfg->use_derivative) return FAOP_ERANGE;
+    if (G == 0 || nK == 0) return 0;
+    if (!r || !q || !sigma || !T || !S || !is_put || !K || !price || !workspace || !tables_dev) return FAOP_EINVAL;
+    if (!(K_min > 0) || !(K_max >= K_min)) return FAOP_EINVAL;
+    if (workspace_bytes < ladder_ws_bytes(cfg, G)) return FAOP_EINVAL;
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    const size_t nn = (size_t)cfg->n_colloc + 1;
+    SurfArgs sa;
+    memset(&sa, 0, sizeof sa);
+    sa.cfg = *cfg;
+    sa.tl = table_layout(cfg->n_colloc, cfg->n_quad, cfg->n_price_quad);
+    sa.g_cnt = (int)G;
+    sa.snap_cap = surf_snap_cap(cfg);
+    double* w = (double*)workspace;
+    double* d_K1 = w;                       // the unit strike of the normalised solves
+    double* d_seed = w + G;
+    double* d_snap = d_seed + (size_t)G * nn;
+    int32_t* d_ns = (int32_t*)(d_snap + (size_t)G * (size_t)sa.snap_cap * (nn + 2));
+    sa.tables = (const double*)tables_dev;
+    sa.snap = d_snap; sa.nsnap = d_ns; sa.price = price; sa.iters = iters;
+    sa.g_r = r; sa.g_q = q; sa.g_sigma = sigma; sa.g_T = T; sa.g_S = S; sa.g_put = is_put; sa.ladder = K; sa.nK = nK;
+    rc = launch_fill(d_K1, 1.0, G, st);
+    if (rc) return rc;
+    AloArgs a;
+    rc = fill_args(a, cfg, G, r, q, sigma, d_K1, T, nullptr, nullptr, is_put, tables_dev);
+    if (rc) return rc;
+    a.cfg.iter_tol = cfg->iter_tol / K_max * (1.0 - 1e-12);
+    a.snap_tol_hi = cfg->iter_tol / K_min * (1.0 + 1e-12);
+    a.snap = d_snap; a.nsnap = d_ns; a.snap_cap = sa.snap_cap;
+    a.seeds_out = d_seed;
+    rc = launch_qd_seed(a, st);
+    if (rc) return rc;
+    a.seeds_in = d_seed;
+    rc = cfg->kernel != 1 ? launch_alo_fast(a, st) : -1000;
+    if (rc == -1000) rc = launch_alo_generic(a, st);
+    if (rc) return rc;
+    return launch_surface_price(sa, st);
+}
+
 int faop_alo_eval_points_batch(const faop_cfg* cfg, int64_t N, int32_t npts, const double* r, const double* q,
                                const double* sigma, const double* K, const double* T, const uint8_t* is_put,
                                const void* tables_dev, const double* B, const double* pts_tau, const double* pts_B,

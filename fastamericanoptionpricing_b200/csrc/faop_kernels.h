@@ -78,10 +78,16 @@ struct SurfArgs {
     int snap_cap;
     double* price;
     int32_t* iters;
+    // ladder mode (faop_alo_ladder_batch): g_cnt explicit scenarios x one strike ladder, output [g * nK + k]
+    const double *g_r, *g_q, *g_sigma, *g_T, *g_S;
+    const uint8_t* g_put;
+    const double* ladder;
+    int nK;
 };
 int launch_surface_groups(const SurfArgs& a, double* r, double* q, double* sigma, double* K, double* T, uint8_t* is_put,
                           cudaStream_t st);
 int launch_surface_price(const SurfArgs& a, cudaStream_t st);
+int launch_fill(double* dst, double value, int64_t count, cudaStream_t st);
 int launch_surface_decode(const faop_surface& s, int64_t first, int64_t count, double* r, double* q, double* sigma,
                           double* K, double* T, double* S, uint8_t* is_put, cudaStream_t st);
 int launch_dev_math(int kind, int64_t N, const double* x, double* out, cudaStream_t st);

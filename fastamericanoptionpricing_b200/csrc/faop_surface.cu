@@ -52,6 +52,10 @@ FAOP_D void phi_pair(double y0, double y1, double& P0, double& P1) {
     P1 = (y1 <= 0.0) ? c1 : 1.0 - c1;
 }
 
+// LADDER = false: surface mode, group g = iT * nV + iV decoded from the faop_surface, strikes linspace(K0, K1, nK), output
+// in the surface's flat order.  LADDER = true: G explicit scenarios (r, q, sigma, T, S, type) x one common strike ladder,
+// output price[g * nK + k].
+template <bool LADDER>
 __global__ void __launch_bounds__(kSurfThreads) surface_price_kernel(SurfArgs a) {
     extern __shared__ double smem[];
     const TableLayout tl = a.tl;
@@ -67,17 +71,25 @@ __global__ void __launch_bounds__(kSurfThreads) surface_price_kernel(SurfArgs a)
     const double* g_wm = a.tables + tl.off_wm;
     const double* g_hm = a.tables + tl.off_hm;
     const double* g_sgm = a.tables + tl.off_sgm;
-    const bool put = a.s.is_put != 0;
-    const double om = put ? 1.0 : -1.0;
-    const double r = a.s.r, q = a.s.q, S = a.s.S;
-    const double x0 = b_at_zero(r, q, 1.0, put);
     const int64_t rowlen = (int64_t)a.s.nT * a.s.nV;
 
     for (int j = blockIdx.x; j < a.g_cnt; j += gridDim.x) {
-        const int g = a.g_lo + j;
-        const int iV = g % a.s.nV, iT = g / a.s.nV;
-        const double T = lin_at(iT, a.s.nT, a.s.T0, a.s.T1, a.stepT);
-        const double sg = lin_at(iV, a.s.nV, a.s.V0, a.s.V1, a.stepV);
+        double r, q, S, T, sg;
+        bool put;
+        int g = 0;
+        if (LADDER) {
+            r = a.g_r[j]; q = a.g_q[j]; S = a.g_S[j]; T = a.g_T[j]; sg = a.g_sigma[j];
+            put = a.g_put[j] != 0;
+        } else {
+            g = a.g_lo + j;
+            const int iV = g % a.s.nV, iT = g / a.s.nV;
+            r = a.s.r; q = a.s.q; S = a.s.S;
+            put = a.s.is_put != 0;
+            T = lin_at(iT, a.s.nT, a.s.T0, a.s.T1, a.stepT);
+            sg = lin_at(iV, a.s.nV, a.s.V0, a.s.V1, a.stepV);
+        }
+        const double om = put ? 1.0 : -1.0;
+        const double x0 = b_at_zero(r, q, 1.0, put);
         const int ns = a.nsnap[j];
         const double* snap = a.snap + (int64_t)j * cap * (n + 3);
         const double sqt = sqrt(T), ssu = sg * sqt, cinv = 1.0 / ssu, apc = ((r - q) + 0.5 * sg * sg) * sqt / sg;
@@ -102,10 +114,19 @@ __global__ void __launch_bounds__(kSurfThreads) surface_price_kernel(SurfArgs a)
             s_root[e] = sqrt(Hu < 0.0 ? 0.0 : Hu);    // NaN propagates
         }
         __syncthreads();
-        for (int iK = a.iK_lo + threadIdx.x; iK <= a.iK_hi; iK += kSurfThreads) {
-            const int64_t flat = (int64_t)iK * rowlen + g;
-            if (flat < a.first || flat >= a.first + a.count) continue;
-            const double K = lin_at(iK, a.s.nK, a.s.K0, a.s.K1, a.stepK);
+        const int k_lo = LADDER ? 0 : a.iK_lo, k_hi = LADDER ? a.nK - 1 : a.iK_hi;
+        for (int iK = k_lo + threadIdx.x; iK <= k_hi; iK += kSurfThreads) {
+            int64_t at;
+            double K;
+            if (LADDER) {
+                at = (int64_t)j * a.nK + iK;
+                K = a.ladder[iK];
+            } else {
+                const int64_t flat = (int64_t)iK * rowlen + g;
+                if (flat < a.first || flat >= a.first + a.count) continue;
+                at = flat - a.first;
+                K = lin_at(iK, a.s.nK, a.s.K0, a.s.K1, a.stepK);
+            }
             const double eur = euro_value(T, S, r, q, sg, K, put);
             double v = eur;
             int its = 0;
@@ -130,10 +151,21 @@ __global__ void __launch_bounds__(kSurfThreads) surface_price_kernel(SurfArgs a)
             } else if (ns >= 0) {
                 its = (int)s_cnt[ns - 1];
             }
-            a.price[flat - a.first] = v;
-            if (a.iters) a.iters[flat - a.first] = its;
+            a.price[at] = v;
+            if (a.iters) a.iters[at] = its;
         }
     }
+}
+
+__global__ void __launch_bounds__(256) fill_kernel(double* dst, double value, int64_t count) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) dst[i] = value;
+}
+int launch_fill(double* dst, double value, int64_t count, cudaStream_t st) {
+    if (count == 0) return 0;
+    fill_kernel<<<(unsigned)((count + 255) / 256), 256, 0, st>>>(dst, value, count);
+    count_launch();
+    return launch_status();
 }
 
 int launch_surface_groups(const SurfArgs& a, double* r, double* q, double* sigma, double* K, double* T, uint8_t* is_put,
@@ -145,12 +177,18 @@ int launch_surface_groups(const SurfArgs& a, double* r, double* q, double* sigma
 }
 
 int launch_surface_price(const SurfArgs& a, cudaStream_t st) {
-    if (a.g_cnt == 0 || a.count == 0) return 0;
+    if (a.g_cnt == 0 || (a.ladder ? a.nK == 0 : a.count == 0)) return 0;
     const size_t sm = sizeof(double) * (size_t)(5 * a.tl.MP + 2 * a.snap_cap + a.snap_cap * a.tl.MP);
-    if (sm > 48 * 1024)
-        FAOP_CUDA_OK(cudaFuncSetAttribute(surface_price_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     const int grid = a.g_cnt < kSMs * 8 ? a.g_cnt : kSMs * 8;
-    surface_price_kernel<<<grid, kSurfThreads, sm, st>>>(a);
+    if (a.ladder) {
+        if (sm > 48 * 1024)
+            FAOP_CUDA_OK(cudaFuncSetAttribute(surface_price_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        surface_price_kernel<true><<<grid, kSurfThreads, sm, st>>>(a);
+    } else {
+        if (sm > 48 * 1024)
+            FAOP_CUDA_OK(cudaFuncSetAttribute(surface_price_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        surface_price_kernel<false><<<grid, kSurfThreads, sm, st>>>(a);
+    }
     count_launch();
     return launch_status();
 }

@@ -31,16 +31,37 @@ def price_batch_sharded(r, q, sigma, K, T, S, is_put, t=None, cfg=None, gather=T
     return gather_slices(local, N, world, group), (lo, hi)
 
 
-def gather_slices(local, N, world, group=None):
-    """all_gather of per-rank slices of unequal length (padded to the longest) back into one length-N vector."""
+def gather_slices(local, N, world, group=None, unit=1):
+    """all_gather of per-rank slices of unequal length (padded to the longest) back into one length-N vector.
+    unit: slices are cut in whole rows of `unit` elements (N = rows * unit), as ladder_batch_sharded cuts scenarios."""
     import torch.distributed as dist
-    longest = -(-N // world)
+    rows = N // unit
+    longest = -(-rows // world) * unit
     pad = torch.zeros(longest, dtype=local.dtype, device=local.device)
     pad[:local.numel()] = local
     parts = [torch.empty_like(pad) for _ in range(world)]
     dist.all_gather(parts, pad, group=group)
     full = torch.empty(N, dtype=local.dtype, device=local.device)
     for rk in range(world):
-        lo, hi = shard_bounds(N, world, rk)
-        full[lo:hi] = parts[rk][:hi - lo]
+        lo, hi = shard_bounds(rows, world, rk)
+        full[lo * unit:hi * unit] = parts[rk][:(hi - lo) * unit]
     return full
+
+
+def ladder_batch_sharded(r, q, sigma, T, S, is_put, K, cfg=None, gather=False, group=None):
+    """Strike ladders (batch.ladder_batch) with the SCENARIOS cut across ranks: rank g prices rows [lo, hi) of the
+    G x nK result — the boundary solves are split too, nothing is replicated and nothing is exchanged.  With `gather`
+    every rank receives the full G x nK matrix (one all_gather).  Returns (prices, (lo, hi))."""
+    import torch.distributed as dist
+    from . import batch
+    cfg = cfg or batch.AloConfig()
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    G = len(r)
+    lo, hi = shard_bounds(G, world, rank)
+    sl = slice(lo, hi)
+    local = batch.ladder_batch(r[sl], q[sl], sigma[sl], T[sl], S[sl], is_put[sl], K, cfg=cfg)
+    if not gather or world == 1:
+        return local, (lo, hi)
+    nK = local.shape[1]
+    return gather_slices(local.reshape(-1), G * nK, world, group, unit=nK).reshape(G, nK), (lo, hi)

@@ -119,6 +119,17 @@ int faop_alo_surface_dedup_batch(const faop_cfg* cfg, const faop_surface* surf, 
                                  const void* tables_dev, double* price, int32_t* iters /* nullable */,
                                  void* workspace, size_t workspace_bytes, void* cuda_stream);
 
+/* Strike ladder (option chain / scenario grid): G scenarios (r, q, sigma, T, S, type), each priced at the same nK strikes
+ * K[0..nK) -> price[g * nK + k] (iters likewise, nullable).  One boundary solve per scenario shared by its strikes, exactly
+ * as in faop_alo_surface_dedup_batch; every (scenario, strike) pair gets the result FastAmericanOptionSolver.solve(0, S)
+ * would give for that strike (FastAmericanOptionSolverBase.py:49-76) to rounding.  K_min / K_max: the extremes of the ladder
+ * (host values; they bound the stopping thresholds the shared solve has to cover).  All array pointers are device pointers. */
+int faop_alo_ladder_workspace_bytes(const faop_cfg* cfg, int64_t G, size_t* bytes);
+int faop_alo_ladder_batch(const faop_cfg* cfg, int64_t G, const double* r, const double* q, const double* sigma,
+                          const double* T, const double* S, const uint8_t* is_put, int32_t nK, const double* K,
+                          double K_min, double K_max, const void* tables_dev, double* price, int32_t* iters /* nullable */,
+                          void* workspace, size_t workspace_bytes, void* cuda_stream);
+
 /* N, D, N', D', f, f' (and the damped update B_new) at `npts` arbitrary (tau, Q) points per option on a GIVEN
  * boundary B (N x (n+1)) — one Jacobi sweep's internals:
  * FastAmericanOptionSolver.compute_f_and_fprime / N_func / D_func / Nprime_func / Dprime_func /

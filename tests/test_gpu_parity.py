@@ -622,3 +622,31 @@ def test_surface_dedup_c5_slice():
     plain, it0 = batch.surface_batch(surf, first, count, cfg, want_iters=True)
     assert torch.isfinite(got).all() and (got - plain).abs().max().item() <= PRICE_ABS_TOL
     assert (it0 != it1).float().mean().item() <= 1e-4
+
+
+def test_ladder_matches_per_option_solves():
+    """faop_alo_ladder_batch: G random scenarios x a strike ladder == every (scenario, strike) pair solved on its own
+    (same sweep counts, prices to 1e-9), puts and calls mixed, q == 0 calls on the European shortcut, and against the C oracle."""
+    from oracle import c_oracle as co
+    G, nK = 300, 41
+    b = {k: v[:G].copy() for k, v in wl.c2_batch(G).items()}
+    b["q"][:10] = 0.0
+    Kl = np.linspace(60.0, 140.0, nK)
+    for cfgk in (dict(wl.C2_CFG), dict(solver="B", n=10, l=20, m=40, iter_tol=1e-6, max_iters=80)):
+        cfg = AloConfig(**cfgk)
+        got, it = batch.ladder_batch(b["r"], b["q"], b["sigma"], b["T"], b["S"], b["is_put"], Kl, cfg=cfg, want_iters=True)
+        rep = lambda x: np.repeat(x, nK)   # noqa: E731
+        a = [rep(b["r"]), rep(b["q"]), rep(b["sigma"]), np.tile(Kl, G), rep(b["T"]), rep(b["S"]), rep(b["is_put"])]
+        plain = batch.price_batch(*a, cfg=cfg, want_boundary=False)
+        p0, i0 = plain["price"].reshape(G, nK), plain["iters"].reshape(G, nK)
+        fin = torch.isfinite(p0)
+        assert torch.equal(fin, torch.isfinite(got)) and fin.float().mean() > 0.97
+        assert (p0 - got)[fin].abs().max().item() <= PRICE_ABS_TOL, cfgk
+        assert (i0 != it).float().mean().item() <= 1e-3
+        assert (it[:10][~torch.as_tensor(b["is_put"][:10])] == 0).all()
+        ref = co.alo_price_batch(cfg.solver, *a, n=cfg.n, l=cfg.l, m=cfg.m, iter_tol=cfg.iter_tol, max_iters=cfg.max_iters)
+        ps = np.isfinite(ref["price"]) & ((ref["err"] < 1e-2) | (ref["iters"] == 0))
+        assert np.abs(got.cpu().numpy().reshape(-1) - ref["price"])[ps].max() <= PRICE_ABS_TOL
+    from fastamericanoptionpricing_b200 import ladder_batch_sharded
+    p, (lo, hi) = ladder_batch_sharded(b["r"], b["q"], b["sigma"], b["T"], b["S"], b["is_put"], Kl, cfg=cfg)
+    assert (lo, hi) == (0, G) and torch.equal(p, got)

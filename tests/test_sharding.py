@@ -39,6 +39,9 @@ def _worker(rank, world, port, N, out):
     local = full[lo:hi].clone()
     got = gather_slices(local, N, world)
     ok = torch.equal(got, full)
+    # row-wise cut (ladder_batch_sharded: scenarios x strikes): N rows of 3
+    mat = torch.arange(3 * N, dtype=torch.float64).reshape(N, 3)
+    ok = ok and torch.equal(gather_slices(mat[lo:hi].reshape(-1).clone(), 3 * N, world, unit=3).reshape(N, 3), mat)
     # every rank reduces its step time with MAX, as bench.py does
     t = torch.tensor([10.0 + rank])
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
