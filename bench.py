@@ -124,6 +124,79 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def run_c5(args):
+    """BASELINE.json configs[4]: 100M puts = 1000 strikes x 1000 maturities x 100 vols (S=100, r=.04, q=.01), Solver A n=12
+    l=32 m=64.  The (T, sigma) scenarios are cut across the ranks; each rank solves its scenarios' boundaries once (K = 1)
+    and prices all 1000 strikes of each (faop_alo_ladder_batch).  Total work is fixed: strong scaling."""
+    import torch
+    import torch.distributed as dist
+    from fastamericanoptionpricing_b200 import batch
+    from fastamericanoptionpricing_b200.sharding import shard_bounds
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    W = max(args.warmup, 3)
+    cfg = batch.AloConfig(**wl.C5_CFG)
+    nK, nT, nV = 1000, 1000, 100
+    Kl = np.linspace(50.0, 150.0, nK)
+    Tg, Vg = np.meshgrid(np.linspace(1.0 / 52, 3.0, nT), np.linspace(0.10, 0.60, nV), indexing="ij")
+    G = nT * nV
+    lo, hi = shard_bounds(G, world, rank)
+    g = hi - lo
+    T = torch.from_numpy(Tg.reshape(-1)[lo:hi].copy()).to(dev)
+    V = torch.from_numpy(Vg.reshape(-1)[lo:hi].copy()).to(dev)
+    r = torch.full((g,), 0.04, dtype=torch.float64, device=dev)
+    q = torch.full((g,), 0.01, dtype=torch.float64, device=dev)
+    S = torch.full((g,), 100.0, dtype=torch.float64, device=dev)
+    put = torch.ones(g, dtype=torch.uint8, device=dev)
+    Kd = torch.from_numpy(Kl).to(dev)
+    out = torch.empty((g, nK), dtype=torch.float64, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(W):
+        batch.ladder_batch(r, q, V, T, S, put, Kd, cfg=cfg, out=out)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    l0 = batch.launch_count()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    for s in range(args.steps):       # the 800 MB/world output per step is itself larger than L2: nothing survives between steps
+        ev[s][0].record()
+        batch.ladder_batch(r, q, V, T, S, put, Kd, cfg=cfg, out=out)
+        ev[s][1].record()
+    barrier()
+    launches = batch.launch_count() - l0
+    clocks = sampler.stop()
+    ms = float(np.mean([a.elapsed_time(b_) for a, b_ in ev]))
+    red = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(red, op=dist.ReduceOp.MAX)
+    ms = red.item()
+    if rank == 0:
+        line = {"metric": METRIC, "value": G * nK / (ms / 1e3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": W,
+                "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic",
+                "config": {"workload": "C5: 100M-put surface (1000 strikes x 1000 maturities x 100 vols), FastAmericanOptionSolverA "
+                                       "n=12 l=32 m=64 tol=1e-5 max_iters=20; boundary solves shared per (T, sigma) scenario "
+                                       "(BASELINE.json configs[4], SURVEY 8f row 1)",
+                           "scenarios": G, "strikes": nK, "parallelism": "scenarios cut across %d ranks, no collective" % world,
+                           "l2": "output (%d MB per rank) exceeds L2" % (g * nK * 8 >> 20)},
+                "gpu_launches": int(launches), "clocks": clocks,
+                "checksum": float(out.sum().item())}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -133,9 +206,14 @@ def main():
     ap.add_argument("--options", type=int, default=N_PER_GPU, help="options per GPU per step (default: the 1M of configs[1])")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--kernel", type=int, default=0)
+    ap.add_argument("--workload", default="c2", choices=["c2", "c5"],
+                    help="c2 (default, the headline line) or c5: the 100M-option surface as 100k (T, sigma) scenarios x "
+                         "1000 strikes through the deduplicated ladder path, scenarios cut across the ranks (strong scaling)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    if args.workload == "c5":
+        return run_c5(args)
 
     import torch
     import torch.distributed as dist
@@ -262,7 +340,15 @@ def main():
                              "kernel_ms": ms_kernel, "flops_per_option": fl,
                              "flop_model": "SURVEY 8d nominal: add/mul 1, FMA 2, div/sqrt 16, exp 40, log 56, Phi 120, phi 42 "
                                            "at the realised mean iteration count",
-                             "executed_fp64_pipe_active_pct_ncu": 67.1 if args.kernel == 0 else None,
+                             # hardware-side view of the same launch: DFMA x2 + DMUL + DADD thread instructions per option
+                             # counted by ncu (profiles/r1_alo_fast_A12_ncu_full.csv, 1.123 MFLOP at 19.32 sweeps), scaled
+                             # to this run's sweep count; the nominal model prices exp/Phi/sqrt as 40/120/16 flops where
+                             # the kernel spends 24/50/12, which is why `frac` can exceed 1
+                             "executed": None if args.kernel != 0 else {
+                                 "flops_per_option": 1.123e6 * iters_mean / 19.316,
+                                 "tflops": 1.123e6 * iters_mean / 19.316 * Nopt / (ms_kernel / 1e3) / 1e12,
+                                 "frac": 1.123e6 * iters_mean / 19.316 * Nopt / (ms_kernel / 1e3) / 1e12 / tf_peak,
+                                 "fp64_pipe_active_pct_ncu": 69.5},
                              "peak_source": "register-operand DFMA chains measured in this run (faop_measure_fp64_peak); "
                                             "MEASURED_PEAKS.json has no FP64 figure"},
                 "cpu_baseline": {"value": cpu_rate, "unit": UNIT, "cores": threads, "kind": "port",
