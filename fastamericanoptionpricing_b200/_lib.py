@@ -38,6 +38,8 @@ _SIGNATURES = {
     "faop_alo_eval_points_batch": (ctypes.c_int, [_P(FaopCfg), c_i64, c_i32] + [c_vp] * 20),
     "faop_alo_interp_boundary_batch": (ctypes.c_int, [_P(FaopCfg), c_i64, c_i32] + [c_vp] * 10),
     "faop_alo_price_known_boundary_batch": (ctypes.c_int, [_P(FaopCfg), c_i64] + [c_vp] * 13),
+    "faop_alo_greeks_known_boundary_batch": (ctypes.c_int, [_P(FaopCfg), c_i64] + [c_vp] * 10 + [c_dbl, c_dbl] + [c_vp] * 5),
+    "faop_iv_update_batch": (ctypes.c_int, [c_i64] + [c_vp] * 9),
     "faop_qd_boundary_batch": (ctypes.c_int, [c_i64] + [c_vp] * 8),
     "faop_qd_residual_batch": (ctypes.c_int, [c_i64] + [c_vp] * 9),
     "faop_qd_price_batch": (ctypes.c_int, [c_i64] + [c_vp] * 10),

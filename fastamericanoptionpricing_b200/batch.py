@@ -29,6 +29,9 @@ class AloConfig:
     use_derivative: bool = False
     eta: float = 0.5
     kernel: int = 0        # 0 = auto (specialised kernel when available), 1 = generic kernel
+    # opt-in accuracy modes named in the north-star but absent from the reference (they change results):
+    rule_l: str = "gauss-legendre"   # or "tanh-sinh": rule of the boundary-equation integrals (l points)
+    rule_m: str = "gauss-legendre"   # or "tanh-sinh": rule of the price integral (m points)
 
     def c(self):
         return FaopCfg(0 if self.solver == "A" else 1, int(bool(self.use_derivative)), int(self.n), int(self.l),
@@ -76,9 +79,33 @@ def gauss_legendre(num):
     return np.ascontiguousarray(y, dtype=np.float64), np.ascontiguousarray(w, dtype=np.float64)
 
 
+def tanh_sinh(num, t_max=3.16):
+    """Double-exponential (tanh-sinh) rule on [-1, 1] with `num` points: y = tanh(pi/2 sinh t), w = h pi/2 cosh t /
+    cosh^2(pi/2 sinh t) on the uniform grid t = (k - (num-1)/2) h, h = 2 t_max / (num - 1); t_max = 3.16 puts the outermost
+    nodes 1e-16 from the end points, where the weights have decayed below 1e-15.  Not in the reference."""
+    num = int(num)
+    if num < 2:
+        return np.zeros(1), np.full(1, 2.0)
+    h = 2.0 * t_max / (num - 1)
+    t = (np.arange(num) - 0.5 * (num - 1)) * h
+    u = 0.5 * np.pi * np.sinh(t)
+    y = np.tanh(u)
+    w = h * 0.5 * np.pi * np.cosh(t) / np.cosh(u) ** 2
+    y = np.clip(y, -1.0 + 2.0 ** -52, 1.0 - 2.0 ** -53)     # keep (1 + y)/2 > 0: the kernels divide by it
+    return np.ascontiguousarray(y), np.ascontiguousarray(w)
+
+
+def quadrature_rule(name, num):
+    if name == "gauss-legendre":
+        return gauss_legendre(num)
+    if name == "tanh-sinh":
+        return tanh_sinh(num)
+    raise ValueError("unknown quadrature rule %r" % (name,))
+
+
 def tables_for(cfg: AloConfig, dev):
-    """Device table blob for (n, l, m), built once per device by faop_tables_build."""
-    key = (cfg.n, cfg.l, cfg.m, str(dev))
+    """Device table blob for (n, l, m) and the two rules, built once per device by faop_tables_build."""
+    key = (cfg.n, cfg.l, cfg.m, cfg.rule_l, cfg.rule_m, str(dev))
     t = _TABLES.get(key)
     if t is None:
         lib = _lib.load()
@@ -86,8 +113,8 @@ def tables_for(cfg: AloConfig, dev):
         nbytes = ctypes.c_size_t()
         check(lib.faop_tables_bytes(ctypes.byref(c), ctypes.byref(nbytes)), "faop_tables_bytes")
         host = np.empty(nbytes.value // 8, dtype=np.float64)
-        yl, wl = gauss_legendre(cfg.l)
-        ym, wm = gauss_legendre(cfg.m)
+        yl, wl = quadrature_rule(cfg.rule_l, cfg.l)
+        ym, wm = quadrature_rule(cfg.rule_m, cfg.m)
         check(lib.faop_tables_build(ctypes.byref(c), yl.ctypes.data, wl.ctypes.data, ym.ctypes.data, wm.ctypes.data,
                                     host.ctypes.data), "faop_tables_build")
         t = torch.from_numpy(host).to(dev)
@@ -266,6 +293,69 @@ def surface_batch(surface: dict, first, count, cfg: AloConfig, want_iters=False,
         check(lib.faop_alo_surface_batch(ctypes.byref(c), ctypes.byref(s), int(first), int(count), _ptr(tab), _ptr(price),
                                          _ptr(iters), _ptr(ws), ws.numel(), _stream(dev)), "faop_alo_surface_batch")
         return (price, iters) if want_iters else price
+
+
+def greeks_batch(r, q, sigma, K, T, S, is_put, t=None, cfg: AloConfig = AloConfig(), bump_S_rel=1e-3, bump_t=1e-4,
+                 bump_sigma=1e-4, bump_r=1e-5, want_vega=True, want_rho=True, device=None):
+    """Price and Greeks of a batch.  delta, gamma, theta (dV/dt) reuse the solved boundary — it depends neither on S nor on t —
+    through faop_alo_greeks_known_boundary_batch; vega and rho are central differences of two re-solved batches each
+    (the boundary does depend on sigma and r).  Returns dict(price, delta, gamma, theta[, vega][, rho], iters, err)."""
+    lib = _lib.load()
+    base = price_batch(r, q, sigma, K, T, S, is_put, t=t, cfg=cfg, want_boundary=True, device=device)
+    dev = base["price"].device
+    with torch.cuda.device(dev):
+        N = base["price"].numel()
+        r_, q_, sg_, K_, T_, S_ = (_f64(x, dev, N) for x in (r, q, sigma, K, T, S))
+        ip = _u8(is_put, dev, N)
+        tt = None if t is None else _f64(t, dev, N)
+        tab = tables_for(cfg, dev)
+        price, delta, gamma, theta = (torch.empty(N, dtype=torch.float64, device=dev) for _ in range(4))
+        c = cfg.c()
+        check(lib.faop_alo_greeks_known_boundary_batch(ctypes.byref(c), N, _ptr(r_), _ptr(q_), _ptr(sg_), _ptr(K_), _ptr(T_),
+                                                       _ptr(tt), _ptr(S_), _ptr(ip), _ptr(tab), _ptr(base["B"]),
+                                                       float(bump_S_rel), float(bump_t), _ptr(price), _ptr(delta), _ptr(gamma),
+                                                       _ptr(theta), _stream(dev)), "faop_alo_greeks_known_boundary_batch")
+        out = dict(price=base["price"], delta=delta, gamma=gamma, theta=theta, iters=base["iters"], err=base["err"])
+        # the finite differences of re-solved prices need a converged boundary: tighten the stopping rule for them
+        if want_vega:
+            up = price_batch(r_, q_, sg_ + bump_sigma, K_, T_, S_, ip, t=tt, cfg=cfg, want_boundary=False)["price"]
+            dn = price_batch(r_, q_, sg_ - bump_sigma, K_, T_, S_, ip, t=tt, cfg=cfg, want_boundary=False)["price"]
+            out["vega"] = (up - dn) / (2 * bump_sigma)
+        if want_rho:
+            up = price_batch(r_ + bump_r, q_, sg_, K_, T_, S_, ip, t=tt, cfg=cfg, want_boundary=False)["price"]
+            dn = price_batch(r_ - bump_r, q_, sg_, K_, T_, S_, ip, t=tt, cfg=cfg, want_boundary=False)["price"]
+            out["rho"] = (up - dn) / (2 * bump_r)
+        return out
+
+
+def implied_vol_batch(target, r, q, K, T, S, is_put, cfg: AloConfig = AloConfig(), sigma_lo=0.05, sigma_hi=3.0, iters=48,
+                      tol=1e-12, check_every=4, device=None):
+    """Implied volatility of American prices: per option the root of price_batch(sigma) - target in [sigma_lo, sigma_hi]
+    by a bracketed Illinois search (bisection when the secant stalls) whose state lives on the device (faop_iv_update_batch); every trial is one full batch
+    solve.  Stops after `iters` trials or when every bracket is narrower than tol (checked every `check_every` trials).
+    Targets outside [price(sigma_lo), price(sigma_hi)] give NaN.  Returns (sigma, trials)."""
+    lib = _lib.load()
+    dev, N, (target, r, q, K, T, S) = _common([target, r, q, K, T, S], device)
+    with torch.cuda.device(dev):
+        ip = _u8(is_put, dev, N)
+        lo = torch.full((N,), float(sigma_lo), dtype=torch.float64, device=dev)
+        hi = torch.full((N,), float(sigma_hi), dtype=torch.float64, device=dev)
+        flo = torch.full((N,), float("nan"), dtype=torch.float64, device=dev)
+        fhi = torch.full((N,), float("nan"), dtype=torch.float64, device=dev)
+        side = torch.full((N,), -2, dtype=torch.int32, device=dev)
+        sig = lo.clone()
+        trials = 0
+        for it in range(int(iters) + 2):
+            ok = torch.isfinite(sig)
+            p = price_batch(r, q, torch.where(ok, sig, lo), K, T, S, ip, cfg=cfg, want_boundary=False)["price"]
+            trials += 1
+            check(lib.faop_iv_update_batch(N, _ptr(target), _ptr(p), _ptr(sig), _ptr(lo), _ptr(hi), _ptr(flo), _ptr(fhi),
+                                           _ptr(side), _stream(dev)), "faop_iv_update_batch")
+            if it >= 2 and (it - 2) % check_every == check_every - 1:
+                live = side >= 0
+                if not bool(((hi - lo)[live] > tol).any()):
+                    break
+        return sig, trials
 
 
 def ladder_batch(r, q, sigma, T, S, is_put, K, cfg: AloConfig = AloConfig(), want_iters=False, device=None, out=None):
@@ -538,8 +628,8 @@ class HostContext:
             if want_boundary:
                 out["B"] = np.empty((N, nn))
                 out["B0"] = np.empty((N, nn))
-        yl, wl = gauss_legendre(cfg.l)
-        ym, wm = gauss_legendre(cfg.m)
+        yl, wl = quadrature_rule(cfg.rule_l, cfg.l)
+        ym, wm = quadrature_rule(cfg.rule_m, cfg.m)
         c = cfg.c()
         check(self._lib.faop_alo_price_batch_host(self._h, ctypes.byref(c), N, hp(r), hp(q), hp(sigma), hp(K), hp(T), hp(t),
                                                   hp(S), hp(is_put), hp(yl), hp(wl), hp(ym), hp(wm), None, hp(out["price"]),

@@ -312,6 +312,48 @@ __global__ void __launch_bounds__(kGenWarps * 32) alo_price_known_kernel(AloArgs
     }
 }
 
+// ---------------------------------------------------------------- Greeks by bump-and-reprice on a given boundary
+// The boundary does not depend on the spot or on the valuation date, so delta, gamma and theta are differences of the price
+// integral (american_value_with_known_boundary, FastAmericanOptionSolverBase.py:92-103) evaluated on the SAME boundary:
+//   delta = (V(S+h) - V(S-h)) / 2h,  gamma = (V(S+h) - 2 V(S) + V(S-h)) / h^2,  h = bump_S_rel * S
+//   theta = (V(t + dt) - V(t)) / dt  (calendar-time derivative dV/dt, one-sided; dt is clipped to the remaining life)
+// SURVEY 8f row 2; the reference itself only offers european_option_theta.
+__global__ void __launch_bounds__(kGenWarps * 32) alo_greeks_known_kernel(AloArgs a, double bump_S_rel, double bump_t,
+                                                                          double* delta, double* gamma, double* theta) {
+    extern __shared__ double smem[];
+    const TableLayout tl = a.tl;
+    const int n = tl.n, nn = n + 1;
+    stage_tables(smem, a.tables, tl.small);
+    const CtaTables tb(smem, tl);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const WarpSmem w(smem + tl.small + warp * WarpSmem::doubles(nn), nn);
+    const int64_t stride = (int64_t)gridDim.x * kGenWarps;
+    for (int64_t opt = (int64_t)blockIdx.x * kGenWarps + warp; opt < a.N; opt += stride) {
+        Opt o = load_option(a, opt);
+        for (int j = lane; j <= n; j += 32) w.B[j] = a.seeds_in[opt * nn + j];
+        __syncwarp();
+        double eur;
+        const double S0 = o.S, t0 = o.t;
+        const double v0 = price_integral(w, tb, tl, o, lane, &eur);
+        const double h = bump_S_rel * S0;
+        o.S = S0 + h;
+        const double vp = price_integral(w, tb, tl, o, lane, &eur);
+        o.S = S0 - h;
+        const double vm = price_integral(w, tb, tl, o, lane, &eur);
+        o.S = S0;
+        double dt = fmin(bump_t, o.T - t0);
+        o.t = t0 + dt;
+        const double vt = price_integral(w, tb, tl, o, lane, &eur);
+        if (lane == 0) {
+            if (a.price) a.price[opt] = v0;
+            if (delta) delta[opt] = (vp - vm) / (2.0 * h);
+            if (gamma) gamma[opt] = (vp - 2.0 * v0 + vm) / (h * h);
+            if (theta) theta[opt] = (vt - v0) / dt;
+        }
+        __syncwarp();
+    }
+}
+
 // ---------------------------------------------------------------- host-side launchers
 static int generic_grid(int64_t N) {
     int64_t ctas = (N + kGenWarps - 1) / kGenWarps;
@@ -369,6 +411,17 @@ int launch_alo_interp(const AloArgs& a, double* Bu, cudaStream_t st) {
     if (sm > 48 * 1024)
         FAOP_CUDA_OK(cudaFuncSetAttribute(alo_interp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     alo_interp_kernel<<<generic_grid(a.N), kGenWarps * 32, sm, st>>>(a, Bu);
+    count_launch();
+    return launch_status();
+}
+
+int launch_alo_greeks_known(const AloArgs& a, double bump_S_rel, double bump_t, double* delta, double* gamma, double* theta,
+                            cudaStream_t st) {
+    if (a.N == 0) return 0;
+    size_t sm = generic_smem(a.tl);
+    if (sm > 48 * 1024)
+        FAOP_CUDA_OK(cudaFuncSetAttribute(alo_greeks_known_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    alo_greeks_known_kernel<<<generic_grid(a.N), kGenWarps * 32, sm, st>>>(a, bump_S_rel, bump_t, delta, gamma, theta);
     count_launch();
     return launch_status();
 }

@@ -378,6 +378,28 @@ int faop_alo_price_known_boundary_batch(const faop_cfg* cfg, int64_t N, const do
     return launch_alo_price_known(a, (cudaStream_t)cuda_stream);
 }
 
+int faop_alo_greeks_known_boundary_batch(const faop_cfg* cfg, int64_t N, const double* r, const double* q,
+                                         const double* sigma, const double* K, const double* T, const double* t,
+                                         const double* S, const uint8_t* is_put, const void* tables_dev, const double* B,
+                                         double bump_S_rel, double bump_t, double* price, double* delta, double* gamma,
+                                         double* theta, void* cuda_stream) {
+    AloArgs a;
+    int rc = fill_args(a, cfg, N, r, q, sigma, K, T, t, S, is_put, tables_dev);
+    if (rc) return rc;
+    if (!(bump_S_rel > 0) || !(bump_t > 0)) return FAOP_EINVAL;
+    if (N == 0) return 0;
+    if (!B || !S) return FAOP_EINVAL;
+    a.seeds_in = B;
+    a.price = price;
+    return launch_alo_greeks_known(a, bump_S_rel, bump_t, delta, gamma, theta, (cudaStream_t)cuda_stream);
+}
+
+int faop_iv_update_batch(int64_t N, const double* target, const double* price, double* sigma, double* lo, double* hi,
+                         double* flo, double* fhi, int32_t* side, void* cuda_stream) {
+    if (N < 0 || (N > 0 && (!target || !price || !sigma || !lo || !hi || !flo || !fhi || !side))) return FAOP_EINVAL;
+    return launch_iv_update(N, target, price, sigma, lo, hi, flo, fhi, side, (cudaStream_t)cuda_stream);
+}
+
 int faop_qd_boundary_batch(int64_t N, const double* r, const double* q, const double* sigma, const double* K,
                            const double* tau, const uint8_t* is_put, double* B, void* cuda_stream) {
     if (N < 0 || (N > 0 && (!r || !q || !sigma || !K || !tau || !is_put || !B))) return FAOP_EINVAL;

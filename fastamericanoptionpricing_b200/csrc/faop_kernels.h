@@ -38,6 +38,10 @@ int launch_qd_seed(const AloArgs& a, cudaStream_t st);
 int launch_alo_generic(const AloArgs& a, cudaStream_t st);
 int launch_alo_eval_nodes(const AloArgs& a, const EvalOut& eo, cudaStream_t st);
 int launch_alo_price_known(const AloArgs& a, cudaStream_t st);
+int launch_alo_greeks_known(const AloArgs& a, double bump_S_rel, double bump_t, double* delta, double* gamma, double* theta,
+                            cudaStream_t st);
+int launch_iv_update(int64_t N, const double* target, const double* price, double* sigma, double* lo, double* hi, double* flo,
+                     double* fhi, int32_t* side, cudaStream_t st);
 int launch_alo_interp(const AloArgs& a, double* Bu, cudaStream_t st);
 // specialised kernels (faop_alo_fast.cu); returns -1000 when no specialisation matches the config
 int launch_alo_fast(const AloArgs& a, cudaStream_t st);

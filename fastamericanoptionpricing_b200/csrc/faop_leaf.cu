@@ -209,6 +209,60 @@ __global__ void __launch_bounds__(256) fp64_peak_kernel(double* sink, double m, 
     if (s == 123456.789) sink[0] = s;  // never true; keeps the chains alive
 }
 
+// ---------------------------------------------------------------- implied volatility: one Illinois (regula falsi) step
+// The American price is increasing in sigma, so price(sigma) - target has one root in a bracket [lo, hi].  State per
+// option: the bracket, the residuals at its ends (NaN = not evaluated yet) and which end moved last.  Each call consumes
+// the price just computed at `sigma` and writes the next trial point into `sigma`:
+//   first two calls evaluate the ends of the bracket; afterwards the secant point of the bracket, with the retained end's
+//   residual halved whenever the same end moves twice in a row (Illinois), clipped into the bracket's interior.
+// A target outside [price(lo), price(hi)] pins sigma to NaN.  SURVEY 8f row 2 (callers of solve(); not in the reference).
+__global__ void __launch_bounds__(256) iv_update_kernel(int64_t N, const double* target, const double* price, double* sigma,
+                                                        double* lo, double* hi, double* flo, double* fhi, int32_t* side) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const double x = sigma[i], f = price[i] - target[i];
+    double a = lo[i], b = hi[i], fa = flo[i], fb = fhi[i];
+    const int state = side[i];
+    if (state == -3) return;                    // target outside the bracket: stays NaN
+    if (state == -2) {                          // first call: x == lo
+        flo[i] = f; side[i] = -1; sigma[i] = b;
+        return;
+    }
+    int sd = state & 3, slow = state >> 2;      // which end moved last; consecutive steps that shrank the bracket < 2x
+    const double w_old = b - a;
+    if (state == -1) {                          // second call: x == hi
+        fb = f;
+        if (!(fa <= 0.0) || !(fb >= 0.0)) { side[i] = -3; fhi[i] = fb; sigma[i] = nan(""); return; }
+        sd = 0; slow = 0;
+    } else if (f == 0.0) {
+        lo[i] = hi[i] = x; flo[i] = fhi[i] = 0.0;
+        return;                                 // sigma[i] stays at the root
+    } else if (f < 0.0) {
+        a = x; fa = f;
+        if (sd == 1) fb *= 0.5;
+        sd = 1;
+    } else {
+        b = x; fb = f;
+        if (sd == 2) fa *= 0.5;
+        sd = 2;
+    }
+    const double w = b - a;
+    slow = (state >= 0 && w > 0.5 * w_old) ? slow + 1 : 0;
+    double xn = (fb == fa) ? 0.5 * (a + b) : (a * fb - b * fa) / (fb - fa);
+    if (slow >= 2) { xn = 0.5 * (a + b); slow = 0; }   // flat-then-steep residuals stall the secant: bisect
+    if (!(xn > a + 1e-3 * w)) xn = a + 1e-3 * w;      // also catches NaN
+    if (!(xn < b - 1e-3 * w)) xn = b - 1e-3 * w;
+    if (w <= 4e-16 * b) xn = x;                        // bracket at rounding level: stay
+    lo[i] = a; hi[i] = b; flo[i] = fa; fhi[i] = fb; side[i] = sd | (slow << 2); sigma[i] = xn;
+}
+int launch_iv_update(int64_t N, const double* target, const double* price, double* sigma, double* lo, double* hi, double* flo,
+                     double* fhi, int32_t* side, cudaStream_t st) {
+    if (N == 0) return 0;
+    iv_update_kernel<<<blocks_for(N, 256), 256, 0, st>>>(N, target, price, sigma, lo, hi, flo, fhi, side);
+    count_launch();
+    return launch_status();
+}
+
 int launch_qd_boundary(int64_t N, const double* r, const double* q, const double* sigma, const double* K,
                        const double* tau, const uint8_t* is_put, double* B, cudaStream_t st) {
     if (N == 0) return 0;

@@ -160,6 +160,21 @@ int faop_alo_price_known_boundary_batch(const faop_cfg* cfg, int64_t N,
                               const void* tables_dev, const double* B /* N x (n+1) */,
                               double* price, double* european, void* cuda_stream);
 
+/* Delta, gamma, theta by bump-and-reprice on a GIVEN boundary (the boundary depends neither on the spot nor on the valuation
+ * date, so the three are differences of american_value_with_known_boundary, FastAmericanOptionSolverBase.py:92-103):
+ * central differences in S with h = bump_S_rel * S, one-sided dV/dt with step min(bump_t, T - t).  Outputs nullable.
+ * SURVEY 8f row 2; vega / rho need re-solved boundaries and are composed by the caller (batch.greeks_batch).            */
+int faop_alo_greeks_known_boundary_batch(const faop_cfg* cfg, int64_t N,
+                              const double* r, const double* q, const double* sigma, const double* K,
+                              const double* T, const double* t, const double* S, const uint8_t* is_put,
+                              const void* tables_dev, const double* B /* N x (n+1) */, double bump_S_rel, double bump_t,
+                              double* price, double* delta, double* gamma, double* theta, void* cuda_stream);
+/* One step of a bracketed Illinois root search for the implied volatility (price is increasing in sigma): consumes
+ * `price` = the American price at the current `sigma`, updates the bracket state and writes the next trial sigma.
+ * Initial state: sigma = lo, flo = fhi = NaN, side = -2; a target outside [price(lo), price(hi)] ends as sigma = NaN.     */
+int faop_iv_update_batch(int64_t N, const double* target, const double* price, double* sigma, double* lo, double* hi,
+                         double* flo, double* fhi, int32_t* side, void* cuda_stream);
+
 /* ---- leaf kernels -----------------------------------------------------------------------------*/
 /* QDplus.compute_exercise_boundary(tau) (QDplusAmericanOptionSolver.py:69-76; residual :110-125):
  * safeguarded Newton from x0 = K instead of MINPACK hybr; tau == 0 -> B_at_zero (:78-88).         */
