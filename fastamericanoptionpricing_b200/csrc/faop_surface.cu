@@ -40,14 +40,12 @@ __global__ void __launch_bounds__(256) surface_groups_kernel(SurfArgs a, double*
     is_put[j] = (uint8_t)(a.s.is_put != 0);
 }
 
-// Phi(-om d) for the pair (d-, d+): Phi(y) = E G(|y|) for y <= 0, 1 - E G(|y|) otherwise, with x = y / sqrt2,
-// E = exp(-x^2), G = erfcx(|x|)/2 (full-accuracy fits of faop_fastmath.cuh).
-FAOP_D void phi_pair(double y0, double y1, double& P0, double& P1) {
-    const double x[2] = {y0 * kInvSqrt2, y1 * kInvSqrt2};
-    double ex[2] = {-x[0] * x[0], -x[1] * x[1]}, xa[2] = {fabs(x[0]), fabs(x[1])}, E[2], G[2];
-    fast_exp_n<2, false>(ex, E);
+// Phi(y0), Phi(y1) from E0 = exp(-y0^2/2), E1 = exp(-y1^2/2): Phi(y) = E G(|y|/sqrt2) for y <= 0, 1 - E G otherwise,
+// G = erfcx/2 (full-accuracy fit of faop_fastmath.cuh).
+FAOP_D void phi_pair(double y0, double y1, double E0, double E1, double& P0, double& P1) {
+    double xa[2] = {fabs(y0) * kInvSqrt2, fabs(y1) * kInvSqrt2}, G[2];
     half_erfcx_n<2, false>(xa, G);
-    const double c0 = E[0] * G[0], c1 = E[1] * G[1];
+    const double c0 = E0 * G[0], c1 = E1 * G[1];
     P0 = (y0 <= 0.0) ? c0 : 1.0 - c0;
     P1 = (y1 <= 0.0) ? c1 : 1.0 - c1;
 }
@@ -68,6 +66,7 @@ __global__ void __launch_bounds__(kSurfThreads) surface_price_kernel(SurfArgs a)
     double* s_e = s_ssuh + MP;     // [cap] recorded errors
     double* s_cnt = s_e + cap;     // [cap] sweep counts
     double* s_root = s_cnt + cap;  // [cap][MP] sqrt(max(0, H(u_k)))
+    double* s_T = s_root + cap * MP;   // [cap][MP] exp(om sqrt(H(u_k)) + (r-q) tau h_k^2) = (X/B(u_k))^{-om} e^{(r-q)(tau-u_k)}
     const double* g_wm = a.tables + tl.off_wm;
     const double* g_hm = a.tables + tl.off_hm;
     const double* g_sgm = a.tables + tl.off_sgm;
@@ -111,7 +110,9 @@ __global__ void __launch_bounds__(kSurfThreads) surface_price_kernel(SurfArgs a)
             // z = sqrt(4 u / T) - 1 with u = T g_k (t = 0): 2 sqrt(g_k) - 1 (to_cheby_point, Base.py:235-237)
             const double z = fma(2.0, g_sgm[k], -1.0);
             const double Hu = clenshaw(n, snap + sidx * (n + 3) + 2, z);
-            s_root[e] = sqrt(Hu < 0.0 ? 0.0 : Hu);    // NaN propagates
+            const double root = sqrt(Hu < 0.0 ? 0.0 : Hu);    // NaN propagates
+            s_root[e] = root;
+            s_T[e] = exp(fma(om, root, (r - q) * T * g_hm[k] * g_hm[k]));
         }
         __syncthreads();
         const int k_lo = LADDER ? 0 : a.iK_lo, k_hi = LADDER ? a.nK - 1 : a.iK_hi;
@@ -136,14 +137,21 @@ __global__ void __launch_bounds__(kSurfThreads) surface_price_kernel(SurfArgs a)
                     if (s_e[e] * K <= a.cfg.iter_tol) { sidx = e; break; }   // first recorded iterate the strike accepts
                 its = (int)s_cnt[sidx];
                 const double* root = s_root + sidx * MP;
-                const double LS = log(S / (K * x0));
+                const double* Tk = s_T + sidx * MP;
+                const double SX = S / (K * x0);
+                const double LS = log(SX);
                 double accA = 0.0, accB = 0.0;
                 for (int k = 0; k < MP; ++k) {
                     const double lnz = fma(om, root[k], LS);
                     const double dp = fma(lnz, s_inv[k], s_apch[k]);
                     const double dm = dp - s_ssuh[k];
+                    // one exponential per point: phi(d-)/phi(d+) = exp(d+ s - s^2/2) with s = sigma sqrt(tau) h, and
+                    // d+ s - s^2/2 = ln(S/B(u)) + (r-q) tau h^2, whose strike-independent factor is tabulated (s_T)
+                    double ex[1] = {-0.5 * dp * dp}, Ep[1];
+                    fast_exp_n<1, false>(ex, Ep);
+                    const double Em = Ep[0] * (SX * Tk[k]);
                     double Pm, Pp;
-                    phi_pair(-om * dm, -om * dp, Pm, Pp);
+                    phi_pair(-om * dm, -om * dp, Em, Ep[0], Pm, Pp);
                     accA = fma(s_A[k], Pm, accA);
                     accB = fma(s_Bq[k], Pp, accB);
                 }
@@ -178,7 +186,7 @@ int launch_surface_groups(const SurfArgs& a, double* r, double* q, double* sigma
 
 int launch_surface_price(const SurfArgs& a, cudaStream_t st) {
     if (a.g_cnt == 0 || (a.ladder ? a.nK == 0 : a.count == 0)) return 0;
-    const size_t sm = sizeof(double) * (size_t)(5 * a.tl.MP + 2 * a.snap_cap + a.snap_cap * a.tl.MP);
+    const size_t sm = sizeof(double) * (size_t)(5 * a.tl.MP + 2 * a.snap_cap + 2 * a.snap_cap * a.tl.MP);
     const int grid = a.g_cnt < kSMs * 8 ? a.g_cnt : kSMs * 8;
     if (a.ladder) {
         if (sm > 48 * 1024)
