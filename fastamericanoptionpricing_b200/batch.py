@@ -33,9 +33,9 @@ class AloConfig:
     rule_l: str = "gauss-legendre"   # or "tanh-sinh": rule of the boundary-equation integrals (l points)
     rule_m: str = "gauss-legendre"   # or "tanh-sinh": rule of the price integral (m points)
 
-    def c(self):
+    def c(self, flags=0):
         return FaopCfg(0 if self.solver == "A" else 1, int(bool(self.use_derivative)), int(self.n), int(self.l),
-                       int(self.m), int(self.max_iters), float(self.iter_tol), float(self.eta), int(self.kernel), 0)
+                       int(self.m), int(self.max_iters), float(self.iter_tol), float(self.eta), int(self.kernel), int(flags))
 
 
 def _device(device=None):
@@ -149,20 +149,16 @@ def price_batch(r, q, sigma, K, T, S, is_put, t=None, cfg: AloConfig = AloConfig
         err = torch.empty(N, dtype=torch.float64, device=dev)
         B = torch.empty((N, nn), dtype=torch.float64, device=dev) if want_boundary else None
         B0_in = None
+        B0_out = None
         if B0 is not None:
             B0_in = torch.as_tensor(B0, dtype=torch.float64).to(dev).reshape(N, nn).contiguous()
-            B0_out = None
-            ws = None
         elif want_boundary:
             B0_out = torch.empty((N, nn), dtype=torch.float64, device=dev)
-            ws = None
-        else:
-            B0_out = None
-            c = cfg.c()
-            nb = ctypes.c_size_t()
-            check(lib.faop_workspace_bytes(ctypes.byref(c), N, ctypes.byref(nb)), "faop_workspace_bytes")
-            ws = torch.empty(nb.value, dtype=torch.uint8, device=dev)
-        c = cfg.c()
+        # workspace: QD seeds (when no B0 tensor takes them) + the kernels' invariant-table scratch
+        c = cfg.c(_lib.FLAG_WS_SCRATCH)
+        nb = ctypes.c_size_t()
+        check(lib.faop_workspace_bytes(ctypes.byref(c), N, ctypes.byref(nb)), "faop_workspace_bytes")
+        ws = torch.empty(max(nb.value, 256), dtype=torch.uint8, device=dev)
         ierr = torch.empty((N, cfg.max_iters), dtype=torch.float64, device=dev) if want_iter_errs else None
         check(lib.faop_alo_price_batch(ctypes.byref(c), N, _ptr(r), _ptr(q), _ptr(sigma), _ptr(K), _ptr(T), _ptr(tt),
                                        _ptr(S), _ptr(is_put), _ptr(tab), _ptr(B0_in), _ptr(price), _ptr(eur), _ptr(B),

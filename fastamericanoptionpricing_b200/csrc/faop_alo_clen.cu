@@ -8,7 +8,10 @@
 //     by lanes 0..n, ChebyshevInterpolation.py:43-51), read from shared memory as broadcast loads;
 //   * two point slots advance in lock step: with l > 32 (PPL = 2) the lane's two quadrature points k and k+32 of one
 //     node, with l <= 32 (PPL = 1) the points of two consecutive nodes;
-//   * e^{qu}, e^{ru} are recomputed per point (no room to keep n*l of them per warp).
+//   * e^{q u_ik}, e^{r u_ik} (iteration invariant, 2 n l doubles per option: 24.6 KB at C3) do not fit in shared memory next
+//     to 16 warps' state; with SCR they live in a per-warp global scratch that stays in L2 (2368 resident warps x 24.6 KB
+//     = 58 MB of the 126 MB), written once per option and re-read every sweep by the lane that wrote them (coalesced
+//     256-byte rows); without a scratch they are recomputed per point.
 // Solver B per point: E+ = exp(qu - d+^2/2), E- = exp(ru - d-^2/2), e^{qu}, e^{ru}, erfcx(|d+|/sqrt2)/2, erfcx(|d-|/sqrt2)/2
 //   D-sum += w h e^{qu} Phi(om d+),  N-sum += w h e^{ru} Phi(om d-)           (FastAmericanOptionSolverB.py:25-39)
 #include "faop_alo_fast.cuh"
@@ -49,7 +52,7 @@ FAOP_D void clenshaw2(int n, const double* A, const double (&z)[2], double (&out
     out[1] = 0.5 * (b0[1] - b2[1]);
 }
 
-template <int SOLVER, int PPL>
+template <int SOLVER, int PPL, bool SCR>
 __global__ void __launch_bounds__(kClenWarps * 32, 1) alo_clen_kernel(AloArgs a) {
     extern __shared__ double smem[];
     const TableLayout tl = a.tl;
@@ -71,6 +74,8 @@ __global__ void __launch_bounds__(kClenWarps * 32, 1) alo_clen_kernel(AloArgs a)
     }
     WarpSmem gw(ws.B, kClenMaxNodes);
     gw.B = ws.B; gw.L = ws.L; gw.H = ws.H; gw.A = ws.A;
+    // scratch rows of this warp: [(node * PPL + p) * 2 + {q, r}][lane]
+    double* scr = SCR ? a.inv_scratch + ((size_t)blockIdx.x * kClenWarps + warp) * (size_t)(2 * n * PPL * 32) + lane : nullptr;
 
     const int64_t stride = (int64_t)gridDim.x * kClenWarps;
     for (int64_t opt = (int64_t)blockIdx.x * kClenWarps + warp; opt < a.N; opt += stride) {
@@ -109,6 +114,18 @@ __global__ void __launch_bounds__(kClenWarps * 32, 1) alo_clen_kernel(AloArgs a)
             degenerate = !(o.T > 0);
         }
         __syncwarp();
+        if (SCR && !degenerate) {
+            for (int i = 0; i < n; ++i) {
+                const double qt = ws.node[i].qtau, rt = ws.node[i].rtau;
+#pragma unroll
+                for (int p = 0; p < PPL; ++p) {
+                    double ex2[2] = {qt * g[p], rt * g[p]}, e2[2];
+                    fast_exp_n<2, false>(ex2, e2);
+                    __stcg(scr + ((i * PPL + p) * 2) * 32, e2[0]);
+                    __stcg(scr + ((i * PPL + p) * 2 + 1) * 32, e2[1]);
+                }
+            }
+        }
 
         int count = 0;
         double err = 1.0;
@@ -173,8 +190,31 @@ __global__ void __launch_bounds__(kClenWarps * 32, 1) alo_clen_kernel(AloArgs a)
                             xs[2 * c] = xp; xs[2 * c + 1] = xm;
                             xa[2 * c] = fabs(xp); xa[2 * c + 1] = fabs(xm);
                         }
+                        double inv[4];   // e^{qu}, e^{ru} of the two slots, fetched before the exp / erfcx chains that hide the L2 latency
+                        if (SCR) {
+#pragma unroll
+                            for (int c = 0; c < 2; ++c) {
+                                const int p = (PPL == 2) ? c : 0;
+                                const double* row = scr + ((nd_i[c] * PPL + p) * 2) * 32;
+                                inv[2 * c] = __ldcg(row);
+                                if (SOLVER == 1) inv[2 * c + 1] = __ldcg(row + 32);
+                            }
+                        }
                         double E[8], G[4];
-                        if (SOLVER == 0) {
+                        if (SCR) {
+                            double ex4[4] = {ex[0], ex[1], ex[4], ex[5]}, E4[4];
+                            fast_exp_n<4, true>(ex4, E4);
+                            E[0] = E4[0]; E[1] = E4[1]; E[4] = E4[2]; E[5] = E4[3];
+                            E[2] = inv[0]; E[6] = inv[2];
+                            if (SOLVER == 1) { E[3] = inv[1]; E[7] = inv[3]; }
+                            if (SOLVER == 0) {
+                                double xa2[2] = {xa[0], xa[2]}, G2[2];
+                                half_erfcx_n<2, true>(xa2, G2);
+                                G[0] = G2[0]; G[2] = G2[1];
+                            } else {
+                                half_erfcx_n<4, true>(xa, G);
+                            }
+                        } else if (SOLVER == 0) {
                             // Solver A needs e^{qu} but not e^{ru}, and one erfcx: reuse the B layout, skip the spare chains
                             double ex6[6] = {ex[0], ex[1], ex[2], ex[4], ex[5], ex[6]}, E6[6];
                             fast_exp_n<6, true>(ex6, E6);
@@ -263,15 +303,29 @@ __global__ void __launch_bounds__(kClenWarps * 32, 1) alo_clen_kernel(AloArgs a)
     }
 }
 
-template <int SOLVER, int PPL>
+template <int SOLVER, int PPL, bool SCR>
 static int launch_clen_t(const AloArgs& a, cudaStream_t st) {
     const size_t sm = sizeof(double) * (size_t)a.tl.small + sizeof(ClenWarpSmem) * kClenWarps;
-    FAOP_CUDA_OK(cudaFuncSetAttribute(alo_clen_kernel<SOLVER, PPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    FAOP_CUDA_OK(cudaFuncSetAttribute(alo_clen_kernel<SOLVER, PPL, SCR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     int64_t ctas = (a.N + kClenWarps - 1) / kClenWarps;
     int grid = (int)(ctas < kSMs ? ctas : kSMs);
-    alo_clen_kernel<SOLVER, PPL><<<grid, kClenWarps * 32, sm, st>>>(a);
+    alo_clen_kernel<SOLVER, PPL, SCR><<<grid, kClenWarps * 32, sm, st>>>(a);
     count_launch();
     return launch_status();
+}
+
+static bool clen_match(const faop_cfg& cfg) {
+    const int n = cfg.n_colloc, LP = 32 * ((cfg.n_quad + 31) / 32);
+    // n = 12, l <= 32 Solver A runs in the matrix kernel (faop_alo_fast.cu)
+    return !cfg.use_derivative && n % 4 == 0 && n + 1 <= kClenMaxNodes && LP <= 64;
+}
+
+// Scratch for the invariant tables: one region per resident warp of the persistent grid.  Used for Solver B (two of four
+// exponentials per point saved); Solver A would save one of three, which does not pay for the loads.
+size_t alo_clen_scratch_bytes(const faop_cfg& cfg) {
+    if (!clen_match(cfg) || cfg.solver != 1 || cfg.kernel == 1) return 0;
+    const int LP = 32 * ((cfg.n_quad + 31) / 32);
+    return sizeof(double) * (size_t)kSMs * kClenWarps * 2 * (size_t)cfg.n_colloc * LP;
 }
 
 int launch_alo_clen(const AloArgs& a, cudaStream_t st) {
@@ -279,8 +333,9 @@ int launch_alo_clen(const AloArgs& a, cudaStream_t st) {
     const bool match = !a.cfg.use_derivative && n % 4 == 0 && n + 1 <= kClenMaxNodes && a.tl.LP <= 64 && a.iter_errs == nullptr && a.snap == nullptr;
     if (!match) return -1000;
     if (a.N == 0) return 0;
-    if (a.cfg.solver == 0) return a.tl.LP == 64 ? launch_clen_t<0, 2>(a, st) : launch_clen_t<0, 1>(a, st);
-    return a.tl.LP == 64 ? launch_clen_t<1, 2>(a, st) : launch_clen_t<1, 1>(a, st);
+    if (a.cfg.solver == 0) return a.tl.LP == 64 ? launch_clen_t<0, 2, false>(a, st) : launch_clen_t<0, 1, false>(a, st);
+    if (a.inv_scratch) return a.tl.LP == 64 ? launch_clen_t<1, 2, true>(a, st) : launch_clen_t<1, 1, true>(a, st);
+    return a.tl.LP == 64 ? launch_clen_t<1, 2, false>(a, st) : launch_clen_t<1, 1, false>(a, st);
 }
 
 }  // namespace faop

@@ -96,7 +96,9 @@ int faop_workspace_bytes(const faop_cfg* cfg, int64_t N, size_t* bytes) {
     if (rc) return rc;
     if (!bytes || N < 0) return FAOP_EINVAL;
     size_t b = sizeof(double) * (size_t)N * (size_t)(cfg->n_colloc + 1);
-    *bytes = (b + 255) & ~(size_t)255;
+    b = (b + 255) & ~(size_t)255;
+    if (cfg->flags & FAOP_FLAG_WS_SCRATCH) b += alo_clen_scratch_bytes(*cfg);
+    *bytes = b;
     return 0;
 }
 
@@ -129,6 +131,8 @@ int faop_alo_price_batch(const faop_cfg* cfg, int64_t N, const double* r, const 
     cudaStream_t st = (cudaStream_t)cuda_stream;
     a.price = price; a.european = european; a.B = B; a.iters = iters; a.err = err; a.iter_errs = iter_errs;
     const size_t seed_bytes = sizeof(double) * (size_t)N * (size_t)(cfg->n_colloc + 1);
+    if (workspace && (cfg->flags & FAOP_FLAG_WS_SCRATCH) && alo_clen_scratch_bytes(*cfg))
+        a.inv_scratch = (double*)((char*)workspace + ((seed_bytes + 255) & ~(size_t)255));
     if (B0_in) {
         a.seeds_in = B0_in;
         if (B0_out && B0_out != B0_in) FAOP_CUDA_OK(cudaMemcpyAsync(B0_out, B0_in, seed_bytes, cudaMemcpyDeviceToDevice, st));
@@ -167,11 +171,13 @@ int faop_alo_surface_batch(const faop_cfg* cfg, const faop_surface* surf, int64_
     uint8_t* d_put = (uint8_t*)(w + 6 * chunk);
     double* d_seed = w + 7 * chunk;
     cudaStream_t st = (cudaStream_t)cuda_stream;
+    faop_cfg plain = *cfg;
+    plain.flags &= ~FAOP_FLAG_WS_SCRATCH;      // the chunk workspace below holds the seeds only
     for (int64_t off = 0; off < count; off += chunk) {
         int64_t cnt = count - off < chunk ? count - off : chunk;
         rc = launch_surface_decode(*surf, first + off, cnt, d_r, d_q, d_s, d_K, d_T, d_S, d_put, st);
         if (rc) return rc;
-        rc = faop_alo_price_batch(cfg, cnt, d_r, d_q, d_s, d_K, d_T, nullptr, d_S, d_put, tables_dev, nullptr, price + off,
+        rc = faop_alo_price_batch(&plain, cnt, d_r, d_q, d_s, d_K, d_T, nullptr, d_S, d_put, tables_dev, nullptr, price + off,
                                   nullptr, nullptr, nullptr, iters ? iters + off : nullptr, nullptr, nullptr, d_seed, st);
         if (rc) return rc;
     }

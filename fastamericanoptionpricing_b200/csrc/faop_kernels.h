@@ -23,6 +23,7 @@ struct AloArgs {
     // snapshot mode (deduplicated surface sweep, faop_surface.cu): instead of pricing, the solve records every iterate
     // whose error is a new minimum <= snap_tol_hi as a row [err, count, a_0..a_n] (a = DCT-I fit of ln(B/X)^2) and the
     // final iterate as a catch-all row with err = 0; cfg.iter_tol is the LOWEST tolerance any sharing option needs.
+    double* inv_scratch;     // nullable: per-warp scratch for e^{q u_ik}, e^{r u_ik} (faop_alo_clen.cu), kSMs*16 warps x 2*n*LP
     double* snap;            // N x snap_cap x (n+3)
     int32_t* nsnap;          // rows written per option; -1 = European shortcut (q == 0 call)
     int snap_cap;
@@ -47,6 +48,7 @@ int launch_alo_interp(const AloArgs& a, double* Bu, cudaStream_t st);
 int launch_alo_fast(const AloArgs& a, cudaStream_t st);
 // Clenshaw-based specialised kernels (faop_alo_clen.cu): Solver A/B, no derivative, n % 4 == 0, n <= 28, l <= 64
 int launch_alo_clen(const AloArgs& a, cudaStream_t st);
+size_t alo_clen_scratch_bytes(const faop_cfg& cfg);   // 0 when the config does not run there
 
 int launch_qd_boundary(int64_t N, const double* r, const double* q, const double* sigma, const double* K,
                        const double* tau, const uint8_t* is_put, double* B, cudaStream_t st);

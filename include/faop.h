@@ -54,8 +54,14 @@ typedef struct faop_cfg {
     double  eta;            /* 0.5 in the reference                                           */
     int32_t kernel;         /* 0 = auto (specialised kernel when one exists for (solver,n,l)),
                                1 = force the generic kernel; results agree to rounding          */
-    int32_t reserved;
+    int32_t flags;          /* FAOP_FLAG_* bits, 0 in the reference-equivalent default                        */
 } faop_cfg;
+
+/* `workspace` was sized by faop_workspace_bytes() with this same flag set: besides the QD seeds it then holds the
+ * per-warp scratch in which the n > 12 kernels keep the iteration-invariant tables e^{q u_ik}, e^{r u_ik} (they stay in L2
+ * and save two of Solver B's four exponentials per quadrature point).  Without the flag (or with workspace == NULL) those
+ * values are recomputed; results are identical to rounding.                                                            */
+#define FAOP_FLAG_WS_SCRATCH 1
 
 /* ---- tables ---------------------------------------------------------------------------------
  * Gauss-Legendre nodes/weights are produced by the CALLER with numpy.polynomial.legendre.leggauss
@@ -69,7 +75,8 @@ int faop_tables_build(const faop_cfg* cfg, const double* y_l, const double* w_l,
                       const double* y_m, const double* w_m,                     /* leggauss(m) */
                       void* host_out);
 
-/* Device scratch needed by faop_alo_price_batch for N options (QD seeds when B0_out is NULL). */
+/* Device scratch needed by faop_alo_price_batch for N options: the QD seeds (used when B0_out is NULL) and, with
+ * FAOP_FLAG_WS_SCRATCH, the invariant-table scratch (a fixed ~58 MB at n = 24, l = 64, independent of N). */
 int faop_workspace_bytes(const faop_cfg* cfg, int64_t N, size_t* bytes);
 
 /* ---- the hot path -----------------------------------------------------------------------------
