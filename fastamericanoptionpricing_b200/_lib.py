@@ -52,6 +52,7 @@ _SIGNATURES = {
     "faop_cheb_eval_batch": (ctypes.c_int, [c_i64, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp]),
     "faop_cn_workspace_bytes": (ctypes.c_int, [c_i64, c_i32, c_i32, _P(c_sz)]),
     "faop_cn_put_batch": (ctypes.c_int, [c_i64, c_i32, c_i32] + [c_vp] * 7 + [c_i32, c_dbl, c_dbl, c_i32] + [c_vp] * 4),
+    "faop_cn_put_countdown_batch": (ctypes.c_int, [c_i64, c_i32, c_i32] + [c_vp] * 7 + [c_dbl, c_dbl, c_i32] + [c_vp] * 4),
     "faop_ctx_create": (ctypes.c_int, [ctypes.c_int, _P(c_vp)]),
     "faop_ctx_destroy": (ctypes.c_int, [c_vp]),
     "faop_alo_price_batch_host": (ctypes.c_int, [c_vp, _P(FaopCfg), c_i64] + [c_vp] * 19),

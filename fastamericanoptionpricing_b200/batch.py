@@ -545,28 +545,37 @@ CN_MODE_DIRECT, CN_MODE_SOR, CN_MODE_PROJECTED = 0, 1, 2
 
 
 def cn_put_batch(r, q, sigma, K, T, S0, n_space=200, max_dt=1 / 12.0, mode=CN_MODE_PROJECTED, omega=1.2, tol=1e-5,
-                 max_iter=200, want_grid=False, device=None):
+                 max_iter=200, want_grid=False, device=None, schedule=None):
     """CNOptionSolver(r,q,sigma,K,T).solve(S0) for a batch of American puts (CrankNicolsonOptionSolver.py:27-107).
     mode 0 = the reference default (dense solve, no projection), 1 = the reference's SOR+project loop,
-    2 = projected tridiagonal sweep.  Returns price (and the final grid values X, N x n_space)."""
+    2 = projected tridiagonal sweep.  Returns price (and the final grid values X, N x n_space).
+    The time steps are the reference's float countdown from T in steps of max_dt, run on the device
+    (faop_cn_put_countdown_batch); schedule=(dts [N x steps], n_steps [N]) supplies explicit steps instead."""
     lib = _lib.load()
     dev, N, (r, q, sigma, K, T, S0) = _common([r, q, sigma, K, T, S0], device)
     with torch.cuda.device(dev):
-        dts, ns = cn_dt_schedule_batch(T.cpu().numpy(), np.broadcast_to(np.asarray(max_dt, dtype=np.float64), (N,)))
-        dts_d = torch.from_numpy(np.ascontiguousarray(dts)).to(dev)
-        ns_d = torch.from_numpy(ns).to(dev)
         price = torch.empty(N, dtype=torch.float64, device=dev)
         X = torch.empty((N, n_space), dtype=torch.float64, device=dev) if want_grid else None
         nb = ctypes.c_size_t()
         check(lib.faop_cn_workspace_bytes(N, n_space, mode, ctypes.byref(nb)), "faop_cn_workspace_bytes")
         ws = torch.empty(max(nb.value, 1), dtype=torch.uint8, device=dev)
-        check(lib.faop_cn_put_batch(N, n_space, mode, _ptr(r), _ptr(q), _ptr(sigma), _ptr(K), _ptr(S0), _ptr(dts_d),
-                                    _ptr(ns_d), dts.shape[1], float(omega), float(tol), int(max_iter), _ptr(price), _ptr(X),
-                                    _ptr(ws), _stream(dev)), "faop_cn_put_batch")
+        if schedule is None:
+            mdt = _f64(np.broadcast_to(np.asarray(max_dt.cpu() if isinstance(max_dt, torch.Tensor) else max_dt, dtype=np.float64),
+                                       (N,)).copy(), dev, N)
+            check(lib.faop_cn_put_countdown_batch(N, n_space, mode, _ptr(r), _ptr(q), _ptr(sigma), _ptr(K), _ptr(T), _ptr(S0),
+                                                  _ptr(mdt), float(omega), float(tol), int(max_iter), _ptr(price), _ptr(X),
+                                                  _ptr(ws), _stream(dev)), "faop_cn_put_countdown_batch")
+        else:
+            dts, ns = schedule
+            dts = np.ascontiguousarray(dts, dtype=np.float64)
+            dts_d = torch.from_numpy(dts).to(dev)
+            ns_d = torch.from_numpy(np.ascontiguousarray(ns, dtype=np.int32)).to(dev)
+            check(lib.faop_cn_put_batch(N, n_space, mode, _ptr(r), _ptr(q), _ptr(sigma), _ptr(K), _ptr(S0), _ptr(dts_d),
+                                        _ptr(ns_d), dts.shape[1], float(omega), float(tol), int(max_iter), _ptr(price), _ptr(X),
+                                        _ptr(ws), _stream(dev)), "faop_cn_put_batch")
         return (price, X) if want_grid else price
 
 
-# ------------------------------------------------------------------------------------------ misc
 def launch_count():
     return int(_lib.load().faop_launch_count())
 

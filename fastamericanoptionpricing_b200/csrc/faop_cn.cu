@@ -29,6 +29,7 @@ struct CnArgs {
     int n_space, max_steps, mode, max_iter;
     const double *r, *q, *sigma, *K, *S0, *dts;
     const int32_t* n_steps;
+    const double *T, *max_dt;   // countdown mode (dts == nullptr): the kernel runs solvePDE's own float countdown
     double omega, tol;
     double *price, *X_out, *ws;
 };
@@ -122,13 +123,22 @@ __global__ void __launch_bounds__(kCnThreads, (NPT <= 8 ? 2 : 1)) cn_scan_kernel
             Q[j] = R[j] = 0.0;
         }
         double Af[5], Ab[5], excA = 0.0, nxtA = 0.0, cR3 = 0.0, cR4 = 0.0, cinv = 0.0;
-        const int nsteps = a.n_steps[opt];
+        // time stepping: either the caller's schedule, or solvePDE's countdown `while t > 0: dt = min(t, max_dt); ...; t -= dt`
+        // (CrankNicolsonOptionSolver.py:36-45) in the same IEEE arithmetic, including its last ~1e-16-long step
+        const bool sched = a.dts != nullptr;
+        const int nsteps = sched ? a.n_steps[opt] : 0;
+        double trem = sched ? 0.0 : a.T[opt];
+        const double mdt = sched ? 0.0 : a.max_dt[opt];
         double dt_prev = -1.0;
         __syncthreads();                          // the previous option's output pass is done with s_seq
         if (lane == 0) s_eL[warp] = X[0];
         if (lane == 31) s_eR[warp] = X[NPT - 1];
-        for (int st = 0; st < nsteps; ++st) {
-            const double dt = a.dts[opt * a.max_steps + st];
+        for (int st = 0; sched ? st < nsteps : trem > 0; ++st) {
+            const double dt = sched ? a.dts[opt * a.max_steps + st] : fmin(trem, mdt);
+            if (!sched) {
+                if (!(dt > 0)) break;     // max_dt <= 0 never terminates upstream
+                trem -= dt;
+            }
             if (dt != dt_prev) {
                 // ---- coefficients for this dt (setCoeff, :55-79) and the c' recurrence of the elimination
                 __syncthreads();   // nobody still reads the previous dt's rows or s_seq
@@ -366,9 +376,16 @@ __global__ void __launch_bounds__(64) cn_sor_kernel(CnArgs a) {
     const double omega = a.omega;
     for (int i = 0; i < n; ++i) X[i * ld] = fmax(K - grid_point(i, n, K), 0.0);
     const double dS = grid_point(1, n, K) - grid_point(0, n, K);
-    const int nsteps = a.n_steps[opt];
-    for (int st = 0; st < nsteps; ++st) {
-        const double dt = a.dts[opt * a.max_steps + st];
+    const bool sched = a.dts != nullptr;
+    const int nsteps = sched ? a.n_steps[opt] : 0;
+    double trem = sched ? 0.0 : a.T[opt];
+    const double mdt = sched ? 0.0 : a.max_dt[opt];
+    for (int st = 0; sched ? st < nsteps : trem > 0; ++st) {
+        const double dt = sched ? a.dts[opt * a.max_steps + st] : fmin(trem, mdt);
+        if (!sched) {
+            if (!(dt > 0)) break;
+            trem -= dt;
+        }
         for (int i = 0; i < n - 1; ++i) {
             double S = grid_point(i, n, K);
             double aa = sg * S / dS;
@@ -458,6 +475,30 @@ int faop_cn_put_batch(int64_t N, int32_t n_space, int32_t mode, const double* r,
     CnArgs a;
     a.N = N; a.n_space = n_space; a.max_steps = max_steps; a.mode = mode; a.max_iter = max_iter;
     a.r = r; a.q = q; a.sigma = sigma; a.K = K; a.S0 = S0; a.dts = dts; a.n_steps = n_steps;
+    a.T = nullptr; a.max_dt = nullptr;
+    a.omega = omega; a.tol = tol; a.price = price; a.X_out = X_out; a.ws = (double*)workspace;
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    if (mode == 1) {
+        cn_sor_kernel<<<(unsigned)((N + 63) / 64), 64, 0, st>>>(a);
+        count_launch();
+        return launch_status();
+    }
+    return mode == 2 ? launch_scan_npt<true>(a, st) : launch_scan_npt<false>(a, st);
+}
+
+int faop_cn_put_countdown_batch(int64_t N, int32_t n_space, int32_t mode, const double* r, const double* q,
+                                const double* sigma, const double* K, const double* T, const double* S0, const double* max_dt,
+                                double omega, double tol, int32_t max_iter, double* price, double* X_out, void* workspace,
+                                void* cuda_stream) {
+    if (N < 0 || n_space < 5 || mode < 0 || mode > 2) return FAOP_EINVAL;
+    if (n_space > kCnThreads * 16) return FAOP_ERANGE;
+    if (N == 0) return 0;
+    if (!r || !q || !sigma || !K || !T || !S0 || !max_dt || !price) return FAOP_EINVAL;
+    if (mode == 1 && !workspace) return FAOP_EINVAL;
+    CnArgs a;
+    a.N = N; a.n_space = n_space; a.max_steps = 0; a.mode = mode; a.max_iter = max_iter;
+    a.r = r; a.q = q; a.sigma = sigma; a.K = K; a.S0 = S0; a.dts = nullptr; a.n_steps = nullptr;
+    a.T = T; a.max_dt = max_dt;
     a.omega = omega; a.tol = tol; a.price = price; a.X_out = X_out; a.ws = (double*)workspace;
     cudaStream_t st = (cudaStream_t)cuda_stream;
     if (mode == 1) {

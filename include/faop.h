@@ -234,6 +234,15 @@ int faop_cn_put_batch(int64_t N, int32_t n_space, int32_t mode,
                       double omega, double tol, int32_t max_iter,
                       double* price, double* X_out, void* workspace, void* cuda_stream);
 
+/* The same solver with the time stepping of CNOptionSolver.solvePDE itself (:36-45): `while t > 0: dt = min(t, max_dt); ...;
+ * t -= dt`, run on the device in the same IEEE arithmetic from per-option T and max_dt — no N x steps schedule to build or
+ * copy (1.6 GB at C4).  Identical results to faop_cn_put_batch fed with that countdown's schedule.                        */
+int faop_cn_put_countdown_batch(int64_t N, int32_t n_space, int32_t mode,
+                                const double* r, const double* q, const double* sigma, const double* K,
+                                const double* T, const double* S0, const double* max_dt,
+                                double omega, double tol, int32_t max_iter,
+                                double* price, double* X_out, void* workspace, void* cuda_stream);
+
 /* ---- host-buffer convenience (what a non-torch caller binds) ----------------------------------
  * A context owns a device, a stream, device scratch, pinned staging buffers and the table blobs it
  * has built; it grows on demand and is freed by faop_ctx_destroy.  One context per host thread.    */

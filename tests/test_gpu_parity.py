@@ -754,3 +754,22 @@ def test_tanh_sinh_and_undamped_newton_opt_in():
     assert both.sum() > 0.8 * N
     assert np.nanmax(np.abs(dn["B"] / gl["B"] - 1)[both]) <= 1e-7 and np.abs(dn["price"] - gl["price"])[both].max() <= 1e-7
     # (for Solver A the undamped step is not faster than the reference's damping: ~45 against ~34 sweeps to 1e-9 here)
+
+
+def test_cn_device_countdown_equals_host_schedule():
+    """faop_cn_put_countdown_batch (solvePDE's float countdown run on the device, CrankNicolsonOptionSolver.py:36-45) ==
+    faop_cn_put_batch fed with the schedule of the same countdown built on the host, bit for bit, in all three modes,
+    including maturities that are not a multiple of max_dt and the ~1e-16-long last step (SURVEY App. B#14)."""
+    b = {k: v[:48] for k, v in wl.c4_batch(48).items()}
+    a = [b[k] for k in ("r", "q", "sigma", "K", "T", "S")]
+    for n_space, max_dt in ((200, 1 / 12.0), (300, b["T"] / 37), (64, 0.3)):
+        mdt = np.broadcast_to(np.asarray(max_dt, dtype=np.float64), (48,))
+        sched = batch.cn_dt_schedule_batch(b["T"], mdt)
+        assert sched[1].min() >= 1 and (np.abs(sched[0].sum(axis=1) - b["T"]) < 1e-12).all()
+        for mode in (0, 1, 2):
+            cnt = 8 if mode == 1 else 48
+            aa = [x[:cnt] for x in a]
+            p1, X1 = batch.cn_put_batch(*aa, n_space=n_space, max_dt=mdt[:cnt], mode=mode, want_grid=True)
+            p2, X2 = batch.cn_put_batch(*aa, n_space=n_space, max_dt=mdt[:cnt], mode=mode, want_grid=True,
+                                        schedule=(sched[0][:cnt], sched[1][:cnt]))
+            assert torch.equal(p1, p2) and torch.equal(X1, X2), (n_space, mode)
