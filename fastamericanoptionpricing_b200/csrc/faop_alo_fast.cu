@@ -1,6 +1,8 @@
 // faop_alo_fast.cu — specialised boundary + price kernel for the flagship configuration
 // (FastAmericanOptionSolverA, no derivative, n = 12 collocation nodes, l <= 32 quadrature points):
-// BASELINE.json configs[1] (C2), configs[4] (C5) and the reference's own testA case (C1).
+// BASELINE.json configs[1] (C2), configs[4] (C5) and the reference's own testA case (C1) — and, as the SOLVER = 1
+// instantiation, FastAmericanOptionSolverB at the same sizes (the reference's testB case: per point two Phi instead of
+// one Phi and two phi, FastAmericanOptionSolverB.py:25-39, with both invariant tables w e^{qu}, w e^{ru} in shared memory).
 //
 // One option per warp, lane = quadrature index k.  What makes it fast (all FP64-pipe instruction savings):
 //   * H(u_ik) comes from the option-independent interpolation matrix M[i][j][k] staged once per CTA in shared
@@ -21,8 +23,10 @@ constexpr int NC = 12;        // collocation n
 constexpr int NN = NC + 1;    // nodes
 constexpr int kGroup = 4;     // nodes per transposing reduction
 
+template <int SOLVER>
 struct FastWarpSmem {
     double eq[NC * 32];   // w_k e^{q u_ik}, [i][k]
+    double er[SOLVER == 1 ? NC * 32 : 1];   // w_k e^{r u_ik} (Solver B only)
     NodePack node[16];
     double B[16], L[16], H[16], A[16];
     double tau[16], disc[16];
@@ -31,13 +35,13 @@ struct FastWarpSmem {
     double red[8 * 36];   // transpose buffer of the per-group reduction, row pitch 36 = 4 (mod 16): conflict-free both ways
 };
 
-template <int kFastWarps, bool SNAP = false>
+template <int kFastWarps, bool SNAP = false, int SOLVER = 0>
 __global__ void __launch_bounds__(kFastWarps * 32, 1) alo_fast_A12_kernel(AloArgs a) {
     extern __shared__ double smem[];
     const TableLayout tl = a.tl;
     double* s_tab = smem;
     double* s_M = smem + tl.small;          // re-laid out as M2[i][j/2][k][j&1], j < 12: one 16-byte load feeds two DFMAs
-    FastWarpSmem* s_w = reinterpret_cast<FastWarpSmem*>(s_M + NC * NC * 32);
+    FastWarpSmem<SOLVER>* s_w = reinterpret_cast<FastWarpSmem<SOLVER>*>(s_M + NC * NC * 32);
     for (int i = threadIdx.x; i < tl.small; i += blockDim.x) smem[i] = a.tables[i];
     for (int e = threadIdx.x; e < NC * NC * 32; e += blockDim.x) {
         const int k = e & 31, j = (e >> 5) % NC, i = e / (32 * NC);
@@ -47,7 +51,7 @@ __global__ void __launch_bounds__(kFastWarps * 32, 1) alo_fast_A12_kernel(AloArg
     __syncthreads();
     const CtaTables tb(s_tab, tl);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    FastWarpSmem& ws = s_w[warp];
+    FastWarpSmem<SOLVER>& ws = s_w[warp];
 
     // lane constants of the l-point rule
     const double h = tb.hl[lane], rh = tb.rhl[lane], sgk = tb.sgl[lane], wk = tb.wl[lane];
@@ -103,7 +107,10 @@ __global__ void __launch_bounds__(kFastWarps * 32, 1) alo_fast_A12_kernel(AloArg
         }
         __syncwarp();
 #pragma unroll
-        for (int i = 0; i < NC; ++i) ws.eq[i * 32 + lane] = wk * fast_exp(oq * ws.tau[i] * g);
+        for (int i = 0; i < NC; ++i) {
+            ws.eq[i * 32 + lane] = wk * fast_exp(oq * ws.tau[i] * g);
+            if (SOLVER == 1) ws.er[i * 32 + lane] = wk * fast_exp(orr * ws.tau[i] * g);
+        }
 
         int count = 0;
         double err = 1.0;
@@ -149,31 +156,49 @@ __global__ void __launch_bounds__(kFastWarps * 32, 1) alo_fast_A12_kernel(AloArg
                             Hu[p] = acc0;
                         }
                         sqrt_clamped_n<2>(Hu, root);        // sqrt(max(0, H)), NaN propagates
-                        double ex[4], xa[2], xp[2], cis[2];
+                        double ex[4], xa[4], xp[2], xm[2], cis[2];
 #pragma unroll
                         for (int p = 0; p < 2; ++p) {
                             const NodePack& nd = ws.node[i0 + p];
                             const double lnz = fma(om, root[p], nd.L);
                             xp[p] = fma(lnz, nd.cinv2 * rh, nd.apc2 * h);        // d+ / sqrt2
-                            const double xm = fma(-nd.ssu2, h, xp[p]);             // d- / sqrt2
-                            ex[2 * p] = fma(-xp[p], xp[p], fma(nd.qtau, g, lnw));  // ln w + q u - d+^2/2
-                            ex[2 * p + 1] = fma(-xm, xm, fma(nd.rtau, g, lnw));    // ln w + r u - d-^2/2
-                            xa[p] = fabs(xp[p]);
+                            xm[p] = fma(-nd.ssu2, h, xp[p]);                       // d- / sqrt2
+                            ex[2 * p] = fma(-xp[p], xp[p], fma(nd.qtau, g, lnw));        // ln w + q u - d+^2/2
+                            ex[2 * p + 1] = fma(-xm[p], xm[p], fma(nd.rtau, g, lnw));    // ln w + r u - d-^2/2
+                            xa[2 * p] = fabs(xp[p]);
+                            xa[2 * p + 1] = fabs(xm[p]);
                             cis[p] = nd.cis;
                         }
-                        double E[4], G[2];
+                        double E[4];
                         fast_exp_n<4, true>(ex, E);         // E[2p] = w e^{qu} phi(d+) sqrt(2 pi), E[2p+1] = w e^{ru} phi(d-) sqrt(2 pi)
-                        half_erfcx_n<2, true>(xa, G);
+                        if (SOLVER == 0) {
+                            double xa2[2] = {xa[0], xa[2]}, G[2];
+                            half_erfcx_n<2, true>(xa2, G);
 #pragma unroll
-                        for (int p = 0; p < 2; ++p) {
-                            // put: +w e^{qu} Phi(d+); call: -w e^{qu} Phi(-d+)   (FastAmericanOptionSolverA.py:27-32)
-                            const double ec = E[2 * p] * G[p];
-                            const double eqw = ws.eq[(i0 + p) * 32 + lane];
-                            const bool neg = (__double2hiint(xp[p]) ^ sgn) < 0;   // om * d+ < 0 (both branches agree at 0)
-                            double cdf = neg ? ec : eqw - ec;
-                            cdf = __hiloint2double(__double2hiint(cdf) ^ sgn, __double2loint(cdf));  // times om
-                            acc[4 * pr + 2 * p] = E[2 * p + 1];                          // -> K3  = tau cinv/sqrt(2 pi) * sum
-                            acc[4 * pr + 2 * p + 1] = fma(cis[p], E[2 * p], h * cdf);    // -> K12 = tau * sum
+                            for (int p = 0; p < 2; ++p) {
+                                // put: +w e^{qu} Phi(d+); call: -w e^{qu} Phi(-d+)   (FastAmericanOptionSolverA.py:27-32)
+                                const double ec = E[2 * p] * G[p];
+                                const double eqw = ws.eq[(i0 + p) * 32 + lane];
+                                const bool neg = (__double2hiint(xp[p]) ^ sgn) < 0;   // om * d+ < 0 (both branches agree at 0)
+                                double cdf = neg ? ec : eqw - ec;
+                                cdf = __hiloint2double(__double2hiint(cdf) ^ sgn, __double2loint(cdf));  // times om
+                                acc[4 * pr + 2 * p] = E[2 * p + 1];                          // -> K3  = tau cinv/sqrt(2 pi) * sum
+                                acc[4 * pr + 2 * p + 1] = fma(cis[p], E[2 * p], h * cdf);    // -> K12 = tau * sum
+                            }
+                        } else {
+                            double G[4];
+                            half_erfcx_n<4, true>(xa, G);
+#pragma unroll
+                            for (int p = 0; p < 2; ++p) {
+                                // w e^{qu} Phi(om d+) and w e^{ru} Phi(om d-)   (FastAmericanOptionSolverB.py:25-39)
+                                const double ecp = E[2 * p] * G[2 * p], ecm = E[2 * p + 1] * G[2 * p + 1];
+                                const bool negp = (__double2hiint(xp[p]) ^ sgn) < 0;
+                                const bool negm = (__double2hiint(xm[p]) ^ sgn) < 0;
+                                const double cdfp = negp ? ecp : ws.eq[(i0 + p) * 32 + lane] - ecp;
+                                const double cdfm = negm ? ecm : ws.er[(i0 + p) * 32 + lane] - ecm;
+                                acc[4 * pr + 2 * p] = h * cdfm;          // -> N integral = tau * sum
+                                acc[4 * pr + 2 * p + 1] = h * cdfp;      // -> D integral = tau * sum
+                            }
                         }
                     }
                     const double tot = transpose_reduce8(acc, ws.red, lane);
@@ -199,10 +224,16 @@ __global__ void __launch_bounds__(kFastWarps * 32, 1) alo_fast_A12_kernel(AloArg
                     const double xpK = fma(LK, nd.cinv2, nd.apc2);      // d+(tau_i, B_i/K) / sqrt2
                     const double xmK = xpK - nd.ssu2;
                     const double Ep = fast_exp(-xpK * xpK), Em = fast_exp(-xmK * xmK);
-                    const double K3 = tau * nd.cis * ws.sN[lane];
-                    const double K12 = tau * ws.sD[lane];
-                    const double Nv = Em * nd.cis + orr * K3;                                               // A.py:5-10
-                    const double Dv = Ep * nd.cis + om * fast_half_erfcx_cdf(om * xpK, Ep) + oq * K12;      // A.py:13-19
+                    double Nv, Dv;
+                    if (SOLVER == 0) {
+                        const double K3 = tau * nd.cis * ws.sN[lane];
+                        const double K12 = tau * ws.sD[lane];
+                        Nv = Em * nd.cis + orr * K3;                                               // A.py:5-10
+                        Dv = Ep * nd.cis + om * fast_half_erfcx_cdf(om * xpK, Ep) + oq * K12;      // A.py:13-19
+                    } else {
+                        Nv = fast_half_erfcx_cdf(om * xmK, Em) + orr * (tau * ws.sN[lane]);        // B.py:5-13
+                        Dv = fast_half_erfcx_cdf(om * xpK, Ep) + oq * (tau * ws.sD[lane]);         // B.py:15-23
+                    }
                     const double f = ws.disc[lane] * Nv / Dv;                                               // Base.py:273
                     Bn = Bj + a.cfg.eta * (Bj - f) / (0.0 - 1.0);                                           // Base.py:164
                 }
@@ -236,23 +267,23 @@ __global__ void __launch_bounds__(kFastWarps * 32, 1) alo_fast_A12_kernel(AloArg
     }
 }
 
-template <int kFastWarps, bool SNAP = false>
+template <int kFastWarps, bool SNAP = false, int SOLVER = 0>
 static int launch_fast_t(const AloArgs& a, cudaStream_t st) {
-    const size_t sm = sizeof(double) * (size_t)(a.tl.small + NC * NC * 32) + sizeof(FastWarpSmem) * kFastWarps;
-    FAOP_CUDA_OK(cudaFuncSetAttribute(alo_fast_A12_kernel<kFastWarps, SNAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    const size_t sm = sizeof(double) * (size_t)(a.tl.small + NC * NC * 32) + sizeof(FastWarpSmem<SOLVER>) * kFastWarps;
+    FAOP_CUDA_OK(cudaFuncSetAttribute(alo_fast_A12_kernel<kFastWarps, SNAP, SOLVER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     int64_t ctas = (a.N + kFastWarps - 1) / kFastWarps;
     int grid = (int)(ctas < kSMs ? ctas : kSMs);
-    alo_fast_A12_kernel<kFastWarps, SNAP><<<grid, kFastWarps * 32, sm, st>>>(a);
+    alo_fast_A12_kernel<kFastWarps, SNAP, SOLVER><<<grid, kFastWarps * 32, sm, st>>>(a);
     count_launch();
     return launch_status();
 }
 
 // cfg.kernel: 0 = default (16 warps/CTA, <= 128 registers/thread); tuning variants 2 / 3 = 12 / 20 warps per CTA
 int launch_alo_fast(const AloArgs& a, cudaStream_t st) {
-    const bool match = a.cfg.solver == 0 && !a.cfg.use_derivative && a.tl.n == NC && a.tl.LP == 32 && a.tl.has_matrix &&
-                       a.iter_errs == nullptr;
+    const bool match = !a.cfg.use_derivative && a.tl.n == NC && a.tl.LP == 32 && a.tl.has_matrix && a.iter_errs == nullptr;
     if (!match) return -1000;
     if (a.N == 0) return 0;
+    if (a.cfg.solver == 1) return a.snap ? launch_fast_t<16, true, 1>(a, st) : launch_fast_t<16, false, 1>(a, st);
     if (a.snap) return launch_fast_t<16, true>(a, st);
     if (a.cfg.kernel == 2) return launch_fast_t<12>(a, st);
     if (a.cfg.kernel == 3) return launch_fast_t<20>(a, st);

@@ -27,13 +27,13 @@ for name, cfg in (("C2 A n12 l32 m64 (specialised)", AloConfig(**wl.C2_CFG)),
                   ("C2 A n12 l32 m64 (generic kernel)", AloConfig(kernel=1, **wl.C2_CFG)),
                   ("C1-style A n12 l24 m48 tol1e-5 max20 (specialised)", AloConfig("A", 12, 24, 48, 1e-5, 20)),
                   ("A+derivative n12 l32 m64 (generic)", AloConfig(**{**wl.C2_CFG, "use_derivative": True})),
-                  ("B n12 l32 m64 max_iters 200 (Clenshaw specialised)", AloConfig(**{**wl.C2_CFG, "solver": "B", "max_iters": 200}))):
+                  ("B n12 l32 m64 max_iters 200 (specialised, matrix kernel)", AloConfig(**{**wl.C2_CFG, "solver": "B", "max_iters": 200}))):
     ms, out = timeit(lambda: batch.price_batch(*a2, cfg=cfg, want_boundary=False))
     rows.append((name, N, ms, N / ms * 1e3, float(out["iters"].double().mean()), int(torch.isnan(out["price"]).sum())))
 N3 = 200_000
 a3 = dev(wl.c3_batch(N3))
 ms, out = timeit(lambda: batch.price_batch(*a3, cfg=AloConfig(**wl.C3_CFG), want_boundary=False), reps=2)
-rows.append(("C3 B n24 l64 m128 max_iters 200 (Clenshaw specialised)", N3, ms, N3 / ms * 1e3, float(out["iters"].double().mean()), int(torch.isnan(out["price"]).sum())))
+rows.append(("C3 B n24 l64 m128 max_iters 200 (Clenshaw + L2 scratch)", N3, ms, N3 / ms * 1e3, float(out["iters"].double().mean()), int(torch.isnan(out["price"]).sum())))
 surf = dict(K0=50.0, K1=150.0, T0=1.0 / 52, T1=3.0, V0=0.10, V1=0.60, S=100.0, r=0.04, q=0.01, nK=1000, nT=1000, nV=100)
 N5 = 4_000_000
 ms, out = timeit(lambda: batch.surface_batch(surf, 48_000_000, N5, AloConfig(**wl.C5_CFG), want_iters=True), reps=2)
