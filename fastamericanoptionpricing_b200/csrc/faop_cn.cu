@@ -245,8 +245,12 @@ __global__ void __launch_bounds__(kCnThreads, (NPT <= 8 ? 2 : 1)) cn_scan_kernel
             }
             if (lane == 31) s_fwB[warp] = b;
             __syncthreads();
-            double din = 0.0;  // d' entering this warp
-            for (int w = 0; w < warp; ++w) din = fma(s_fwA[w], din, s_fwB[w]);
+            double din = 0.0;  // d' entering this warp: fixed trip count, so the 14 broadcast loads issue ahead of the FMA chain
+#pragma unroll
+            for (int w = 0; w < kCnWarps - 1; ++w) {
+                const double Aw = s_fwA[w], Bw = s_fwB[w];
+                if (w < warp) din = fma(Aw, din, Bw);
+            }
             const double eb = __shfl_up_sync(kFullMask, b, 1);
             double dprev = (lane == 0) ? din : fma(excA, din, eb);
 #pragma unroll
@@ -290,9 +294,11 @@ __global__ void __launch_bounds__(kCnThreads, (NPT <= 8 ? 2 : 1)) cn_scan_kernel
                 const double p4 = fma(cR4, p3, s_clo[0]);
                 double v = (p4 - 4.0 * p3 + 5.0 * p2) * cinv;
                 if (PROJ) v = dmax(v, s_misc[1]);
-                for (int w = kCnWarps - 1; w > warp; --w) {
-                    const double y = fma(s_bwA[w], v, s_bwB[w]);
-                    v = PROJ ? dmax(y, s_bwC[w]) : y;
+#pragma unroll
+                for (int w = kCnWarps - 1; w > 0; --w) {
+                    const double Aw = s_bwA[w], Bw = s_bwB[w], Cw = PROJ ? s_bwC[w] : 0.0;
+                    const double y = fma(Aw, v, Bw);
+                    if (w > warp) v = PROJ ? dmax(y, Cw) : y;
                 }
                 const double nB = __shfl_down_sync(kFullMask, B, 1);
                 double nC = 0.0;
