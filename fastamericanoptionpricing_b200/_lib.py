@@ -29,6 +29,7 @@ _SIGNATURES = {
     "faop_launch_count": (c_i64, []),
     "faop_tables_bytes": (ctypes.c_int, [_P(FaopCfg), _P(c_sz)]),
     "faop_tables_build": (ctypes.c_int, [_P(FaopCfg), c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "faop_gauss_legendre_host": (ctypes.c_int, [c_i32, c_vp, c_vp]),
     "faop_workspace_bytes": (ctypes.c_int, [_P(FaopCfg), c_i64, _P(c_sz)]),
     "faop_alo_price_batch": (ctypes.c_int, [_P(FaopCfg), c_i64] + [c_vp] * 19),
     "faop_alo_surface_batch": (ctypes.c_int, [_P(FaopCfg), _P(FaopSurface), c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),

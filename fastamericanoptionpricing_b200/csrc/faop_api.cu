@@ -91,6 +91,43 @@ int faop_tables_build(const faop_cfg* cfg, const double* y_l, const double* w_l,
     return 0;
 }
 
+// Gauss-Legendre rule for callers without numpy: Newton iteration on P_n in long double from the Chebyshev-like initial
+// guess cos(pi (k + 3/4) / (n + 1/2)), nodes ascending as numpy.polynomial.legendre.leggauss returns them.  Agrees with
+// numpy's eigenvalue-based rule to ~1e-16; callers that need the reference's exact bits pass numpy's arrays instead.
+int faop_gauss_legendre_host(int32_t n, double* y, double* w) {
+    if (n < 1 || n > FAOP_MAX_QUAD || !y || !w) return FAOP_EINVAL;
+    for (int k = 0; k < (n + 1) / 2; ++k) {
+        long double x = cosl(M_PIl * (k + 0.75L) / (n + 0.5L)), dp = 1.0L;
+        for (int it = 0; it < 100; ++it) {
+            long double p0 = 1.0L, p1 = x;
+            for (int j = 2; j <= n; ++j) {
+                long double p2 = ((2 * j - 1) * x * p1 - (j - 1) * p0) / j;
+                p0 = p1;
+                p1 = p2;
+            }
+            if (n == 1) { p0 = 1.0L; p1 = x; }
+            dp = n * (x * p1 - p0) / (x * x - 1.0L);
+            long double dx = p1 / dp;
+            x -= dx;
+            if (fabsl(dx) < 1e-19L) break;
+        }
+        {   // derivative at the converged node for the weight
+            long double p0 = 1.0L, p1 = x;
+            for (int j = 2; j <= n; ++j) {
+                long double p2 = ((2 * j - 1) * x * p1 - (j - 1) * p0) / j;
+                p0 = p1;
+                p1 = p2;
+            }
+            dp = n * (x * p1 - p0) / (x * x - 1.0L);
+        }
+        long double wt = 2.0L / ((1.0L - x * x) * dp * dp);
+        y[k] = (double)(-x); y[n - 1 - k] = (double)x;
+        w[k] = (double)wt; w[n - 1 - k] = (double)wt;
+    }
+    if (n & 1) y[n / 2] = 0.0;
+    return 0;
+}
+
 int faop_workspace_bytes(const faop_cfg* cfg, int64_t N, size_t* bytes) {
     int rc = check_cfg(cfg);
     if (rc) return rc;

@@ -75,6 +75,11 @@ int faop_tables_build(const faop_cfg* cfg, const double* y_l, const double* w_l,
                       const double* y_m, const double* w_m,                     /* leggauss(m) */
                       void* host_out);
 
+/* Convenience for callers without numpy: the n-point Gauss-Legendre rule on [-1, 1] (nodes ascending), host code.  Agrees
+ * with numpy.polynomial.legendre.leggauss to 1e-16 in the nodes and 1e-14 in the weights (numpy's own rounding), not bit for
+ * bit; prices move by ~1e-13.                                                                                            */
+int faop_gauss_legendre_host(int32_t n, double* y, double* w);
+
 /* Device scratch needed by faop_alo_price_batch for N options: the QD seeds (used when B0_out is NULL) and, with
  * FAOP_FLAG_WS_SCRATCH, the invariant-table scratch (a fixed ~58 MB at n = 24, l = 64, independent of N). */
 int faop_workspace_bytes(const faop_cfg* cfg, int64_t N, size_t* bytes);

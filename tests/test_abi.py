@@ -84,3 +84,27 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 txt = open(os.path.join(root, f)).read()
                 assert not re.search(r"(import\s+oracle|from\s+oracle|from\s+\.+oracle|liboracle|oracle/|oracle\.)", txt), (root, f)
+
+
+def test_gauss_legendre_host_matches_numpy():
+    """faop_gauss_legendre_host (for callers without numpy) against numpy.polynomial.legendre.leggauss."""
+    from numpy.polynomial.legendre import leggauss
+    lib = _lib.load()
+    for n in (1, 2, 3, 24, 32, 48, 64, 101, 128):
+        y, w = np.empty(n), np.empty(n)
+        assert lib.faop_gauss_legendre_host(n, y.ctypes.data, w.ctypes.data) == 0
+        yn, wn = leggauss(n)
+        # numpy's weights carry ~1e-14 of rounding of their own (they do not sum to 2 exactly; these do)
+        assert np.max(np.abs(y - yn)) <= 4e-16 and np.max(np.abs(w - wn)) <= 1e-14 and abs(w.sum() - 2) <= 1e-15
+    assert lib.faop_gauss_legendre_host(0, y.ctypes.data, w.ctypes.data) == -1
+
+
+def test_plain_c_caller_compiles_and_links():
+    """tests/cabi/testA.c needs nothing but include/faop.h and libfaop.so (run on the GPU by test_gpu_parity)."""
+    import subprocess
+    import tempfile
+    exe = os.path.join(tempfile.mkdtemp(prefix="faop_cabi_"), "testA")
+    csrc = os.path.join(REPO, "fastamericanoptionpricing_b200", "csrc")
+    subprocess.check_call(["gcc", "-O2", "-Wall", "-I", os.path.join(REPO, "include"), os.path.join(REPO, "tests", "cabi", "testA.c"),
+                           "-o", exe, "-L", csrc, "-lfaop", "-lm", "-Wl,-rpath," + csrc])
+    assert os.path.exists(exe)

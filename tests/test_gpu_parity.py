@@ -773,3 +773,17 @@ def test_cn_device_countdown_equals_host_schedule():
             p2, X2 = batch.cn_put_batch(*aa, n_space=n_space, max_dt=mdt[:cnt], mode=mode, want_grid=True,
                                         schedule=(sched[0][:cnt], sched[1][:cnt]))
             assert torch.equal(p1, p2) and torch.equal(X1, X2), (n_space, mode)
+
+
+def test_plain_c_caller_runs():
+    """A C program that includes only include/faop.h prices the reference's testA case through faop_alo_price_batch_host."""
+    import os
+    import subprocess
+    import tempfile
+    from conftest import REPO
+    exe = os.path.join(tempfile.mkdtemp(prefix="faop_cabi_"), "testA")
+    csrc = os.path.join(REPO, "fastamericanoptionpricing_b200", "csrc")
+    subprocess.check_call(["gcc", "-O2", "-I", os.path.join(REPO, "include"), os.path.join(REPO, "tests", "cabi", "testA.c"),
+                           "-o", exe, "-L", csrc, "-lfaop", "-lm", "-Wl,-rpath," + csrc])
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0 and out.stdout.strip().endswith("ok"), out.stdout + out.stderr
