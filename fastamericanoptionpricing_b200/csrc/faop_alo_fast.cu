@@ -113,10 +113,13 @@ __global__ void __launch_bounds__(kFastWarps * 32, 1) alo_fast_A12_kernel(AloArg
         }
 
         int count = 0;
+        // the stopping rule ||B_old - B_new||_2 > tol (Base.py:119) is tested on the squares (err holds the squared norm
+        // inside the loop), which keeps the square root out of the sweep; snapshot mode records the norm itself
         double err = 1.0;
+        const double tol_cmp = SNAP ? a.cfg.iter_tol : (a.cfg.iter_tol < 0 ? -1.0 : a.cfg.iter_tol * a.cfg.iter_tol);
         int ns = 0;                  // snapshot mode only
         double best = 1.79e308;
-        while (err > a.cfg.iter_tol && count < a.cfg.max_iters) {
+        while (err > tol_cmp && count < a.cfg.max_iters) {
             ++count;
             // ---- L_j = ln(B_j/X), H_j = L_j^2 (FastAmericanOptionSolverBase.py:184), broadcast through shared memory
             if (lane < NN) {
@@ -223,7 +226,9 @@ __global__ void __launch_bounds__(kFastWarps * 32, 1) alo_fast_A12_kernel(AloArg
                     const double LK = nd.L + ws.par[2];
                     const double xpK = fma(LK, nd.cinv2, nd.apc2);      // d+(tau_i, B_i/K) / sqrt2
                     const double xmK = xpK - nd.ssu2;
-                    const double Ep = fast_exp(-xpK * xpK), Em = fast_exp(-xmK * xmK);
+                    double exK[2] = {-xpK * xpK, -xmK * xmK}, EK[2];
+                    fast_exp_n<2, false>(exK, EK);      // full-accuracy table, the two chains interleaved
+                    const double Ep = EK[0], Em = EK[1];
                     double Nv, Dv;
                     if (SOLVER == 0) {
                         const double K3 = tau * nd.cis * ws.sN[lane];
@@ -234,13 +239,14 @@ __global__ void __launch_bounds__(kFastWarps * 32, 1) alo_fast_A12_kernel(AloArg
                         Nv = fast_half_erfcx_cdf(om * xmK, Em) + orr * (tau * ws.sN[lane]);        // B.py:5-13
                         Dv = fast_half_erfcx_cdf(om * xpK, Ep) + oq * (tau * ws.sD[lane]);         // B.py:15-23
                     }
-                    const double f = ws.disc[lane] * Nv / Dv;                                               // Base.py:273
+                    const double f = ws.disc[lane] * Nv * fast_rcp(Dv);                                     // Base.py:273
                     Bn = Bj + a.cfg.eta * (Bj - f) / (0.0 - 1.0);                                           // Base.py:164
                 }
                 dd = fabs(Bj - Bn);
                 ws.B[lane] = Bn;
             }
-            err = sqrt(warp_sum(dd * dd));         // norm1_error is the 2-norm over all n+1 nodes (:230-233)
+            err = warp_sum(dd * dd);               // norm1_error is the 2-norm over all n+1 nodes (:230-233)
+            if (SNAP) err = sqrt(err);
             __syncwarp();
             if (SNAP && err <= a.snap_tol_hi && err < best) {
                 best = err;
@@ -253,6 +259,7 @@ __global__ void __launch_bounds__(kFastWarps * 32, 1) alo_fast_A12_kernel(AloArg
             __syncwarp();
             continue;
         }
+        if (count > 0) err = sqrt(err);            // not SNAP here: back to the norm the reference reports (self.error)
         if (a.B && lane < NN) a.B[opt * NN + lane] = ws.B[lane];
         double eur;
         const Opt o = load_option(a, opt);

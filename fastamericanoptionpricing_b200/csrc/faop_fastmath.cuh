@@ -106,6 +106,8 @@ FAOP_D double mills_half(double y) {
 // ln(a) for positive normal a: a = m 2^e with m in [sqrt(1/2), sqrt 2), ln m = 2 atanh(s), s = (m-1)/(m+1), |s| <= 0.1716,
 // odd series through s^21 (truncation 2.4e-17 relative).  Anything else (zero, negative, denormal, inf, NaN) takes the
 // libdevice path so that the reference's NaN / -inf behaviour (numpy log of a non-positive boundary) is kept.
+static __constant__ double kLogC[10] = {2.0 / 3.0, 2.0 / 5.0, 2.0 / 7.0, 2.0 / 9.0, 2.0 / 11.0, 2.0 / 13.0, 2.0 / 15.0, 2.0 / 17.0,
+                                        2.0 / 19.0, 2.0 / 21.0};
 FAOP_D double fast_log(double a) {
     const int hi = __double2hiint(a);
     if ((unsigned)(hi - 0x00100000) >= 0x7fe00000u) return log(a);
@@ -115,16 +117,9 @@ FAOP_D double fast_log(double a) {
     const double m = __hiloint2double(mhi, __double2loint(a));
     const double s = (m - 1.0) * fast_rcp(m + 1.0);
     const double z = s * s;
-    double p = 2.0 / 21.0;
-    p = fma(p, z, 2.0 / 19.0);
-    p = fma(p, z, 2.0 / 17.0);
-    p = fma(p, z, 2.0 / 15.0);
-    p = fma(p, z, 2.0 / 13.0);
-    p = fma(p, z, 2.0 / 11.0);
-    p = fma(p, z, 2.0 / 9.0);
-    p = fma(p, z, 2.0 / 7.0);
-    p = fma(p, z, 2.0 / 5.0);
-    p = fma(p, z, 2.0 / 3.0);
+    double p = kLogC[9];
+#pragma unroll
+    for (int k = 8; k >= 0; --k) p = fma(p, z, kLogC[k]);
     const double lm = fma(s * z, p, 2.0 * s);
     const double ef = (double)e;
     return fma(ef, 6.93147180559945286e-01, fma(ef, 2.31904681384629956e-17, lm));
