@@ -292,7 +292,7 @@ __global__ void __launch_bounds__(kClenWarps * 32, 1) alo_clen_kernel(AloArgs a)
         if (a.B && lane < nn) a.B[opt * nn + lane] = ws.B[lane];
         double eur;
         const Opt o = load_option(a, opt);
-        const double v = price_integral(gw, tb, tl, o, lane, &eur);
+        const double v = price_integral_fast(gw, tb, tl, o, lane, &eur);
         if (lane == 0) {
             a.price[opt] = v;
             if (a.european) a.european[opt] = eur;

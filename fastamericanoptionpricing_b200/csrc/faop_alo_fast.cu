@@ -107,9 +107,20 @@ __global__ void __launch_bounds__(kFastWarps * 32, 1) alo_fast_A12_kernel(AloArg
         }
         __syncwarp();
 #pragma unroll
-        for (int i = 0; i < NC; ++i) {
-            ws.eq[i * 32 + lane] = wk * fast_exp(oq * ws.tau[i] * g);
-            if (SOLVER == 1) ws.er[i * 32 + lane] = wk * fast_exp(orr * ws.tau[i] * g);
+        for (int i = 0; i < NC; i += 4) {       // invariant tables, four interleaved chains with constant-bank coefficients
+            double eqa[4], eqv[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) eqa[c] = oq * ws.tau[i + c] * g;
+            fast_exp_n<4, false>(eqa, eqv);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) ws.eq[(i + c) * 32 + lane] = wk * eqv[c];
+            if (SOLVER == 1) {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) eqa[c] = orr * ws.tau[i + c] * g;
+                fast_exp_n<4, false>(eqa, eqv);
+#pragma unroll
+                for (int c = 0; c < 4; ++c) ws.er[(i + c) * 32 + lane] = wk * eqv[c];
+            }
         }
 
         int count = 0;
@@ -263,7 +274,7 @@ __global__ void __launch_bounds__(kFastWarps * 32, 1) alo_fast_A12_kernel(AloArg
         if (a.B && lane < NN) a.B[opt * NN + lane] = ws.B[lane];
         double eur;
         const Opt o = load_option(a, opt);
-        const double v = price_integral(gw, tb, tl, o, lane, &eur);
+        const double v = price_integral_fast(gw, tb, tl, o, lane, &eur);
         if (lane == 0) {
             a.price[opt] = v;
             if (a.european) a.european[opt] = eur;
