@@ -341,14 +341,14 @@ def main():
                              "flop_model": "SURVEY 8d nominal: add/mul 1, FMA 2, div/sqrt 16, exp 40, log 56, Phi 120, phi 42 "
                                            "at the realised mean iteration count",
                              # hardware-side view of the same launch: DFMA x2 + DMUL + DADD thread instructions per option
-                             # counted by ncu (profiles/r1_alo_fast_A12_ncu_full.csv, 1.123 MFLOP at 19.32 sweeps), scaled
+                             # counted by ncu (profiles/r1_alo_fast_A12_ncu_full.csv, 1.104 MFLOP at 19.32 sweeps), scaled
                              # to this run's sweep count; the nominal model prices exp/Phi/sqrt as 40/120/16 flops where
                              # the kernel spends 24/50/12, which is why `frac` can exceed 1
                              "executed": None if args.kernel != 0 else {
-                                 "flops_per_option": 1.123e6 * iters_mean / 19.316,
-                                 "tflops": 1.123e6 * iters_mean / 19.316 * Nopt / (ms_kernel / 1e3) / 1e12,
-                                 "frac": 1.123e6 * iters_mean / 19.316 * Nopt / (ms_kernel / 1e3) / 1e12 / tf_peak,
-                                 "fp64_pipe_active_pct_ncu": 69.5},
+                                 "flops_per_option": 1.104e6 * iters_mean / 19.316,
+                                 "tflops": 1.104e6 * iters_mean / 19.316 * Nopt / (ms_kernel / 1e3) / 1e12,
+                                 "frac": 1.104e6 * iters_mean / 19.316 * Nopt / (ms_kernel / 1e3) / 1e12 / tf_peak,
+                                 "fp64_pipe_active_pct_ncu": 70.1},
                              "peak_source": "register-operand DFMA chains measured in this run (faop_measure_fp64_peak); "
                                             "MEASURED_PEAKS.json has no FP64 figure"},
                 "cpu_baseline": {"value": cpu_rate, "unit": UNIT, "cores": threads, "kind": "port",
