@@ -108,3 +108,18 @@ def test_plain_c_caller_compiles_and_links():
     subprocess.check_call(["gcc", "-O2", "-Wall", "-I", os.path.join(REPO, "include"), os.path.join(REPO, "tests", "cabi", "testA.c"),
                            "-o", exe, "-L", csrc, "-lfaop", "-lm", "-Wl,-rpath," + csrc])
     assert os.path.exists(exe)
+
+
+def test_tanh_sinh_rule_host():
+    """batch.tanh_sinh (opt-in rule): symmetric, weights sum to 2, integrates an end-point singularity
+    that defeats Gauss-Legendre at the same size."""
+    y, w = batch.tanh_sinh(64)
+    assert np.allclose(y, -y[::-1], atol=1e-15) and np.allclose(w, w[::-1], rtol=1e-12) and abs(w.sum() - 2) < 1e-10
+    assert (np.diff(y) >= 0).all() and y[0] > -1 and y[-1] < 1
+    f = lambda x: 1 / np.sqrt(1 - x * x)          # noqa: E731   integral over [-1, 1] = pi
+    assert abs((w * f(y)).sum() - np.pi) < 1e-6
+    yg, wg = batch.gauss_legendre(64)
+    assert abs((wg * f(yg)).sum() - np.pi) > 1e-2
+    assert abs((w * np.exp(y)).sum() - (np.e - 1 / np.e)) < 1e-12
+    with pytest.raises(ValueError):
+        batch.quadrature_rule("simpson", 8)
