@@ -127,7 +127,8 @@ def gen_c1(pool):
     print("c1:", repr(out["price"][0]), out["iters"][0], repr(out["err"][0]))
 
 
-def gen_c2(pool, count=1024):
+def gen_c2(pool, count=None):
+    count = count or int(os.environ.get("FAOP_GOLDEN_C2", "4096"))   # first 4,096 options through the live reference
     b = wl.c2_batch()
     out = run_batch(pool, "A", b, wl.C2_CFG, list(range(count)))
     np.savez(os.path.join(OUT, "ref_c2_A.npz"), **out)
@@ -136,7 +137,8 @@ def gen_c2(pool, count=1024):
         np.isnan(out["price"]).sum()))
 
 
-def gen_c3(pool, count=96):
+def gen_c3(pool, count=None):
+    count = count or int(os.environ.get("FAOP_GOLDEN_C3", "96"))
     b = wl.c3_batch()
     out = run_batch(pool, "B", b, wl.C3_CFG, list(range(count)))
     out["in_category"] = b["category"][:count]
