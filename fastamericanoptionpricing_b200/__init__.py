@@ -10,7 +10,7 @@ Two surfaces:
 
 There is no CPU fallback: without a CUDA device or without csrc/libfaop.so every compute call raises.
 """
-from .batch import (AloConfig, HostContext, bjerksund_stensland_batch, bs_phi_batch, cheb_eval_batch, cheb_fit_batch, cn_put_batch, eval_nodes_batch,  # noqa: F401
+from .batch import (AloConfig, HostContext, MultiGpuHost, bjerksund_stensland_batch, bs_phi_batch, cheb_eval_batch, cheb_fit_batch, cn_put_batch, eval_nodes_batch,  # noqa: F401
                     eval_points_batch, european_batch, european_greeks_batch, greeks_batch, implied_vol_batch, interp_boundary_batch, ladder_batch, price_batch,
                     price_known_boundary_batch, qd_boundary_batch, qd_price_batch, qd_residual_batch, surface_batch)
 from .sharding import ladder_batch_sharded, price_batch_sharded, shard_bounds  # noqa: F401

@@ -641,3 +641,41 @@ class HostContext:
                                                   hp(out.get("european")), hp(out.get("B")), hp(out.get("B0")),
                                                   hp(out.get("iters")), hp(out.get("err"))), "faop_alo_price_batch_host")
         return out
+
+
+class MultiGpuHost:
+    """One host process, several GPUs (SURVEY 8e's single-process form): host arrays are cut into contiguous slices, one per
+    device; every slice goes through its own faop_ctx (own stream pair, own arena) on its own Python thread — ctypes releases
+    the GIL for the duration of faop_alo_price_batch_host, so the devices run concurrently — and the results land directly in
+    the caller's output arrays.  No collective, no copy between devices."""
+
+    def __init__(self, devices=None):
+        if not torch.cuda.is_available():
+            raise _lib.FaopError("CUDA device required: fastamericanoptionpricing_b200 has no CPU fallback")
+        self.devices = list(range(torch.cuda.device_count())) if devices is None else [int(d) for d in devices]
+        self.ctx = [HostContext(d) for d in self.devices]
+
+    def close(self):
+        for c in self.ctx:
+            c.close()
+
+    def price_batch(self, r, q, sigma, K, T, S, is_put, t=None, cfg: AloConfig = AloConfig(), out=None):
+        from concurrent.futures import ThreadPoolExecutor
+        from .sharding import shard_bounds
+        N = len(r)
+        if out is None:
+            out = dict(price=np.empty(N), european=np.empty(N), iters=np.empty(N, dtype=np.int32), err=np.empty(N))
+        W = len(self.ctx)
+
+        def work(g):
+            lo, hi = shard_bounds(N, W, g)
+            if hi > lo:
+                sl = slice(lo, hi)
+                self.ctx[g].price_batch(r[sl], q[sl], sigma[sl], K[sl], T[sl], S[sl], is_put[sl], None if t is None else t[sl],
+                                        cfg=cfg, out={k: v[sl] for k, v in out.items()})
+            return hi - lo
+
+        with ThreadPoolExecutor(max_workers=W) as ex:
+            done = sum(ex.map(work, range(W)))
+        assert done == N
+        return out

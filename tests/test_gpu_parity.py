@@ -787,3 +787,21 @@ def test_plain_c_caller_runs():
                            "-o", exe, "-L", csrc, "-lfaop", "-lm", "-Wl,-rpath," + csrc])
     out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
     assert out.returncode == 0 and out.stdout.strip().endswith("ok"), out.stdout + out.stderr
+
+
+def test_multigpu_host_single_process():
+    """batch.MultiGpuHost: contiguous slices of host arrays through one faop_ctx per device on concurrent threads == the
+    one-context result (runs with however many devices the box has; 2 GPUs measured 1.95x, profiles/)."""
+    N = 30_001
+    b = wl.c2_batch(N)
+    a = [b[k] for k in ("r", "q", "sigma", "K", "T", "S")] + [b["is_put"].astype(np.uint8)]
+    cfg = AloConfig(**wl.C2_CFG)
+    ref = batch.HostContext(0).price_batch(*a, cfg=cfg)
+    mg = batch.MultiGpuHost()
+    out = mg.price_batch(*a, cfg=cfg)
+    assert np.array_equal(out["price"], ref["price"], equal_nan=True) and np.array_equal(out["iters"], ref["iters"])
+    # more slices than work, and a device listed twice (two contexts on one GPU)
+    mg2 = batch.MultiGpuHost(devices=[0, 0, 0])
+    out2 = mg2.price_batch(*[x[:2] for x in a], cfg=cfg)
+    assert np.array_equal(out2["price"], ref["price"][:2], equal_nan=True)
+    mg.close(); mg2.close()
