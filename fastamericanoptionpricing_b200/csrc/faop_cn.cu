@@ -81,25 +81,28 @@ __device__ __forceinline__ MaxAff shfl_down_map(const MaxAff& m, int d) {
     return {__shfl_down_sync(kFullMask, m.A, d), __shfl_down_sync(kFullMask, m.B, d), __shfl_down_sync(kFullMask, m.C, d)};
 }
 
-// Everything that depends only on (option, dt) is computed once per distinct dt (normally once per option): the scaled
-// rows Q_i = alpha_i/den_i, O_i = (1-beta_i)/den_i, R_i = gamma_i/den_i of the elimination, and the A-components (products
-// of Q resp. R) of every composed map the two scans form — thread-local, per shuffle level, per warp.  A time step then
-// only moves the B (and, projected, C) components: one FMA per composition.  Q, R, X, the payoff and D live in registers,
-// O in shared memory; three barriers per step (halo exchange, forward warp totals, backward warp totals + closure data).
 // max without fmax's NaN canonicalisation (one DSETP + two selects): the operands here are never NaN unless the inputs are
 __device__ __forceinline__ double dmax(double x, double y) { return x > y ? x : y; }
 
+// Everything that depends only on (option, dt) is computed once per distinct dt (normally once per option): the scaled
+// rows Q_i = alpha_i/den_i, O_i = (1-beta_i)/den_i, R_i = gamma_i/den_i of the elimination, and the A-components (products
+// of Q resp. R) of every composed map the two scans form — thread-local, per shuffle level, per warp.  A time step then
+// only moves the B (and, projected, C) components: one FMA per composition.  Q, R, X and D live in registers, O and the
+// payoff in shared memory; three barriers per step (halo exchange, forward warp totals, backward warp totals + closure data).
+// Slot layout: the N-1 scanned nodes 0..N-2 occupy the LAST N-1 of the kCnThreads*NPT slots (node i = slot - off), the
+// unused slots in front carry all-zero rows (identity-free padding that nobody reads), and X_{N-1} — fixed by the closure
+// row, not by the scans — is a scalar every thread holds.  Every slot therefore runs the same unpredicated code.
 template <int NPT, bool PROJ>
 __global__ void __launch_bounds__(kCnThreads, (NPT <= 8 ? 2 : 1)) cn_scan_kernel(CnArgs a) {
-    constexpr int NS = kCnThreads * NPT;  // padded node slots
+    constexpr int NS = kCnThreads * NPT;  // slots
     constexpr double kNegBig = -1.79e308;
     extern __shared__ double sm[];
-    double* s_Q = sm;                    // [j * T + t] for node t*NPT + j
+    double* s_Q = sm;                    // [j * T + t] for slot t*NPT + j
     double* s_R = s_Q + NS;
     double* s_O = s_R + NS;
-    double* s_seq = s_O + NS;            // natural-order scratch (c' recurrence, fallback back-substitution)
+    double* s_seq = s_O + NS;            // natural (node) order scratch (c' recurrence, fallback back-substitution, output)
     double* s_G = s_seq + NS;            // payoff K - S_i, [j * T + t]
-    double* s_eL = s_G + NS;             // [warp] X of the warp's first node / last node (halo of the neighbours)
+    double* s_eL = s_G + NS;             // [warp] X of the warp's first slot / last slot (halo of the neighbours)
     double* s_eR = s_eL + kCnWarps;
     double* s_fwA = s_eR + kCnWarps;     // forward warp totals: A (per dt) and B (per step)
     double* s_fwB = s_fwA + kCnWarps;
@@ -107,20 +110,26 @@ __global__ void __launch_bounds__(kCnThreads, (NPT <= 8 ? 2 : 1)) cn_scan_kernel
     double* s_bwB = s_bwA + kCnWarps;
     double* s_bwC = s_bwB + kCnWarps;
     double* s_clo = s_bwC + kCnWarps;    // D_{N-4}, D_{N-3}, D_{N-2}
-    double* s_misc = s_clo + 4;          // [0] flag: some R_i < 0 outside thread 0
+    double* s_misc = s_clo + 4;          // [0] flag: some R_i < 0 outside the thread of node 0, [1] payoff at the last node
 
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const int n = a.n_space;
+    const int off = NS - (n - 1);        // node i lives in slot i + off
+    auto at_node = [&](int i) { const int sl = i + off; const int tt = sl / NPT; return (sl - tt * NPT) * kCnThreads + tt; };
     for (int64_t opt = blockIdx.x; opt < a.N; opt += gridDim.x) {
         double X[NPT], Q[NPT], R[NPT];
-#pragma unroll
-        for (int j = 0; j < NPT; ++j) {
+        double xlast;                    // X_{N-1}
+        {
             const double K = a.K[opt];
-            int i = t * NPT + j;
-            double S = grid_point(i < n ? i : n - 1, n, K);
-            s_G[j * kCnThreads + t] = K - S;      // payoff (applyConstraint, :106-107); read by this thread only
-            X[j] = (i < n) ? fmax(K - S, 0.0) : 0.0;   // setInitialCondition, :48-52
-            Q[j] = R[j] = 0.0;
+#pragma unroll
+            for (int j = 0; j < NPT; ++j) {
+                const int i = t * NPT + j - off;
+                const double S = grid_point(i >= 0 ? i : 0, n, K);
+                s_G[j * kCnThreads + t] = (i >= 0) ? K - S : kNegBig;     // payoff (applyConstraint, :106-107); own slots only
+                X[j] = (i >= 0) ? fmax(K - S, 0.0) : 0.0;                  // setInitialCondition, :48-52
+                Q[j] = R[j] = 0.0;
+            }
+            xlast = fmax(K - grid_point(n - 1, n, K), 0.0);
         }
         double Af[5], Ab[5], excA = 0.0, nxtA = 0.0, cR3 = 0.0, cR4 = 0.0, cinv = 0.0;
         // time stepping: either the caller's schedule, or solvePDE's countdown `while t > 0: dt = min(t, max_dt); ...; t -= dt`
@@ -147,28 +156,29 @@ __global__ void __launch_bounds__(kCnThreads, (NPT <= 8 ? 2 : 1)) cn_scan_kernel
                 if (t == 0) s_misc[1] = K - 3.0 * K;            // payoff at the last node (floor of X_{N-1})
 #pragma unroll
                 for (int j = 0; j < NPT; ++j) {
-                    int i = t * NPT + j;
+                    const int i = t * NPT + j - off;
                     double al = 0.0, be = 0.0, ga = 0.0;
-                    if (i < n - 1) {
+                    if (i >= 0) {
                         double S = grid_point(i, n, K);
                         double aa = sg * S / dS;
                         double m = (r - q) * S / dS;
                         al = 0.25 * dt * (aa * aa - m);
                         be = 0.5 * dt * (r + aa * aa);
                         ga = 0.25 * dt * (aa * aa + m);
+                        s_seq[i] = 1.0 + be;      // diagonal, node order, for the sequential recurrence below
                     }
                     s_Q[j * kCnThreads + t] = al;
                     s_R[j * kCnThreads + t] = ga;
-                    s_O[j * kCnThreads + t] = 1.0 - be;
-                    s_seq[i] = 1.0 + be;          // diagonal, natural order, for the sequential recurrence below
+                    s_O[j * kCnThreads + t] = (i >= 0) ? 1.0 - be : 0.0;
                 }
                 __syncthreads();
                 if (t == 0) {
                     // den_i = (1+beta_i) - (-alpha_i)(c'_{i-1}),  c'_i = -gamma_i / den_i   (rows 0..N-2)
                     double cp = 0.0;
                     int neg = 0;
+                    const int t0 = off / NPT;     // the thread holding node 0: its own maps are applied one by one, never composed
                     for (int i = 0; i < n - 1; ++i) {
-                        int tt = i / NPT, jj = i - tt * NPT, at = jj * kCnThreads + tt;
+                        const int at = at_node(i);
                         double al = s_Q[at], ga = s_R[at];
                         double den = s_seq[i] + al * cp;
                         double rd = 1.0 / den;
@@ -177,11 +187,7 @@ __global__ void __launch_bounds__(kCnThreads, (NPT <= 8 ? 2 : 1)) cn_scan_kernel
                         s_R[at] = Ri;
                         s_O[at] = s_O[at] * rd;
                         cp = -Ri;
-                        if (Ri < 0.0 && tt > 0) neg = 1;
-                    }
-                    for (int i = n - 1; i < NS; ++i) {
-                        int tt = i / NPT, jj = i - tt * NPT, at = jj * kCnThreads + tt;
-                        s_Q[at] = 0.0; s_R[at] = 0.0; s_O[at] = 0.0;
+                        if (Ri < 0.0 && (i + off) / NPT > t0) neg = 1;
                     }
                     s_misc[0] = (double)neg;
                 }
@@ -193,7 +199,7 @@ __global__ void __launch_bounds__(kCnThreads, (NPT <= 8 ? 2 : 1)) cn_scan_kernel
                     Q[j] = s_Q[j * kCnThreads + t];
                     R[j] = s_R[j * kCnThreads + t];
                     aF *= Q[j];
-                    if (t * NPT + j <= n - 2) aB *= R[j];
+                    aB *= R[j];
                 }
 #pragma unroll
                 for (int lv = 0; lv < 5; ++lv) {
@@ -212,10 +218,9 @@ __global__ void __launch_bounds__(kCnThreads, (NPT <= 8 ? 2 : 1)) cn_scan_kernel
                 if (lane == 31) s_fwA[warp] = aF;
                 if (lane == 0) s_bwA[warp] = aB;
                 {   // closure of the 4-term last row: X_{N-2..N-4} are affine in x = X_{N-1} with slopes m2, m3, m4
-                    auto Rat = [&](int i) { int tt = i / NPT, jj = i - tt * NPT; return s_R[jj * kCnThreads + tt]; };
-                    const double m2 = Rat(n - 2);
-                    cR3 = Rat(n - 3);
-                    cR4 = Rat(n - 4);
+                    const double m2 = s_R[at_node(n - 2)];
+                    cR3 = s_R[at_node(n - 3)];
+                    cR4 = s_R[at_node(n - 4)];
                     const double m3 = cR3 * m2, m4 = cR4 * m3;
                     cinv = 1.0 / (2.0 - m4 + 4.0 * m3 - 5.0 * m2);
                 }
@@ -226,7 +231,7 @@ __global__ void __launch_bounds__(kCnThreads, (NPT <= 8 ? 2 : 1)) cn_scan_kernel
             double xl = __shfl_up_sync(kFullMask, X[NPT - 1], 1);
             double xr = __shfl_down_sync(kFullMask, X[0], 1);
             if (lane == 0) xl = (warp > 0) ? s_eR[warp - 1] : 0.0;
-            if (lane == 31) xr = (warp < kCnWarps - 1) ? s_eL[warp + 1] : 0.0;
+            if (lane == 31) xr = (warp < kCnWarps - 1) ? s_eL[warp + 1] : xlast;   // node N-2 sees X_{N-1}
             double D[NPT];
 #pragma unroll
             for (int j = 0; j < NPT; ++j) {
@@ -258,10 +263,12 @@ __global__ void __launch_bounds__(kCnThreads, (NPT <= 8 ? 2 : 1)) cn_scan_kernel
                 dprev = fma(Q[j], dprev, D[j]);
                 D[j] = dprev;
             }
+            if (t >= kCnThreads - 3) {      // D of the last three scanned nodes N-4, N-3, N-2 (slots NS-3 .. NS-1)
 #pragma unroll
-            for (int j = 0; j < NPT; ++j) {
-                const int i = t * NPT + j;
-                if (i >= n - 4 && i <= n - 2) s_clo[i - (n - 4)] = D[j];
+                for (int j = 0; j < NPT; ++j) {
+                    const int sl = t * NPT + j;
+                    if (sl >= NS - 3) s_clo[sl - (NS - 3)] = D[j];
+                }
             }
             const bool fallback = PROJ && s_misc[0] != 0.0;
             if (!fallback) {
@@ -269,10 +276,8 @@ __global__ void __launch_bounds__(kCnThreads, (NPT <= 8 ? 2 : 1)) cn_scan_kernel
                 double B = 0.0, C = kNegBig;
 #pragma unroll
                 for (int j = NPT - 1; j >= 0; --j) {
-                    if (t * NPT + j <= n - 2) {
-                        if (PROJ) C = dmax(fma(R[j], C, D[j]), s_G[j * kCnThreads + t]);
-                        B = fma(R[j], B, D[j]);
-                    }
+                    if (PROJ) C = dmax(fma(R[j], C, D[j]), s_G[j * kCnThreads + t]);
+                    B = fma(R[j], B, D[j]);
                 }
 #pragma unroll
                 for (int lv = 0; lv < 5; ++lv) {
@@ -292,8 +297,9 @@ __global__ void __launch_bounds__(kCnThreads, (NPT <= 8 ? 2 : 1)) cn_scan_kernel
                 const double p2 = s_clo[2];
                 const double p3 = fma(cR3, p2, s_clo[1]);
                 const double p4 = fma(cR4, p3, s_clo[0]);
-                double v = (p4 - 4.0 * p3 + 5.0 * p2) * cinv;
-                if (PROJ) v = dmax(v, s_misc[1]);
+                xlast = (p4 - 4.0 * p3 + 5.0 * p2) * cinv;
+                if (PROJ) xlast = dmax(xlast, s_misc[1]);
+                double v = xlast;
 #pragma unroll
                 for (int w = kCnWarps - 1; w > 0; --w) {
                     const double Aw = s_bwA[w], Bw = s_bwB[w], Cw = PROJ ? s_bwC[w] : 0.0;
@@ -310,11 +316,8 @@ __global__ void __launch_bounds__(kCnThreads, (NPT <= 8 ? 2 : 1)) cn_scan_kernel
                 }
 #pragma unroll
                 for (int j = NPT - 1; j >= 0; --j) {
-                    double xn = xin;          // i == n-1 holds X_{N-1}; slots beyond mirror it (never read back)
-                    if (t * NPT + j <= n - 2) {
-                        xn = fma(R[j], xin, D[j]);
-                        if (PROJ) xn = dmax(xn, s_G[j * kCnThreads + t]);
-                    }
+                    double xn = fma(R[j], xin, D[j]);
+                    if (PROJ) xn = dmax(xn, s_G[j * kCnThreads + t]);
                     X[j] = xn;
                     xin = xn;
                 }
@@ -323,29 +326,29 @@ __global__ void __launch_bounds__(kCnThreads, (NPT <= 8 ? 2 : 1)) cn_scan_kernel
                 // so this step falls back to a sequential projected back-substitution by one thread
 #pragma unroll
                 for (int j = 0; j < NPT; ++j) {
-                    int i = t * NPT + j;
-                    if (i <= n - 2) s_seq[i] = D[j];
+                    const int i = t * NPT + j - off;
+                    if (i >= 0) s_seq[i] = D[j];
                 }
                 __syncthreads();
                 if (t == 0) {
+                    const double K = a.K[opt];
                     const double p2 = s_clo[2];
                     const double p3 = fma(cR3, p2, s_clo[1]);
                     const double p4 = fma(cR4, p3, s_clo[0]);
-                    const double K = a.K[opt];
                     double x = dmax((p4 - 4.0 * p3 + 5.0 * p2) * cinv, s_misc[1]);
                     s_seq[n - 1] = x;
                     for (int i = n - 2; i >= 0; --i) {
-                        int tt = i / NPT, jj = i - tt * NPT;
-                        x = dmax(fma(s_R[jj * kCnThreads + tt], x, s_seq[i]), K - grid_point(i, n, K));
+                        x = dmax(fma(s_R[at_node(i)], x, s_seq[i]), K - grid_point(i, n, K));
                         s_seq[i] = x;
                     }
                 }
                 __syncthreads();
 #pragma unroll
                 for (int j = 0; j < NPT; ++j) {
-                    int i = t * NPT + j;
-                    X[j] = s_seq[i < n ? i : n - 1];
+                    const int i = t * NPT + j - off;
+                    X[j] = (i >= 0) ? s_seq[i] : 0.0;
                 }
+                xlast = s_seq[n - 1];
             }
             if (lane == 0) s_eL[warp] = X[0];
             if (lane == 31) s_eR[warp] = X[NPT - 1];
@@ -354,11 +357,15 @@ __global__ void __launch_bounds__(kCnThreads, (NPT <= 8 ? 2 : 1)) cn_scan_kernel
         __syncthreads();
 #pragma unroll
         for (int j = 0; j < NPT; ++j) {
-            int i = t * NPT + j;
-            if (i < n) {
+            const int i = t * NPT + j - off;
+            if (i >= 0) {
                 s_seq[i] = X[j];
                 if (a.X_out) a.X_out[opt * n + i] = X[j];
             }
+        }
+        if (t == 0) {
+            s_seq[n - 1] = xlast;
+            if (a.X_out) a.X_out[opt * n + n - 1] = xlast;
         }
         __syncthreads();
         if (t == 0) a.price[opt] = interp_uniform(a.S0[opt], n, a.K[opt], [&](int i) { return s_seq[i]; });
@@ -448,7 +455,7 @@ static int launch_scan(const CnArgs& a, cudaStream_t st) {
 
 template <bool PROJ>
 static int launch_scan_npt(const CnArgs& a, cudaStream_t st) {
-    int npt = (a.n_space + kCnThreads - 1) / kCnThreads;
+    int npt = (a.n_space - 1 + kCnThreads - 1) / kCnThreads;   // the N-1 scanned nodes; X_{N-1} is a scalar
     if (npt <= 1) return launch_scan<1, PROJ>(a, st);
     if (npt <= 2) return launch_scan<2, PROJ>(a, st);
     if (npt <= 4) return launch_scan<4, PROJ>(a, st);
