@@ -805,3 +805,94 @@ def test_multigpu_host_single_process():
     out2 = mg2.price_batch(*[x[:2] for x in a], cfg=cfg)
     assert np.array_equal(out2["price"], ref["price"][:2], equal_nan=True)
     mg.close(); mg2.close()
+
+
+class _Guarded:
+    """Device buffer with sentinel zones on both sides (compute-sanitizer is not available on this pool): after the launch
+    the zones must be intact."""
+    PAD = 4096
+
+    def __init__(self, nbytes):
+        self.n = int(nbytes)
+        self.buf = torch.full((self.n + 2 * self.PAD,), 0xA5, dtype=torch.uint8, device="cuda")
+
+    @property
+    def ptr(self):
+        import ctypes
+        return ctypes.c_void_p(self.buf.data_ptr() + self.PAD)
+
+    def view(self, dtype, shape):
+        return self.buf[self.PAD:self.PAD + self.n].view(dtype).reshape(shape)
+
+    def intact(self):
+        return bool((self.buf[:self.PAD] == 0xA5).all()) and bool((self.buf[self.PAD + self.n:] == 0xA5).all())
+
+
+def test_no_out_of_bounds_writes():
+    """Every output / scratch buffer of the C ABI entry points is given exactly the documented size between two sentinel
+    zones; ragged batch sizes (not a multiple of the warps per CTA), all kernel families."""
+    import ctypes
+    from fastamericanoptionpricing_b200 import _lib
+    lib = _lib.load()
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    P = lambda t: ctypes.c_void_p(t.data_ptr())    # noqa: E731
+    for N, cfgk, flag in ((1003, dict(wl.C2_CFG), 0), (77, dict(wl.C3_CFG), _lib.FLAG_WS_SCRATCH), (77, dict(wl.C3_CFG), 0),
+                          (131, dict(wl.C2_CFG, kernel=1, n=9, l=17, m=33), 0), (131, dict(wl.C2_CFG, solver="B"), 0),
+                          (65, dict(wl.C2_CFG, use_derivative=True), 0)):
+        cfg = AloConfig(**cfgk)
+        b = wl.c2_batch(N) if cfgk.get("solver", "A") == "A" or cfgk["n"] == 12 else wl.c3_batch(N)
+        d = [torch.as_tensor(np.ascontiguousarray(b[k][:N])).cuda() for k in ("r", "q", "sigma", "K", "T", "S")]
+        put = torch.as_tensor(b["is_put"][:N].astype(np.uint8)).cuda()
+        nn = cfg.n + 1
+        c = cfg.c(flag)
+        nb = ctypes.c_size_t()
+        assert lib.faop_workspace_bytes(ctypes.byref(c), N, ctypes.byref(nb)) == 0
+        g = dict(price=_Guarded(8 * N), eur=_Guarded(8 * N), B=_Guarded(8 * N * nn), B0=_Guarded(8 * N * nn), it=_Guarded(4 * N),
+                 err=_Guarded(8 * N), ierr=_Guarded(8 * N * cfg.max_iters), ws=_Guarded(nb.value))
+        tab = batch.tables_for(cfg, torch.device("cuda", torch.cuda.current_device()))
+        for use_ws_for_seeds in (False, True):
+            rc = lib.faop_alo_price_batch(ctypes.byref(c), N, P(d[0]), P(d[1]), P(d[2]), P(d[3]), P(d[4]), None, P(d[5]), P(put),
+                                          P(tab), None, g["price"].ptr, g["eur"].ptr, g["B"].ptr,
+                                          None if use_ws_for_seeds else g["B0"].ptr, g["it"].ptr, g["err"].ptr,
+                                          g["ierr"].ptr if cfgk.get("kernel") == 1 else None, g["ws"].ptr, st)
+            torch.cuda.synchronize()
+            assert rc == 0, (cfgk, rc)
+            assert all(v.intact() for v in g.values()), (cfgk, [k for k, v in g.items() if not v.intact()])
+        assert torch.isfinite(g["price"].view(torch.float64, (N,))).float().mean() > 0.9
+    # strike ladder and deduplicated surface
+    cfg = AloConfig(**wl.C5_CFG)
+    c = cfg.c()
+    tab = batch.tables_for(cfg, torch.device("cuda", torch.cuda.current_device()))
+    G, nK = 37, 29
+    b = wl.c2_batch(G)
+    d = [torch.as_tensor(np.ascontiguousarray(b[k])).cuda() for k in ("r", "q", "sigma", "T", "S")]
+    put = torch.as_tensor(b["is_put"].astype(np.uint8)).cuda()
+    Kl = torch.linspace(70, 130, nK, dtype=torch.float64).cuda()
+    nb = ctypes.c_size_t()
+    assert lib.faop_alo_ladder_workspace_bytes(ctypes.byref(c), G, ctypes.byref(nb)) == 0
+    g = dict(price=_Guarded(8 * G * nK), it=_Guarded(4 * G * nK), ws=_Guarded(nb.value))
+    rc = lib.faop_alo_ladder_batch(ctypes.byref(c), G, P(d[0]), P(d[1]), P(d[2]), P(d[3]), P(d[4]), P(put), nK, P(Kl), 70.0, 130.0,
+                                   P(tab), g["price"].ptr, g["it"].ptr, g["ws"].ptr, nb.value, st)
+    torch.cuda.synchronize()
+    assert rc == 0 and all(v.intact() for v in g.values())
+    surf = _lib.FaopSurface(50.0, 150.0, 0.1, 2.0, 0.15, 0.5, 100.0, 0.04, 0.01, 13, 7, 5, 1)
+    for first, count in ((0, 13 * 7 * 5), (40, 61), (9, 17)):
+        assert lib.faop_alo_surface_dedup_workspace_bytes(ctypes.byref(c), ctypes.byref(surf), first, count, ctypes.byref(nb)) == 0
+        g = dict(price=_Guarded(8 * count), it=_Guarded(4 * count), ws=_Guarded(nb.value))
+        rc = lib.faop_alo_surface_dedup_batch(ctypes.byref(c), ctypes.byref(surf), first, count, P(tab), g["price"].ptr, g["it"].ptr,
+                                              g["ws"].ptr, nb.value, st)
+        torch.cuda.synchronize()
+        assert rc == 0 and all(v.intact() for v in g.values()), (first, count)
+    # Crank-Nicolson (countdown entry), grids that do and do not fill the slots, with the grid output
+    for n_space, mode in ((200, 2), (257, 0), (513, 2), (2000, 2), (64, 1)):
+        Nc = 5
+        b = wl.c4_batch(Nc)
+        d = [torch.as_tensor(np.ascontiguousarray(b[k])).cuda() for k in ("r", "q", "sigma", "K", "T", "S")]
+        mdt = torch.as_tensor(b["T"] / 40).cuda()
+        assert lib.faop_cn_workspace_bytes(Nc, n_space, mode, ctypes.byref(nb)) == 0
+        g = dict(price=_Guarded(8 * Nc), X=_Guarded(8 * Nc * n_space), ws=_Guarded(max(nb.value, 8)))
+        rc = lib.faop_cn_put_countdown_batch(Nc, n_space, mode, P(d[0]), P(d[1]), P(d[2]), P(d[3]), P(d[4]), P(d[5]), P(mdt), 1.2,
+                                             1e-5, 50, g["price"].ptr, g["X"].ptr, g["ws"].ptr, st)
+        torch.cuda.synchronize()
+        assert rc == 0 and all(v.intact() for v in g.values()), (n_space, mode)
+        assert torch.isfinite(g["X"].view(torch.float64, (Nc, n_space))).all()
