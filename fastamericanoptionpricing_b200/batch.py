@@ -73,10 +73,21 @@ def _stream(dev):
 _TABLES = {}
 
 
+_GL_CACHE = {}
+
+
 def gauss_legendre(num):
-    """The reference's quadrature rule: numpy.polynomial.legendre.leggauss (FastAmericanOptionSolverBase.py:175)."""
-    y, w = leggauss(int(num))
-    return np.ascontiguousarray(y, dtype=np.float64), np.ascontiguousarray(w, dtype=np.float64)
+    """The reference's quadrature rule: numpy.polynomial.legendre.leggauss (FastAmericanOptionSolverBase.py:175).
+    Cached per size (an eigenvalue solve each time otherwise); the returned arrays are read-only."""
+    num = int(num)
+    hit = _GL_CACHE.get(num)
+    if hit is None:
+        y, w = leggauss(num)
+        y, w = np.ascontiguousarray(y, dtype=np.float64), np.ascontiguousarray(w, dtype=np.float64)
+        y.setflags(write=False)
+        w.setflags(write=False)
+        hit = _GL_CACHE[num] = (y, w)
+    return hit
 
 
 def tanh_sinh(num, t_max=3.16):
