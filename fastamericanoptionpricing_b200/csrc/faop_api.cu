@@ -155,26 +155,25 @@ static int fill_args(AloArgs& a, const faop_cfg* cfg, int64_t N, const double* r
     return 0;
 }
 
-int faop_alo_price_batch(const faop_cfg* cfg, int64_t N, const double* r, const double* q, const double* sigma,
-                         const double* K, const double* T, const double* t, const double* S, const uint8_t* is_put,
-                         const void* tables_dev, const double* B0_in, double* price, double* european, double* B,
-                         double* B0_out, int32_t* iters, double* err, double* iter_errs, void* workspace,
-                         void* cuda_stream) {
+// seeds_ws: where the QD seeds go when B0_out is NULL; inv_scratch: nullable per-warp invariant-table scratch (faop_alo_clen.cu)
+static int price_batch_impl(const faop_cfg* cfg, int64_t N, const double* r, const double* q, const double* sigma,
+                            const double* K, const double* T, const double* t, const double* S, const uint8_t* is_put,
+                            const void* tables_dev, const double* B0_in, double* price, double* european, double* B,
+                            double* B0_out, int32_t* iters, double* err, double* iter_errs, double* seeds_ws,
+                            double* inv_scratch, cudaStream_t st) {
     AloArgs a;
     int rc = fill_args(a, cfg, N, r, q, sigma, K, T, t, S, is_put, tables_dev);
     if (rc) return rc;
     if (N == 0) return 0;
     if (!S || !price) return FAOP_EINVAL;
-    cudaStream_t st = (cudaStream_t)cuda_stream;
     a.price = price; a.european = european; a.B = B; a.iters = iters; a.err = err; a.iter_errs = iter_errs;
+    a.inv_scratch = inv_scratch;
     const size_t seed_bytes = sizeof(double) * (size_t)N * (size_t)(cfg->n_colloc + 1);
-    if (workspace && (cfg->flags & FAOP_FLAG_WS_SCRATCH) && alo_clen_scratch_bytes(*cfg))
-        a.inv_scratch = (double*)((char*)workspace + ((seed_bytes + 255) & ~(size_t)255));
     if (B0_in) {
         a.seeds_in = B0_in;
         if (B0_out && B0_out != B0_in) FAOP_CUDA_OK(cudaMemcpyAsync(B0_out, B0_in, seed_bytes, cudaMemcpyDeviceToDevice, st));
     } else {
-        a.seeds_out = B0_out ? B0_out : (double*)workspace;
+        a.seeds_out = B0_out ? B0_out : seeds_ws;
         if (!a.seeds_out) return FAOP_EINVAL;
         rc = launch_qd_seed(a, st);
         if (rc) return rc;
@@ -187,6 +186,22 @@ int faop_alo_price_batch(const faop_cfg* cfg, int64_t N, const double* r, const 
         if (rc != -1000) return rc;
     }
     return launch_alo_generic(a, st);
+}
+
+int faop_alo_price_batch(const faop_cfg* cfg, int64_t N, const double* r, const double* q, const double* sigma,
+                         const double* K, const double* T, const double* t, const double* S, const uint8_t* is_put,
+                         const void* tables_dev, const double* B0_in, double* price, double* european, double* B,
+                         double* B0_out, int32_t* iters, double* err, double* iter_errs, void* workspace,
+                         void* cuda_stream) {
+    int rc = check_cfg(cfg);
+    if (rc) return rc;
+    double* scratch = nullptr;
+    if (workspace && N > 0 && (cfg->flags & FAOP_FLAG_WS_SCRATCH) && alo_clen_scratch_bytes(*cfg)) {
+        const size_t seed_bytes = sizeof(double) * (size_t)N * (size_t)(cfg->n_colloc + 1);
+        scratch = (double*)((char*)workspace + ((seed_bytes + 255) & ~(size_t)255));
+    }
+    return price_batch_impl(cfg, N, r, q, sigma, K, T, t, S, is_put, tables_dev, B0_in, price, european, B, B0_out, iters, err,
+                            iter_errs, (double*)workspace, scratch, (cudaStream_t)cuda_stream);
 }
 
 int faop_alo_surface_batch(const faop_cfg* cfg, const faop_surface* surf, int64_t first, int64_t count,
@@ -584,8 +599,9 @@ int faop_alo_price_batch_host(faop_ctx* c, const faop_cfg* cfg, int64_t N, const
     const size_t nn = (size_t)cfg->n_colloc + 1;
     const size_t vec = ((size_t)N * sizeof(double) + 255) & ~(size_t)255;
     const size_t mat = ((size_t)N * nn * sizeof(double) + 255) & ~(size_t)255;
-    // arena: r q sigma K T t S | price european err | is_put iters | B0 B
-    size_t need = 10 * vec + 2 * vec + 2 * mat;
+    // arena: r q sigma K T t S | price european err | is_put iters | B0 B | invariant-table scratch of the two stream lanes
+    const size_t scr = (alo_clen_scratch_bytes(*cfg) + 255) & ~(size_t)255;
+    size_t need = 10 * vec + 2 * vec + 2 * mat + 2 * scr;
     if (need > c->dev_bytes) {
         if (c->dev) { cudaFree(c->dev); c->dev = nullptr; c->dev_bytes = 0; }
         FAOP_CUDA_OK(cudaMalloc(&c->dev, need));
@@ -598,6 +614,7 @@ int faop_alo_price_batch_host(faop_ctx* c, const faop_cfg* cfg, int64_t N, const
     double* d_S = (double*)take(vec); double* d_price = (double*)take(vec); double* d_eur = (double*)take(vec);
     double* d_err = (double*)take(vec); uint8_t* d_put = (uint8_t*)take(vec); int32_t* d_it = (int32_t*)take(vec);
     double* d_B0 = (double*)take(mat); double* d_B = (double*)take(mat);
+    double* d_scr[2] = {scr ? (double*)take(scr) : nullptr, scr ? (double*)take(scr) : nullptr};
     // Chunk pipeline over two streams: while one chunk's kernels run, the other's inputs go up and results come back
     // (asynchronous when the caller's arrays are pinned).  Chunks are slices of the same arena.
     int nchunks = (int)(N / 262144);
@@ -618,11 +635,11 @@ int faop_alo_price_batch_host(faop_ctx* c, const faop_cfg* cfg, int64_t N, const
         FAOP_CUDA_OK(cudaMemcpyAsync(d_S + off, S + off, vb, cudaMemcpyHostToDevice, st));
         FAOP_CUDA_OK(cudaMemcpyAsync(d_put + off, is_put + off, (size_t)cnt, cudaMemcpyHostToDevice, st));
         if (B0_in) FAOP_CUDA_OK(cudaMemcpyAsync(d_B0 + off * nn, B0_in + off * nn, mb, cudaMemcpyHostToDevice, st));
-        rc = faop_alo_price_batch(cfg, cnt, d_r + off, d_q + off, d_s + off, d_K + off, d_T + off, t ? d_t + off : nullptr,
-                                  d_S + off, d_put + off, c->tables_dev, B0_in ? d_B0 + off * nn : nullptr, d_price + off,
-                                  european ? d_eur + off : nullptr, B ? d_B + off * nn : nullptr,
-                                  B0_in ? nullptr : d_B0 + off * nn, iters ? d_it + off : nullptr, err ? d_err + off : nullptr,
-                                  nullptr, nullptr, st);
+        rc = price_batch_impl(cfg, cnt, d_r + off, d_q + off, d_s + off, d_K + off, d_T + off, t ? d_t + off : nullptr,
+                              d_S + off, d_put + off, c->tables_dev, B0_in ? d_B0 + off * nn : nullptr, d_price + off,
+                              european ? d_eur + off : nullptr, B ? d_B + off * nn : nullptr,
+                              B0_in ? nullptr : d_B0 + off * nn, iters ? d_it + off : nullptr, err ? d_err + off : nullptr,
+                              nullptr, nullptr, d_scr[idx & 1], st);
         if (rc) return rc;
         FAOP_CUDA_OK(cudaMemcpyAsync(price + off, d_price + off, vb, cudaMemcpyDeviceToHost, st));
         if (european) FAOP_CUDA_OK(cudaMemcpyAsync(european + off, d_eur + off, vb, cudaMemcpyDeviceToHost, st));

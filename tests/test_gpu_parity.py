@@ -805,6 +805,13 @@ def test_multigpu_host_single_process():
     out2 = mg2.price_batch(*[x[:2] for x in a], cfg=cfg)
     assert np.array_equal(out2["price"], ref["price"][:2], equal_nan=True)
     mg.close(); mg2.close()
+    # the host path of a Solver-B n=24 batch (its two stream lanes each own an invariant-table scratch) against the device path
+    b3 = wl.c3_batch(3000)
+    a3 = [b3[k] for k in ("r", "q", "sigma", "K", "T", "S")] + [b3["is_put"].astype(np.uint8)]
+    cfg3 = AloConfig(**wl.C3_CFG)
+    h3 = batch.HostContext(0).price_batch(*a3, cfg=cfg3)
+    d3 = _np(batch.price_batch(*a3, cfg=cfg3, want_boundary=False))
+    assert np.array_equal(h3["price"], d3["price"], equal_nan=True) and np.array_equal(h3["iters"], d3["iters"])
 
 
 class _Guarded:
