@@ -73,7 +73,7 @@ def test_c3_golden(kernel):
     assert ps.all()
     out = _np(batch.price_batch(*_inputs(g), cfg=cfg))
     seed_ok = np.nanmax(np.abs(out["B0"] / g["B0"] - 1), axis=1) <= 1e-6     # hybr misses one extreme call's root
-    assert seed_ok.sum() >= 95
+    assert seed_ok.sum() >= len(seed_ok) - 3
     _check({k: v[seed_ok] for k, v in out.items()}, {k: g[k][seed_ok] for k in ("price", "err", "B", "iters")}, tag="c3")
     assert np.max(np.abs(out["price"] - g["price"])) <= PRICE_ABS_TOL
 

@@ -65,7 +65,7 @@ def test_c3_golden(name, fn):
     out = fn("B", *_inputs(g), **kw)
     # own seeds: hybr and Newton disagree on one extreme call (q ~ 3e-4, X = rK/q ~ 270 K); the fixed point is the same
     seed_ok = np.nanmax(np.abs(out["B0"] / g["B0"] - 1), axis=1) <= 1e-6
-    assert seed_ok.sum() >= 95
+    assert seed_ok.sum() >= len(seed_ok) - 3
     _check({k: v[seed_ok] for k, v in out.items()}, {k: g[k][seed_ok] for k in ("price", "err", "B", "iters")}, tag="c3 " + name)
     assert np.max(np.abs(out["price"] - g["price"])) <= PRICE_ABS_TOL
     assert np.nanmax(np.abs(out["B"] / g["B"] - 1)) <= 1e-8
