@@ -31,6 +31,7 @@ from fastamericanoptionpricing_b200 import workloads as wl  # noqa: E402
 METRIC = "American options priced/sec (FP64)"
 UNIT = "options/s"
 N_PER_GPU = 1_000_000
+kSMSP = 148 * 4          # SM sub-partitions (issue ports) of one B200
 
 
 def flops_per_option(solver, n, l, m, J):
@@ -348,7 +349,12 @@ def main():
                                  "flops_per_option": 1.104e6 * iters_mean / 19.316,
                                  "tflops": 1.104e6 * iters_mean / 19.316 * Nopt / (ms_kernel / 1e3) / 1e12,
                                  "frac": 1.104e6 * iters_mean / 19.316 * Nopt / (ms_kernel / 1e3) / 1e12 / tf_peak,
-                                 "fp64_pipe_active_pct_ncu": 70.1},
+                                 "fp64_pipe_active_pct_ncu": 70.1,
+                                 # what actually bounds the kernel: an FP64 warp instruction holds the SMSP issue
+                                 # port for two cycles, any other for one.  20.87 k FP64 + 14.92 k other warp instructions per
+                                 # option at 19.32 sweeps (ncu source page) over this run's cycles per option and SMSP
+                                 "issue_port_frac": (2 * 20871.7 + 14922.0) * iters_mean / 19.316 /
+                                                    (ms_kernel * 1e-3 * (clocks["sm_mhz"] or 1965.0) * 1e6 * kSMSP / Nopt)},
                              "peak_source": "register-operand DFMA chains measured in this run (faop_measure_fp64_peak); "
                                             "MEASURED_PEAKS.json has no FP64 figure"},
                 "cpu_baseline": {"value": cpu_rate, "unit": UNIT, "cores": threads, "kind": "port",
