@@ -123,3 +123,40 @@ def test_tanh_sinh_rule_host():
     assert abs((w * np.exp(y)).sum() - (np.e - 1 / np.e)) < 1e-12
     with pytest.raises(ValueError):
         batch.quadrature_rule("simpson", 8)
+
+
+def test_bad_arguments_are_codes_not_crashes():
+    """Every batch entry point refuses null pointers / negative sizes / unsupported modes with a FAOP_E* code before it
+    touches CUDA (this runs without a GPU)."""
+    lib = _lib.load()
+    c = batch.AloConfig(n=12, l=32, m=64).c()
+    cd = batch.AloConfig(n=12, l=32, m=64, use_derivative=True).c()
+    nb = ctypes.c_size_t()
+    N = ctypes.c_int64
+    z = None
+    assert lib.faop_alo_price_batch(ctypes.byref(c), N(-1), *([z] * 19)) == -1
+    assert lib.faop_alo_price_batch(ctypes.byref(c), N(5), *([z] * 19)) == -1
+    assert lib.faop_alo_price_batch(ctypes.byref(c), N(0), *([z] * 19)) == 0            # empty batch: nothing to do
+    assert lib.faop_alo_price_batch(None, N(0), *([z] * 19)) == -1
+    assert lib.faop_alo_ladder_workspace_bytes(ctypes.byref(c), N(-1), ctypes.byref(nb)) == -1
+    assert lib.faop_alo_ladder_workspace_bytes(ctypes.byref(c), N(10), ctypes.byref(nb)) == 0 and nb.value > 10 * 13 * 8
+    assert lib.faop_alo_ladder_batch(ctypes.byref(c), N(3), z, z, z, z, z, z, 4, z, 1.0, 2.0, z, z, z, z, 0, z) == -1
+    assert lib.faop_alo_ladder_batch(ctypes.byref(cd), N(3), z, z, z, z, z, z, 4, z, 1.0, 2.0, z, z, z, z, 0, z) == -2   # no derivative mode
+    assert lib.faop_alo_ladder_batch(ctypes.byref(c), N(0), z, z, z, z, z, z, 4, z, 1.0, 2.0, z, z, z, z, 0, z) == 0
+    s = _lib.FaopSurface(50.0, 150.0, 0.1, 2.0, 0.1, 0.5, 100.0, 0.04, 0.01, 10, 10, 10, 1)
+    assert lib.faop_alo_surface_dedup_workspace_bytes(ctypes.byref(c), ctypes.byref(s), N(0), N(1001), ctypes.byref(nb)) == -1   # past the end
+    assert lib.faop_alo_surface_dedup_workspace_bytes(ctypes.byref(c), ctypes.byref(s), N(0), N(1000), ctypes.byref(nb)) == 0
+    assert lib.faop_alo_surface_dedup_batch(ctypes.byref(c), ctypes.byref(s), N(0), N(10), z, z, z, z, 0, z) == -1
+    assert lib.faop_alo_surface_dedup_batch(ctypes.byref(cd), ctypes.byref(s), N(0), N(10), z, z, z, z, 0, z) == -2
+    assert lib.faop_alo_greeks_known_boundary_batch(ctypes.byref(c), N(4), *([z] * 10), 1e-3, 1e-4, z, z, z, z, z) == -1
+    assert lib.faop_iv_update_batch(N(4), *([z] * 9)) == -1 and lib.faop_iv_update_batch(N(0), *([z] * 9)) == 0
+    assert lib.faop_cn_put_countdown_batch(N(4), 200, 3, *([z] * 7), 1.2, 1e-5, 10, z, z, z, z) == -1       # mode out of range
+    assert lib.faop_cn_put_countdown_batch(N(4), 5000, 2, *([z] * 7), 1.2, 1e-5, 10, z, z, z, z) == -2      # grid beyond the compiled limit
+    assert lib.faop_cn_put_countdown_batch(N(4), 200, 2, *([z] * 7), 1.2, 1e-5, 10, z, z, z, z) == -1
+    assert lib.faop_bjerksund_stensland_batch(N(2), *([z] * 12)) == -1 and lib.faop_bs_phi_batch(N(2), *([z] * 10)) == -1
+    # the scratch flag only changes the size for configurations that use it
+    plain, flagged = ctypes.c_size_t(), ctypes.c_size_t()
+    for cfg, uses in ((batch.AloConfig(**{"solver": "B", "n": 24, "l": 64, "m": 128}), True), (batch.AloConfig(n=12, l=32, m=64), False)):
+        assert lib.faop_workspace_bytes(ctypes.byref(cfg.c()), N(100), ctypes.byref(plain)) == 0
+        assert lib.faop_workspace_bytes(ctypes.byref(cfg.c(_lib.FLAG_WS_SCRATCH)), N(100), ctypes.byref(flagged)) == 0
+        assert (flagged.value > plain.value) == uses
