@@ -253,6 +253,31 @@ def test_vs_c_oracle_32k():
         assert np.array_equal(np.isnan(out["price"]), np.isnan(ref["price"]))
 
 
+def test_solver_b_vs_c_oracle():
+    """Solver B through its two specialised kernels (matrix kernel at n = 12; Clenshaw kernel with and without the L2
+    scratch at n = 24) and the generic one, against the plain-C oracle on seeded batches."""
+    from oracle import c_oracle as co
+    from fastamericanoptionpricing_b200 import _lib
+    for N, gen, cfgk in ((16384, wl.c2_batch, dict(wl.C2_CFG, solver="B", max_iters=200)), (6144, wl.c3_batch, dict(wl.C3_CFG))):
+        b = {k: v[:N] for k, v in gen(N).items()}
+        a = [b[k] for k in ("r", "q", "sigma", "K", "T", "S", "is_put")]
+        ref = co.alo_price_batch("B", *a, **{k: cfgk[k] for k in ("n", "l", "m", "iter_tol", "max_iters")})
+        ps = np.isfinite(ref["price"]) & (ref["err"] < 1e-2)
+        assert ps.sum() >= 0.97 * N
+        for kernel, flag in ((0, _lib.FLAG_WS_SCRATCH), (0, 0), (1, 0)):
+            saved = _lib.FLAG_WS_SCRATCH
+            _lib.FLAG_WS_SCRATCH = flag
+            try:
+                out = _np(batch.price_batch(*a, cfg=AloConfig(kernel=kernel, **cfgk)))
+            finally:
+                _lib.FLAG_WS_SCRATCH = saved
+            tag = (cfgk["n"], kernel, flag)
+            assert np.max(np.abs(out["price"] - ref["price"])[ps]) <= PRICE_ABS_TOL, tag
+            assert np.nanmax(np.abs(out["B"] / ref["B"] - 1)[ps]) <= BOUNDARY_REL_TOL, tag
+            assert (out["iters"][ps] != ref["iters"][ps]).sum() <= 2, tag
+            assert np.array_equal(np.isnan(out["price"]), np.isnan(ref["price"])), tag
+
+
 def test_full_size_properties():
     """BASELINE size (1M): size-independent properties — determinism, slice invariance, American >= European,
     generic and specialised kernels agree, host-buffer entry point agrees with the device-pointer one."""
