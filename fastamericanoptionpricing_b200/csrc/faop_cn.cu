@@ -110,7 +110,9 @@ __global__ void __launch_bounds__(kCnThreads, (NPT <= 8 ? 2 : 1)) cn_scan_kernel
     double* s_bwB = s_bwA + kCnWarps;
     double* s_bwC = s_bwB + kCnWarps;
     double* s_clo = s_bwC + kCnWarps;    // D_{N-4}, D_{N-3}, D_{N-2}
-    double* s_misc = s_clo + 4;          // [0] flag: some R_i < 0 outside the thread of node 0, [1] payoff at the last node
+    double* s_fwC = s_clo + 4;           // [warp][w]: d' entering `warp` = sum_w s_fwC[warp][w] * (forward total B of warp w); per dt
+    double* s_bwK = s_fwC + kCnWarps * kCnWarps;   // unprojected: [warp][w] coefficients of the backward totals, [warp][kCnWarps] of X_{N-1}
+    double* s_misc = s_bwK + kCnWarps * (kCnWarps + 1);          // [0] flag: some R_i < 0 outside the thread of node 0, [1] payoff at the last node
 
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const int n = a.n_space;
@@ -224,9 +226,34 @@ __global__ void __launch_bounds__(kCnThreads, (NPT <= 8 ? 2 : 1)) cn_scan_kernel
                     const double m3 = cR3 * m2, m4 = cR4 * m3;
                     cinv = 1.0 / (2.0 - m4 + 4.0 * m3 - 5.0 * m2);
                 }
+                __syncthreads();   // warp totals A visible
+                if (t < kCnWarps * kCnWarps) {
+                    // d' entering warp `wr` = sum over w < wr of (prod_{w < v < wr} A_v) B_w: the products are per dt
+                    const int wr = t / kCnWarps, w = t % kCnWarps;
+                    double cw = 0.0;
+                    if (w < wr) {
+                        cw = 1.0;
+                        for (int v = w + 1; v < wr; ++v) cw *= s_fwA[v];
+                    }
+                    s_fwC[t] = cw;
+                    if (!PROJ) {
+                        // value entering warp `wr` from above = sum over w > wr of (prod_{wr < v < w} A_v) B_w + (prod_{v > wr} A_v) X_{N-1}
+                        double ck = 0.0;
+                        if (w > wr) {
+                            ck = 1.0;
+                            for (int v = wr + 1; v < w; ++v) ck *= s_bwA[v];
+                        }
+                        s_bwK[wr * (kCnWarps + 1) + w] = ck;
+                        if (w == 0) {
+                            double cx = 1.0;
+                            for (int v = wr + 1; v < kCnWarps; ++v) cx *= s_bwA[v];
+                            s_bwK[wr * (kCnWarps + 1) + kCnWarps] = cx;
+                        }
+                    }
+                }
                 dt_prev = dt;
             }
-            __syncthreads();   // halo values (and, after a dt change, the warp-level A's) are visible
+            __syncthreads();   // halo values (and, after a dt change, the warp-level coefficients) are visible
             // ---- right-hand side, already scaled by 1/den: P_i = Q_i X_{i-1} + O_i X_i + R_i X_{i+1}
             double xl = __shfl_up_sync(kFullMask, X[NPT - 1], 1);
             double xr = __shfl_down_sync(kFullMask, X[0], 1);
@@ -250,12 +277,9 @@ __global__ void __launch_bounds__(kCnThreads, (NPT <= 8 ? 2 : 1)) cn_scan_kernel
             }
             if (lane == 31) s_fwB[warp] = b;
             __syncthreads();
-            double din = 0.0;  // d' entering this warp: fixed trip count, so the 14 broadcast loads issue ahead of the FMA chain
+            double din = 0.0;  // d' entering this warp: a dot product with per-dt coefficients (zero for w >= warp), no selects
 #pragma unroll
-            for (int w = 0; w < kCnWarps - 1; ++w) {
-                const double Aw = s_fwA[w], Bw = s_fwB[w];
-                if (w < warp) din = fma(Aw, din, Bw);
-            }
+            for (int w = 0; w < kCnWarps - 1; ++w) din = fma(s_fwC[warp * kCnWarps + w], s_fwB[w], din);
             const double eb = __shfl_up_sync(kFullMask, b, 1);
             double dprev = (lane == 0) ? din : fma(excA, din, eb);
 #pragma unroll
@@ -300,11 +324,18 @@ __global__ void __launch_bounds__(kCnThreads, (NPT <= 8 ? 2 : 1)) cn_scan_kernel
                 xlast = (p4 - 4.0 * p3 + 5.0 * p2) * cinv;
                 if (PROJ) xlast = dmax(xlast, s_misc[1]);
                 double v = xlast;
+                if (PROJ) {
 #pragma unroll
-                for (int w = kCnWarps - 1; w > 0; --w) {
-                    const double Aw = s_bwA[w], Bw = s_bwB[w], Cw = PROJ ? s_bwC[w] : 0.0;
-                    const double y = fma(Aw, v, Bw);
-                    if (w > warp) v = PROJ ? dmax(y, Cw) : y;
+                    for (int w = kCnWarps - 1; w > 0; --w) {
+                        const double Aw = s_bwA[w], Bw = s_bwB[w], Cw = s_bwC[w];
+                        const double y = fma(Aw, v, Bw);
+                        if (w > warp) v = dmax(y, Cw);
+                    }
+                } else {    // affine maps superpose: a dot product with per-dt coefficients
+                    const double* ck = s_bwK + warp * (kCnWarps + 1);
+                    v = ck[kCnWarps] * xlast;
+#pragma unroll
+                    for (int w = 1; w < kCnWarps; ++w) v = fma(ck[w], s_bwB[w], v);
                 }
                 const double nB = __shfl_down_sync(kFullMask, B, 1);
                 double nC = 0.0;
@@ -445,7 +476,7 @@ __global__ void __launch_bounds__(64) cn_sor_kernel(CnArgs a) {
 template <int NPT, bool PROJ>
 static int launch_scan(const CnArgs& a, cudaStream_t st) {
     constexpr int NS = kCnThreads * NPT;
-    size_t sm = sizeof(double) * (size_t)(5 * NS + 7 * kCnWarps + 8);
+    size_t sm = sizeof(double) * (size_t)(5 * NS + 7 * kCnWarps + kCnWarps * (2 * kCnWarps + 1) + 8);
     FAOP_CUDA_OK(cudaFuncSetAttribute(cn_scan_kernel<NPT, PROJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     int64_t grid = a.N < (int64_t)kSMs * 8 ? a.N : (int64_t)kSMs * 8;
     cn_scan_kernel<NPT, PROJ><<<(unsigned)grid, kCnThreads, sm, st>>>(a);
