@@ -42,6 +42,15 @@ N5d = 100_000_000
 buf = torch.empty(N5d, dtype=torch.float64, device="cuda")
 ms, out = timeit(lambda: batch.surface_batch(surf, 0, N5d, AloConfig(**wl.C5_CFG), dedup=True, out=buf), reps=3)
 rows.append(("C5 full 100M surface, boundary solves deduplicated", N5d, ms, N5d / ms * 1e3, float("nan"), int(torch.isnan(out).sum())))
-print("%-55s %10s %10s %14s %8s %6s" % ("config", "options", "ms", "options/s", "mean_it", "nan"))
+# leaf kernels (thread per element) on 10M elements
+NL = 10_000_000
+bl = wl.c2_batch(NL)
+al = {k: torch.as_tensor(bl[k]).cuda() for k in ("r", "q", "sigma", "K", "T", "S", "is_put")}
+for name, fn, bytes_per in (("leaf: European closed form (64 B/option)", lambda: batch.european_batch(al["T"], al["S"], al["r"], al["q"], al["sigma"], al["K"], al["is_put"]), 57),
+                            ("leaf: QD+ price incl. boundary root (72 B/option)", lambda: batch.qd_price_batch(al["T"], al["S"], al["r"], al["q"], al["sigma"], al["K"], al["is_put"])[0], 73),
+                            ("leaf: Bjerksund-Stensland price (64 B/option)", lambda: batch.bjerksund_stensland_batch(al["S"], al["r"], al["q"], al["sigma"], al["K"], al["T"])[0], 64)):
+    ms, out = timeit(fn, reps=3)
+    rows.append((name + " %.0f GB/s" % (NL * bytes_per / ms / 1e6), NL, ms, NL / ms * 1e3, float("nan"), int(torch.isnan(out).sum())))
+print("%-62s %10s %10s %14s %8s %6s" % ("config", "options", "ms", "options/s", "mean_it", "nan"))
 for r in rows:
-    print("%-55s %10d %10.1f %14.0f %8.2f %6d" % r)
+    print("%-62s %10d %10.1f %14.0f %8.2f %6d" % r)
