@@ -31,12 +31,14 @@ struct FastWarpSmem {
     double B[16], L[16], H[16], A[16];
     double tau[16], disc[16];
     double sN[16], sD[16];
+    double s3[16], s4[16];   // derivative sums (use_derivative, Solver A): N'- and D'-integrals
     double par[8];   // X, 1/X, ln(X/K)
     double red[8 * 36];   // transpose buffer of the per-group reduction, row pitch 36 = 4 (mod 16): conflict-free both ways
 };
 
-template <int kFastWarps, bool SNAP = false, int SOLVER = 0>
+template <int kFastWarps, bool SNAP = false, int SOLVER = 0, bool DERIV = false>
 __global__ void __launch_bounds__(kFastWarps * 32, 1) alo_fast_A12_kernel(AloArgs a) {
+    static_assert(!DERIV || (SOLVER == 0 && !SNAP), "the derivative instantiation exists for Solver A only");
     extern __shared__ double smem[];
     const TableLayout tl = a.tl;
     double* s_tab = smem;
@@ -196,8 +198,25 @@ __global__ void __launch_bounds__(kFastWarps * 32, 1) alo_fast_A12_kernel(AloArg
                                 const bool neg = (__double2hiint(xp[p]) ^ sgn) < 0;   // om * d+ < 0 (both branches agree at 0)
                                 double cdf = neg ? ec : eqw - ec;
                                 cdf = __hiloint2double(__double2hiint(cdf) ^ sgn, __double2loint(cdf));  // times om
-                                acc[4 * pr + 2 * p] = E[2 * p + 1];                          // -> K3  = tau cinv/sqrt(2 pi) * sum
-                                acc[4 * pr + 2 * p + 1] = fma(cis[p], E[2 * p], h * cdf);    // -> K12 = tau * sum
+                                if (!DERIV) {
+                                    acc[4 * pr + 2 * p] = E[2 * p + 1];                          // -> K3  = tau cinv/sqrt(2 pi) * sum
+                                    acc[4 * pr + 2 * p + 1] = fma(cis[p], E[2 * p], h * cdf);    // -> K12 = tau * sum
+                                } else {
+                                    // Nprime_integrand / Dprime_integrand (FastAmericanOptionSolverA.py:55-83) in the same scaling:
+                                    //   s3 += (w/h) d- e^{ru}phi(d-) sqrt(2pi),  s4 += w e^{qu}phi(d+) sqrt(2pi) (1 - d+ cinv/h)
+                                    acc[4 * p] = E[2 * p + 1];
+                                    acc[4 * p + 1] = fma(cis[p], E[2 * p], h * cdf);
+                                    acc[4 * p + 2] = (1.41421356237309504880 * rh) * xm[p] * E[2 * p + 1];
+                                    acc[4 * p + 3] = E[2 * p] * fma(-2.0 * rh * ws.node[i0 + p].cinv2, xp[p], 1.0);
+                                }
+                            }
+                            if (DERIV) {    // two nodes x four sums per reduction
+                                const double tot = transpose_reduce8(acc, ws.red, lane);
+                                if ((lane & 3) == 0) {
+                                    const int v = lane >> 2, node = i0 + (v >> 2);
+                                    double* dst = (v & 2) ? ((v & 1) ? ws.s4 : ws.s3) : ((v & 1) ? ws.sD : ws.sN);
+                                    dst[node] = tot;
+                                }
                             }
                         } else {
                             double G[4];
@@ -215,11 +234,13 @@ __global__ void __launch_bounds__(kFastWarps * 32, 1) alo_fast_A12_kernel(AloArg
                             }
                         }
                     }
-                    const double tot = transpose_reduce8(acc, ws.red, lane);
-                    // lanes 8 ii .. 8 ii + 3 hold the K3 sum of node grp*4+ii, lanes 8 ii + 4 .. 8 ii + 7 its K12 sum
-                    if ((lane & 3) == 0) {
-                        const int node = grp * kGroup + (lane >> 3);
-                        if (lane & 4) ws.sD[node] = tot; else ws.sN[node] = tot;
+                    if (!DERIV) {
+                        const double tot = transpose_reduce8(acc, ws.red, lane);
+                        // lanes 8 ii .. 8 ii + 3 hold the K3 sum of node grp*4+ii, lanes 8 ii + 4 .. 8 ii + 7 its K12 sum
+                        if ((lane & 3) == 0) {
+                            const int node = grp * kGroup + (lane >> 3);
+                            if (lane & 4) ws.sD[node] = tot; else ws.sN[node] = tot;
+                        }
                     }
                 }
             }
@@ -250,8 +271,18 @@ __global__ void __launch_bounds__(kFastWarps * 32, 1) alo_fast_A12_kernel(AloArg
                         Nv = fast_half_erfcx_cdf(om * xmK, Em) + orr * (tau * ws.sN[lane]);        // B.py:5-13
                         Dv = fast_half_erfcx_cdf(om * xpK, Ep) + oq * (tau * ws.sD[lane]);         // B.py:15-23
                     }
-                    const double f = ws.disc[lane] * Nv * fast_rcp(Dv);                                     // Base.py:273
-                    Bn = Bj + a.cfg.eta * (Bj - f) / (0.0 - 1.0);                                           // Base.py:164
+                    const double rD = fast_rcp(Dv);
+                    const double f = ws.disc[lane] * Nv * rD;                                               // Base.py:273
+                    double fp = 0.0;
+                    if (DERIV) {    // N', D' (FastAmericanOptionSolverA.py:46-74), f' (Base.py:276-278)
+                        const double rB = fast_rcp(Bj);
+                        const double Nsum = ws.s3[lane] * kInvSqrt2Pi * tau * rB / (2.0 * nd.ssu2 * nd.ssu2);
+                        const double Dsum = tau * nd.cis * rB * ws.s4[lane];
+                        const double Np = -(1.41421356237309504880 * xmK) * (Em * kInvSqrt2Pi) * rB / (2.0 * nd.ssu2 * nd.ssu2) - orr * Nsum;
+                        const double Dp = Ep * nd.cis * rB * fma(-2.0 * nd.cinv2, xpK, 1.0) + oq * Dsum;
+                        fp = ws.disc[lane] * (Np * rD - Dp * Nv * rD * rD);
+                    }
+                    Bn = Bj + a.cfg.eta * (Bj - f) / (fp - 1.0);                                            // Base.py:164
                 }
                 dd = fabs(Bj - Bn);
                 ws.B[lane] = Bn;
@@ -285,22 +316,25 @@ __global__ void __launch_bounds__(kFastWarps * 32, 1) alo_fast_A12_kernel(AloArg
     }
 }
 
-template <int kFastWarps, bool SNAP = false, int SOLVER = 0>
+template <int kFastWarps, bool SNAP = false, int SOLVER = 0, bool DERIV = false>
 static int launch_fast_t(const AloArgs& a, cudaStream_t st) {
     const size_t sm = sizeof(double) * (size_t)(a.tl.small + NC * NC * 32) + sizeof(FastWarpSmem<SOLVER>) * kFastWarps;
-    FAOP_CUDA_OK(cudaFuncSetAttribute(alo_fast_A12_kernel<kFastWarps, SNAP, SOLVER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    FAOP_CUDA_OK(cudaFuncSetAttribute(alo_fast_A12_kernel<kFastWarps, SNAP, SOLVER, DERIV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     int64_t ctas = (a.N + kFastWarps - 1) / kFastWarps;
     int grid = (int)(ctas < kSMs ? ctas : kSMs);
-    alo_fast_A12_kernel<kFastWarps, SNAP, SOLVER><<<grid, kFastWarps * 32, sm, st>>>(a);
+    alo_fast_A12_kernel<kFastWarps, SNAP, SOLVER, DERIV><<<grid, kFastWarps * 32, sm, st>>>(a);
     count_launch();
     return launch_status();
 }
 
 // cfg.kernel: 0 = default (16 warps/CTA, <= 128 registers/thread); tuning variants 2 / 3 = 12 / 20 warps per CTA
 int launch_alo_fast(const AloArgs& a, cudaStream_t st) {
-    const bool match = !a.cfg.use_derivative && a.tl.n == NC && a.tl.LP == 32 && a.tl.has_matrix && a.iter_errs == nullptr;
+    // Solver B with the derivative is NaN by construction upstream and stays on the generic kernel
+    const bool match = (!a.cfg.use_derivative || (a.cfg.solver == 0 && !a.snap)) && a.tl.n == NC && a.tl.LP == 32 &&
+                       a.tl.has_matrix && a.iter_errs == nullptr;
     if (!match) return -1000;
     if (a.N == 0) return 0;
+    if (a.cfg.use_derivative) return launch_fast_t<16, false, 0, true>(a, st);
     if (a.cfg.solver == 1) return a.snap ? launch_fast_t<16, true, 1>(a, st) : launch_fast_t<16, false, 1>(a, st);
     if (a.snap) return launch_fast_t<16, true>(a, st);
     if (a.cfg.kernel == 2) return launch_fast_t<12>(a, st);

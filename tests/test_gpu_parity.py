@@ -278,6 +278,25 @@ def test_solver_b_vs_c_oracle():
             assert np.array_equal(np.isnan(out["price"]), np.isnan(ref["price"])), tag
 
 
+def test_solver_a_derivative_vs_c_oracle():
+    """use_derivative=True (the diagonal-Newton step with the analytic f', FastAmericanOptionSolverA.py:46-83, Base.py:276-278)
+    through the specialised kernel and the generic one against the plain-C oracle."""
+    from oracle import c_oracle as co
+    N = 16384
+    b = {k: v[:N] for k, v in wl.c2_batch(N).items()}
+    a = [b[k] for k in ("r", "q", "sigma", "K", "T", "S", "is_put")]
+    cfgk = dict(wl.C2_CFG, use_derivative=True, max_iters=60)
+    ref = co.alo_price_batch("A", *a, **{k: cfgk[k] for k in ("n", "l", "m", "iter_tol", "max_iters", "use_derivative")})
+    ps = np.isfinite(ref["price"]) & (ref["err"] < 1e-2)
+    assert ps.sum() >= 0.97 * N
+    for kernel in (0, 1):
+        out = _np(batch.price_batch(*a, cfg=AloConfig(kernel=kernel, **cfgk)))
+        assert np.max(np.abs(out["price"] - ref["price"])[ps]) <= PRICE_ABS_TOL, kernel
+        assert np.nanmax(np.abs(out["B"] / ref["B"] - 1)[ps]) <= BOUNDARY_REL_TOL, kernel
+        assert (out["iters"][ps] != ref["iters"][ps]).sum() <= 2, kernel
+        assert (np.isnan(out["price"]) != np.isnan(ref["price"])).sum() <= 2, kernel
+
+
 def test_full_size_properties():
     """BASELINE size (1M): size-independent properties — determinism, slice invariance, American >= European,
     generic and specialised kernels agree, host-buffer entry point agrees with the device-pointer one."""

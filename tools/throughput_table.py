@@ -26,7 +26,7 @@ a2 = dev(wl.c2_batch(N))
 for name, cfg in (("C2 A n12 l32 m64 (specialised)", AloConfig(**wl.C2_CFG)),
                   ("C2 A n12 l32 m64 (generic kernel)", AloConfig(kernel=1, **wl.C2_CFG)),
                   ("C1-style A n12 l24 m48 tol1e-5 max20 (specialised)", AloConfig("A", 12, 24, 48, 1e-5, 20)),
-                  ("A+derivative n12 l32 m64 (generic)", AloConfig(**{**wl.C2_CFG, "use_derivative": True})),
+                  ("A+derivative n12 l32 m64 (specialised)", AloConfig(**{**wl.C2_CFG, "use_derivative": True})),
                   ("B n12 l32 m64 max_iters 200 (specialised, matrix kernel)", AloConfig(**{**wl.C2_CFG, "solver": "B", "max_iters": 200}))):
     ms, out = timeit(lambda: batch.price_batch(*a2, cfg=cfg, want_boundary=False))
     rows.append((name, N, ms, N / ms * 1e3, float(out["iters"].double().mean()), int(torch.isnan(out["price"]).sum())))
