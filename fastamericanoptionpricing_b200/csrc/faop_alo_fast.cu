@@ -84,6 +84,7 @@ __global__ void __launch_bounds__(kFastWarps * 32, 1) alo_fast_A12_kernel(AloArg
                     if (a.err) a.err[opt] = 1e6;
                 }
                 if (a.B && lane < NN) a.B[opt * NN + lane] = nan("");
+                if (a.iter_errs) for (int j = lane; j < a.cfg.max_iters; j += 32) a.iter_errs[opt * a.cfg.max_iters + j] = nan("");
                 continue;
             }
             // ---- per-option setup: node constants (lanes 0..12) and the invariant e^{q u_ik} table
@@ -289,6 +290,7 @@ __global__ void __launch_bounds__(kFastWarps * 32, 1) alo_fast_A12_kernel(AloArg
             }
             err = warp_sum(dd * dd);               // norm1_error is the 2-norm over all n+1 nodes (:230-233)
             if (SNAP) err = sqrt(err);
+            if (!SNAP && a.iter_errs && lane == 0) a.iter_errs[opt * a.cfg.max_iters + (count - 1)] = sqrt(err);  // iter_records (:130)
             __syncwarp();
             if (SNAP && err <= a.snap_tol_hi && err < best) {
                 best = err;
@@ -302,6 +304,8 @@ __global__ void __launch_bounds__(kFastWarps * 32, 1) alo_fast_A12_kernel(AloArg
             continue;
         }
         if (count > 0) err = sqrt(err);            // not SNAP here: back to the norm the reference reports (self.error)
+        if (!SNAP && a.iter_errs)
+            for (int j = count + lane; j < a.cfg.max_iters; j += 32) a.iter_errs[opt * a.cfg.max_iters + j] = nan("");
         if (a.B && lane < NN) a.B[opt * NN + lane] = ws.B[lane];
         double eur;
         const Opt o = load_option(a, opt);
@@ -331,7 +335,7 @@ static int launch_fast_t(const AloArgs& a, cudaStream_t st) {
 int launch_alo_fast(const AloArgs& a, cudaStream_t st) {
     // Solver B with the derivative is NaN by construction upstream and stays on the generic kernel
     const bool match = (!a.cfg.use_derivative || (a.cfg.solver == 0 && !a.snap)) && a.tl.n == NC && a.tl.LP == 32 &&
-                       a.tl.has_matrix && a.iter_errs == nullptr;
+                       a.tl.has_matrix && (a.iter_errs == nullptr || !a.snap);
     if (!match) return -1000;
     if (a.N == 0) return 0;
     if (a.cfg.use_derivative) return launch_fast_t<16, false, 0, true>(a, st);

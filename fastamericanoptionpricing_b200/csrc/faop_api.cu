@@ -179,11 +179,13 @@ static int price_batch_impl(const faop_cfg* cfg, int64_t N, const double* r, con
         if (rc) return rc;
         a.seeds_in = a.seeds_out;
     }
-    if (cfg->kernel != 1 && !iter_errs) {  // the per-iteration error history is a generic-kernel feature
-        rc = launch_alo_fast(a, st);
+    if (cfg->kernel != 1) {
+        rc = launch_alo_fast(a, st);        // records the per-iteration error history too
         if (rc != -1000) return rc;
-        rc = launch_alo_clen(a, st);
-        if (rc != -1000) return rc;
+        if (!iter_errs) {                   // the Clenshaw kernels do not; the generic kernel serves those requests
+            rc = launch_alo_clen(a, st);
+            if (rc != -1000) return rc;
+        }
     }
     return launch_alo_generic(a, st);
 }
