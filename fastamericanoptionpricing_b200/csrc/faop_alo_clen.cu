@@ -209,10 +209,10 @@ __global__ void __launch_bounds__(kClenWarps * 32, 1) alo_clen_kernel(AloArgs a)
                             if (SOLVER == 1) { E[3] = inv[1]; E[7] = inv[3]; }
                             if (SOLVER == 0) {
                                 double xa2[2] = {xa[0], xa[2]}, G2[2];
-                                half_erfcx_n<2, true>(xa2, G2);
+                                half_erfcx_n<2, 2>(xa2, G2);
                                 G[0] = G2[0]; G[2] = G2[1];
                             } else {
-                                half_erfcx_n<4, true>(xa, G);
+                                half_erfcx_n<4, 2>(xa, G);
                             }
                         } else if (SOLVER == 0) {
                             // Solver A needs e^{qu} but not e^{ru}, and one erfcx: reuse the B layout, skip the spare chains
@@ -220,11 +220,11 @@ __global__ void __launch_bounds__(kClenWarps * 32, 1) alo_clen_kernel(AloArgs a)
                             fast_exp_n<6, true>(ex6, E6);
                             E[0] = E6[0]; E[1] = E6[1]; E[2] = E6[2]; E[4] = E6[3]; E[5] = E6[4]; E[6] = E6[5];
                             double xa2[2] = {xa[0], xa[2]}, G2[2];
-                            half_erfcx_n<2, true>(xa2, G2);
+                            half_erfcx_n<2, 2>(xa2, G2);
                             G[0] = G2[0]; G[2] = G2[1];
                         } else {
                             fast_exp_n<8, true>(ex, E);
-                            half_erfcx_n<4, true>(xa, G);
+                            half_erfcx_n<4, 2>(xa, G);
                         }
 #pragma unroll
                         for (int c = 0; c < 2; ++c) {

@@ -32,6 +32,13 @@ static __constant__ double kErfcx14[15] = {
     5.97638905924903277e-02, -1.34135356524479627e-02, -6.06289213047839443e-04, 1.51662855789247821e-03,
     -2.73829690347347061e-04, -1.37352260196071919e-04, 5.30630226822841820e-05, 1.37163947469176610e-05,
     -7.83813889147139852e-06, -1.19644291282268299e-06, 7.67685587370318563e-07};
+// the same form at degree 16 (max rel 1.4e-12): the long-maturity configurations (C3: r tau up to 1.5) run on this one
+static __constant__ double kErfcx16[17] = {
+    5.37003453544169895e-01, -4.41697226572994928e-01, 2.95114178547531192e-01, -1.55233631526699944e-01,
+    5.97638808610307173e-02, -1.34136091408635482e-02, -6.06211371911752317e-04, 1.51697851049094291e-03,
+    -2.74135460896897365e-04, -1.38207715201892501e-04, 5.37152728700476733e-05, 1.48362796563143242e-05,
+    -8.60891969407260209e-06, -1.94304210166222180e-06, 1.24198041290133434e-06, 1.99095216049436270e-07,
+    -1.18566812020442530e-07};
 #define FAOP_S2 0.70710678118654752440
 static __constant__ double kMillsC[19] = {
     7.69193049750053093e-01 * FAOP_S2, -6.65382502890239702e-01 * FAOP_S2, 4.95305615971961821e-01 * FAOP_S2,
@@ -43,7 +50,7 @@ static __constant__ double kMillsC[19] = {
     -3.23812507239800613e-08 * FAOP_S2};
 constexpr double kMillsShift = 5.0 * FAOP_S2;
 
-template <int NCH, bool LOW> FAOP_D void half_erfcx_n(const double (&x)[NCH], double (&out)[NCH]);
+template <int NCH, int TIER> FAOP_D void half_erfcx_n(const double (&x)[NCH], double (&out)[NCH]);
 
 FAOP_D double fast_rcp(double a) {
     double x0;
@@ -185,9 +192,11 @@ FAOP_D void fast_exp_n(const double (&xin)[NCH], double (&out)[NCH]) {
 
 // erfcx(x[c]) / 2 for NCH arguments x >= 0.  The argument is clamped to ~1e300 on the high word (integer min), so
 // x = +inf gives ~0; a NaN argument always arrives with a NaN exp factor, which keeps the product NaN.
-template <int NCH, bool LOW = false>
+// TIER 0 (false): degree 18, 2e-14;  TIER 1 (true): degree 14, 3e-11;  TIER 2: degree 16, 1.4e-12.
+template <int NCH, int TIER = 0>
 FAOP_D void half_erfcx_n(const double (&xin)[NCH], double (&out)[NCH]) {
-    const double sh = LOW ? 3.0 : kMillsShift;
+    constexpr int DEG = TIER == 0 ? 18 : (TIER == 1 ? 14 : 16);
+    const double sh = TIER == 0 ? kMillsShift : 3.0;
     double w[NCH], t[NCH], q[NCH];
 #pragma unroll
     for (int c = 0; c < NCH; ++c) {
@@ -195,12 +204,12 @@ FAOP_D void half_erfcx_n(const double (&xin)[NCH], double (&out)[NCH]) {
         double x = __hiloint2double(hi, __double2loint(xin[c]));
         w[c] = fast_rcp(x + sh);
         t[c] = fma(-2.0 * sh, w[c], 1.0);
-        q[c] = LOW ? kErfcx14[14] : kMillsC[18];
+        q[c] = TIER == 0 ? kMillsC[DEG] : (TIER == 1 ? kErfcx14[DEG] : kErfcx16[DEG]);
     }
 #pragma unroll
-    for (int k = (LOW ? 13 : 17); k >= 0; --k) {
+    for (int k = DEG - 1; k >= 0; --k) {
 #pragma unroll
-        for (int c = 0; c < NCH; ++c) q[c] = fma(q[c], t[c], LOW ? kErfcx14[k] : kMillsC[k]);
+        for (int c = 0; c < NCH; ++c) q[c] = fma(q[c], t[c], TIER == 0 ? kMillsC[k] : (TIER == 1 ? kErfcx14[k] : kErfcx16[k]));
     }
 #pragma unroll
     for (int c = 0; c < NCH; ++c) out[c] = q[c] * w[c];

@@ -174,6 +174,7 @@ __global__ void __launch_bounds__(256) dev_math_kernel(int kind, int64_t N, cons
         case 6: { double a[1] = {v}, o[1]; sqrt_clamped_n<1>(a, o); r = o[0]; break; }    // sqrt(max(0, v))
         case 8: { double a[1] = {v}, o[1]; half_erfcx_n<1, true>(a, o); r = o[0]; break; }       // erfcx(v)/2, degree 14
         case 9: { double a[1] = {v}, o[1]; fast_exp_n<1, true>(a, o); r = o[0]; break; }         // e^v, degree 8
+        case 12: { double a[1] = {v}, o[1]; half_erfcx_n<1, 2>(a, o); r = o[0]; break; }          // erfcx(v)/2, degree 16
         case 10: r = fast_log(v); break;
         case 11: r = norm_cdf(v); break;                                        // Phi(v), the library-accuracy form
         case 7: { double a[2] = {v, v - 1.0}, o[2]; fast_exp_n<2>(a, o); r = o[0] + o[1]; break; }  // e^v + e^(v-1)

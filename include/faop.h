@@ -273,7 +273,7 @@ int64_t faop_launch_count(void);
  * kind 0 = fast_exp, 1 = mills_half (Phi(-y)/exp(-y^2/2)), 2 = fast_sqrt_pos, 3 = fast_rcp, 4 = Phi via fast path,
  * 5 = erfcx(x)/2 (x >= 0), 6 = sqrt(max(0, x)), 7 = e^x + e^(x-1) (two interleaved chains),
  * 8 = erfcx(x)/2 degree-14 variant, 9 = e^x degree-8 variant (the quadrature-point versions), 10 = fast_log,
- * 11 = Phi(x) as the leaf kernels compute it (erfc based). */
+ * 11 = Phi(x) as the leaf kernels compute it (erfc based), 12 = erfcx(x)/2 degree-16 variant. */
 int faop_dev_math_batch(int32_t kind, int64_t N, const double* x, double* out, void* cuda_stream);
 /* FP64 FMA-pipe peak microbenchmark (the roofline denominator; MEASURED_PEAKS.json has no FP64
  * figure): launches `launches` saturating DFMA kernels, returns measured TFLOP/s (2 flops/DFMA). */

@@ -225,6 +225,8 @@ def test_device_math():
     x = np.concatenate([g.uniform(0, 8, 200000), g.uniform(8, 45, 50000)])
     got = batch.dev_math_batch(8, x).cpu().numpy()
     assert np.max(np.abs(got / (0.5 * erfcx(x)) - 1)) <= 4e-11
+    got = batch.dev_math_batch(12, x).cpu().numpy()                       # degree 16: the n > 12 kernels (r tau up to 1.5 at C3)
+    assert np.max(np.abs(got / (0.5 * erfcx(x)) - 1)) <= 2e-12
     x = g.uniform(-690, 1, 200000)
     got = batch.dev_math_batch(9, x).cpu().numpy()
     assert np.max(np.abs(got / np.exp(x) - 1)) <= 2e-12
