@@ -819,6 +819,10 @@ def test_cn_device_countdown_equals_host_schedule():
             p2, X2 = batch.cn_put_batch(*aa, n_space=n_space, max_dt=mdt[:cnt], mode=mode, want_grid=True,
                                         schedule=(sched[0][:cnt], sched[1][:cnt]))
             assert torch.equal(p1, p2) and torch.equal(X1, X2), (n_space, mode)
+    # inputs the upstream loop would never return from must not hang the device: T = inf / NaN -> no steps (the payoff)
+    for Tbad in (float("inf"), float("nan")):
+        p = batch.cn_put_batch(0.04, 0.01, 0.2, 100.0, Tbad, 80.0, n_space=200, max_dt=0.1, mode=2)
+        assert abs(p.item() - 20.0) < 1e-12
 
 
 def test_plain_c_caller_runs():
