@@ -304,6 +304,7 @@ def main():
     same = bool(np.array_equal(hout["price"], out["price"].cpu().numpy(), equal_nan=True))
 
     tf_peak, _ = batch.measure_fp64_peak(20)
+    mix_pps, _ = batch.measure_point_mix_peak(10)
 
     red = torch.tensor([ms_step, ms_e2e, ms_kernel], dtype=torch.float64, device=dev)
     if world > 1:
@@ -354,7 +355,13 @@ def main():
                                  # port for two cycles, any other for one.  20.87 k FP64 + 14.92 k other warp instructions per
                                  # option at 19.32 sweeps (ncu source page) over this run's cycles per option and SMSP
                                  "issue_port_frac": (2 * 20871.7 + 14922.0) * iters_mean / 19.316 /
-                                                    (ms_kernel * 1e-3 * (clocks["sm_mhz"] or 1965.0) * 1e6 * kSMSP / Nopt)},
+                                                    (ms_kernel * 1e-3 * (clocks["sm_mhz"] or 1965.0) * 1e6 * kSMSP / Nopt),
+                                 # quadrature points/s of this launch (options * sweeps * n * l) over the rate of the same
+                                 # per-point math on register operands alone, measured in this run (faop_measure_point_mix_peak):
+                                 # what the loads, reductions, node closures, seeds and the price integral cost on top
+                                 "points_per_s": Nopt * iters_mean * cfgd["n"] * cfgd["l"] / (ms_kernel / 1e3),
+                                 "point_math_peak_points_per_s": mix_pps,
+                                 "point_math_frac": Nopt * iters_mean * cfgd["n"] * cfgd["l"] / (ms_kernel / 1e3) / mix_pps},
                              "peak_source": "register-operand DFMA chains measured in this run (faop_measure_fp64_peak); "
                                             "MEASURED_PEAKS.json has no FP64 figure"},
                 "cpu_baseline": {"value": cpu_rate, "unit": UNIT, "cores": threads, "kind": "port",

@@ -613,6 +613,18 @@ def measure_fp64_peak(launches=20, device=None):
         return tf.value, ms.value
 
 
+def measure_point_mix_peak(launches=10, device=None):
+    """Quadrature points per second of the flagship kernel's point math alone (register operands, no memory traffic):
+    the speed of light that options/s * sweeps * n * l of the real kernel is compared with.  Returns (points_per_s, ms)."""
+    lib = _lib.load()
+    dev = _device(device)
+    with torch.cuda.device(dev):
+        pps, ms = ctypes.c_double(), ctypes.c_double()
+        check(lib.faop_measure_point_mix_peak(int(launches), ctypes.byref(pps), ctypes.byref(ms), _stream(dev)),
+              "faop_measure_point_mix_peak")
+        return pps.value, ms.value
+
+
 class HostContext:
     """faop_ctx wrapper: the host-buffer entry point (numpy / pinned host arrays in and out), used by the
     e2e leg of bench.py and by callers that do not hold device memory."""

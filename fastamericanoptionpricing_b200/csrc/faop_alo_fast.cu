@@ -36,7 +36,7 @@ struct FastWarpSmem {
     double red[8 * 36];   // transpose buffer of the per-group reduction, row pitch 36 = 4 (mod 16): conflict-free both ways
 };
 
-template <int kFastWarps, bool SNAP = false, int SOLVER = 0, bool DERIV = false>
+template <int kFastWarps, bool SNAP = false, int SOLVER = 0, bool DERIV = false, bool ERRS = false>
 __global__ void __launch_bounds__(kFastWarps * 32, 1) alo_fast_A12_kernel(AloArgs a) {
     static_assert(!DERIV || (SOLVER == 0 && !SNAP), "the derivative instantiation exists for Solver A only");
     extern __shared__ double smem[];
@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(kFastWarps * 32, 1) alo_fast_A12_kernel(AloArg
                     if (a.err) a.err[opt] = 1e6;
                 }
                 if (a.B && lane < NN) a.B[opt * NN + lane] = nan("");
-                if (a.iter_errs) for (int j = lane; j < a.cfg.max_iters; j += 32) a.iter_errs[opt * a.cfg.max_iters + j] = nan("");
+                if (ERRS) for (int j = lane; j < a.cfg.max_iters; j += 32) a.iter_errs[opt * a.cfg.max_iters + j] = nan("");
                 continue;
             }
             // ---- per-option setup: node constants (lanes 0..12) and the invariant e^{q u_ik} table
@@ -290,7 +290,7 @@ __global__ void __launch_bounds__(kFastWarps * 32, 1) alo_fast_A12_kernel(AloArg
             }
             err = warp_sum(dd * dd);               // norm1_error is the 2-norm over all n+1 nodes (:230-233)
             if (SNAP) err = sqrt(err);
-            if (!SNAP && a.iter_errs && lane == 0) a.iter_errs[opt * a.cfg.max_iters + (count - 1)] = sqrt(err);  // iter_records (:130)
+            if (ERRS && lane == 0) a.iter_errs[opt * a.cfg.max_iters + (count - 1)] = sqrt(err);  // iter_records (:130)
             __syncwarp();
             if (SNAP && err <= a.snap_tol_hi && err < best) {
                 best = err;
@@ -304,7 +304,7 @@ __global__ void __launch_bounds__(kFastWarps * 32, 1) alo_fast_A12_kernel(AloArg
             continue;
         }
         if (count > 0) err = sqrt(err);            // not SNAP here: back to the norm the reference reports (self.error)
-        if (!SNAP && a.iter_errs)
+        if (ERRS)
             for (int j = count + lane; j < a.cfg.max_iters; j += 32) a.iter_errs[opt * a.cfg.max_iters + j] = nan("");
         if (a.B && lane < NN) a.B[opt * NN + lane] = ws.B[lane];
         double eur;
@@ -320,13 +320,13 @@ __global__ void __launch_bounds__(kFastWarps * 32, 1) alo_fast_A12_kernel(AloArg
     }
 }
 
-template <int kFastWarps, bool SNAP = false, int SOLVER = 0, bool DERIV = false>
+template <int kFastWarps, bool SNAP = false, int SOLVER = 0, bool DERIV = false, bool ERRS = false>
 static int launch_fast_t(const AloArgs& a, cudaStream_t st) {
     const size_t sm = sizeof(double) * (size_t)(a.tl.small + NC * NC * 32) + sizeof(FastWarpSmem<SOLVER>) * kFastWarps;
-    FAOP_CUDA_OK(cudaFuncSetAttribute(alo_fast_A12_kernel<kFastWarps, SNAP, SOLVER, DERIV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    FAOP_CUDA_OK(cudaFuncSetAttribute(alo_fast_A12_kernel<kFastWarps, SNAP, SOLVER, DERIV, ERRS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     int64_t ctas = (a.N + kFastWarps - 1) / kFastWarps;
     int grid = (int)(ctas < kSMs ? ctas : kSMs);
-    alo_fast_A12_kernel<kFastWarps, SNAP, SOLVER, DERIV><<<grid, kFastWarps * 32, sm, st>>>(a);
+    alo_fast_A12_kernel<kFastWarps, SNAP, SOLVER, DERIV, ERRS><<<grid, kFastWarps * 32, sm, st>>>(a);
     count_launch();
     return launch_status();
 }
@@ -338,6 +338,10 @@ int launch_alo_fast(const AloArgs& a, cudaStream_t st) {
                        a.tl.has_matrix && (a.iter_errs == nullptr || !a.snap);
     if (!match) return -1000;
     if (a.N == 0) return 0;
+    if (a.iter_errs) {      // per-iteration error history (the drop-in classes' iter_records): its own instantiations
+        if (a.cfg.use_derivative) return launch_fast_t<16, false, 0, true, true>(a, st);
+        return a.cfg.solver == 1 ? launch_fast_t<16, false, 1, false, true>(a, st) : launch_fast_t<16, false, 0, false, true>(a, st);
+    }
     if (a.cfg.use_derivative) return launch_fast_t<16, false, 0, true>(a, st);
     if (a.cfg.solver == 1) return a.snap ? launch_fast_t<16, true, 1>(a, st) : launch_fast_t<16, false, 1>(a, st);
     if (a.snap) return launch_fast_t<16, true>(a, st);

@@ -513,6 +513,10 @@ int faop_dev_math_batch(int32_t kind, int64_t N, const double* x, double* out, v
     return launch_dev_math(kind, N, x, out, (cudaStream_t)cuda_stream);
 }
 
+int faop_measure_point_mix_peak(int launches, double* points_per_s, double* ms_per_launch, void* cuda_stream) {
+    if (launches < 1) return FAOP_EINVAL;
+    return launch_point_mix_peak(launches, points_per_s, ms_per_launch, (cudaStream_t)cuda_stream);
+}
 int faop_measure_fp64_peak(int launches, double* tflops, double* ms_per_launch, void* cuda_stream) {
     if (launches < 1) return FAOP_EINVAL;
     return launch_fp64_peak(launches, tflops, ms_per_launch, (cudaStream_t)cuda_stream);

@@ -98,5 +98,6 @@ int launch_surface_decode(const faop_surface& s, int64_t first, int64_t count, d
                           double* K, double* T, double* S, uint8_t* is_put, cudaStream_t st);
 int launch_dev_math(int kind, int64_t N, const double* x, double* out, cudaStream_t st);
 int launch_fp64_peak(int launches, double* tflops, double* ms_per_launch, cudaStream_t st);
+int launch_point_mix_peak(int launches, double* points_per_s, double* ms_per_launch, cudaStream_t st);
 
 }  // namespace faop

@@ -264,6 +264,76 @@ int launch_iv_update(int64_t N, const double* target, const double* price, doubl
     return launch_status();
 }
 
+// Transcendental-mix microbenchmark: the per-quadrature-point math of the flagship kernel — 12 DFMA of
+// interpolation, sqrt, the d+- arguments, two degree-8 exp, one degree-14 erfcx, the combine — on register operands only,
+// two points in lock step, 16 warps per SM: no shared-memory traffic, no reductions, no node closure.  Its rate in
+// points/s is the speed of light of the point math on this GPU; options/s * sweeps * n * l of the real kernel over that rate
+// says how much the surrounding machinery costs.
+constexpr int kMixIters = 2048;
+__global__ void __launch_bounds__(512, 1) point_mix_kernel(double* sink, double seed) {
+    double Hj[12], acc0 = 0.0, acc1 = 0.0;
+#pragma unroll
+    for (int j = 0; j < 12; ++j) Hj[j] = 0.01 * (j + 1) + seed * threadIdx.x;
+    double m0 = 0.3 + 1e-6 * threadIdx.x, m1 = 0.29 - 1e-6 * threadIdx.x;
+    const double L = -0.2 + seed, cinv2rh = 1.7, apc2h = 0.05, ssu2h = 0.11, qtg = 0.02, rtg = 0.04, lnw = -3.0, cis = 0.8, h = 0.37, eqw = 0.9;
+#pragma unroll 1
+    for (int it = 0; it < kMixIters; ++it) {
+        double Hu[2] = {0.0, 0.0}, root[2];
+#pragma unroll
+        for (int j = 0; j < 12; ++j) {      // the matrix entries are lane data in the real kernel; here two drifting registers
+            Hu[0] = fma(m0, Hj[j], Hu[0]);
+            Hu[1] = fma(m1, Hj[j], Hu[1]);
+        }
+        m0 = fma(m0, 0.999999, 1e-9);
+        m1 = fma(m1, 0.999998, 2e-9);
+        sqrt_clamped_n<2>(Hu, root);
+        double ex[4], xa[2], xp[2];
+#pragma unroll
+        for (int p = 0; p < 2; ++p) {
+            const double lnz = L + root[p];
+            xp[p] = fma(lnz, cinv2rh, apc2h);
+            const double xm = xp[p] - ssu2h;
+            ex[2 * p] = fma(-xp[p], xp[p], qtg + lnw);
+            ex[2 * p + 1] = fma(-xm, xm, rtg + lnw);
+            xa[p] = fabs(xp[p]);
+        }
+        double E[4], G[2];
+        fast_exp_n<4, true>(ex, E);
+        half_erfcx_n<2, true>(xa, G);
+#pragma unroll
+        for (int p = 0; p < 2; ++p) {
+            const double ec = E[2 * p] * G[p];
+            const double cdf = (__double2hiint(xp[p]) < 0) ? ec : eqw - ec;
+            acc0 += E[2 * p + 1];
+            acc1 += fma(cis, E[2 * p], h * cdf);
+        }
+    }
+    const double s2 = acc0 + acc1;
+    if (s2 == 123456.789) sink[0] = s2;
+}
+int launch_point_mix_peak(int launches, double* points_per_s, double* ms_per_launch, cudaStream_t st) {
+    double* buf = nullptr;
+    FAOP_CUDA_OK(cudaMalloc(&buf, sizeof(double)));
+    cudaEvent_t e0, e1;
+    FAOP_CUDA_OK(cudaEventCreate(&e0));
+    FAOP_CUDA_OK(cudaEventCreate(&e1));
+    const int blocks = kSMs * 4, threads = 512;
+    for (int w = 0; w < 2; ++w) { point_mix_kernel<<<blocks, threads, 0, st>>>(buf, 1e-7); count_launch(); }
+    FAOP_CUDA_OK(cudaEventRecord(e0, st));
+    for (int i = 0; i < launches; ++i) { point_mix_kernel<<<blocks, threads, 0, st>>>(buf, 1e-7); count_launch(); }
+    FAOP_CUDA_OK(cudaEventRecord(e1, st));
+    FAOP_CUDA_OK(cudaEventSynchronize(e1));
+    float ms = 0;
+    FAOP_CUDA_OK(cudaEventElapsedTime(&ms, e0, e1));
+    const double points = 2.0 * (double)kMixIters * (double)blocks * threads * launches;
+    if (points_per_s) *points_per_s = points / (ms * 1e-3);
+    if (ms_per_launch) *ms_per_launch = ms / launches;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(buf);
+    return launch_status();
+}
+
 int launch_qd_boundary(int64_t N, const double* r, const double* q, const double* sigma, const double* K,
                        const double* tau, const uint8_t* is_put, double* B, cudaStream_t st) {
     if (N == 0) return 0;
