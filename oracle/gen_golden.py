@@ -449,8 +449,28 @@ def gen_bs(pool, count=1024):
     print("bs: %d, main call %r put %r, nan %d" % (count, main_call, main_put, np.isnan(price).sum()))
 
 
+def gen_c5(pool, count=None):
+    """Config 5 (surface sweep): a seeded sample of flat indices of the 1000 x 1000 x 100 grid through the live reference,
+    plus whole strike ladders of a few (T, sigma) scenarios (the deduplicated path's unit of work)."""
+    count = count or int(os.environ.get("FAOP_GOLDEN_C5", "256"))
+    g = np.random.default_rng(55)
+    flat = np.sort(g.choice(100_000_000, size=count, replace=False))
+    ladders = []
+    for iT, iV in ((3, 5), (500, 50), (999, 99)):
+        for iK in range(0, 1000, 37):
+            ladders.append((iK * 1000 + iT) * 100 + iV)
+    idx = np.concatenate([flat, np.array(ladders, dtype=np.int64)])
+    parts = [wl.c5_surface(int(i), 1) for i in idx]
+    b = {k: np.concatenate([p_[k] for p_ in parts]) for k in parts[0]}
+    out = run_batch(pool, "A", b, wl.C5_CFG, list(range(len(idx))))
+    out["flat_index"] = idx
+    np.savez(os.path.join(OUT, "ref_c5_surface.npz"), **out)
+    print("c5: %d options, iters min/med/max %d/%d/%d, nan %d" % (len(idx), out["iters"].min(), np.median(out["iters"]),
+                                                                 out["iters"].max(), np.isnan(out["price"]).sum()))
+
+
 GENS = dict(c1=gen_c1, european=gen_european, cheb=gen_cheb, qd=gen_qd, stage=gen_stage, misc=gen_misc, cn=gen_cn,
-            c3=gen_c3, c2=gen_c2, bs=gen_bs)
+            c3=gen_c3, c2=gen_c2, bs=gen_bs, c5=gen_c5)
 
 
 def main():

@@ -971,3 +971,31 @@ def test_put_call_symmetry():
         ok = np.isfinite(P["price"]) & np.isfinite(C["price"]) & (P["err"] < 1e-8) & (C["err"] < 1e-8)
         d = np.abs(P["price"] - C["price"])[ok]
         assert ok.mean() > 0.9 and d.max() <= 2e-4 and np.median(d) <= 1e-6, (cfg.solver, cfg.kernel, ok.mean(), d.max(), np.median(d))
+
+
+def test_c5_surface_against_live_reference():
+    """Config 5 against the live-reference fixture: the plain sweep and the deduplicated sweep at the sampled flat indices, and
+    whole strike ladders of three (T, sigma) scenarios through faop_alo_ladder_batch — prices to 1e-9, same sweep counts."""
+    g = load_golden("ref_c5_surface.npz")
+    cfg = AloConfig(**wl.C5_CFG)
+    surf = dict(K0=50.0, K1=150.0, T0=1.0 / 52, T1=3.0, V0=0.10, V1=0.60, S=100.0, r=0.04, q=0.01, nK=1000, nT=1000, nV=100)
+    ps = parity_set({k: g[k] for k in ("price", "err")})
+    flat = g["flat_index"]
+    for dedup in (False, True):
+        got = np.empty(len(flat)); its = np.empty(len(flat), dtype=np.int64)
+        for j, i in enumerate(flat):
+            p, it = batch.surface_batch(surf, int(i), 1, cfg, want_iters=True, dedup=dedup)
+            got[j], its[j] = p.item(), it.item()
+        assert np.abs(got - g["price"])[ps].max() <= PRICE_ABS_TOL, dedup
+        assert (its[ps] != g["iters"][ps]).sum() == 0, dedup
+    # ladders: the last 3 x 28 fixture rows are (iT, iV) in ((3, 5), (500, 50), (999, 99)) at every 37th strike
+    Kl = np.linspace(50.0, 150.0, 1000)[::37]
+    Tg, Vg = np.linspace(1.0 / 52, 3.0, 1000), np.linspace(0.10, 0.60, 100)
+    sc = ((3, 5), (500, 50), (999, 99))
+    T = np.array([Tg[a] for a, _ in sc]); V = np.array([Vg[b_] for _, b_ in sc])
+    P, it = batch.ladder_batch(np.full(3, 0.04), np.full(3, 0.01), V, T, np.full(3, 100.0), np.ones(3, dtype=np.uint8), Kl, cfg=cfg,
+                               want_iters=True)
+    n0 = len(flat) - 3 * len(Kl)
+    ref_p = g["price"][n0:].reshape(3, len(Kl)); ref_i = g["iters"][n0:].reshape(3, len(Kl)); okl = ps[n0:].reshape(3, len(Kl))
+    assert np.array_equal(g["in_K"][n0:n0 + len(Kl)], Kl)
+    assert np.abs(P.cpu().numpy() - ref_p)[okl].max() <= PRICE_ABS_TOL and (it.cpu().numpy()[okl] != ref_i[okl]).sum() == 0

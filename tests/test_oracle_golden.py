@@ -217,3 +217,16 @@ def test_bjerksund_stensland_golden():
     assert np.max(np.abs(pg - z["price_g"]) / (1 + np.abs(z["price_g"]))) <= 1e-14
     assert o.bs_price(80, .04, .04, .2, 100, 3.0, 100, 3.0) == 4.342423011041589 == float(z["main_call"])
     assert o.bs_price(100, .04, .04, .2, 80, 3.0, 100, 3.0) == 23.062019527897103 == float(z["main_put"])
+
+
+def test_c5_surface_sample_golden():
+    """Config 5 sample (seeded flat indices of the 1000 x 1000 x 100 grid + strike ladders of three scenarios) through the
+    live reference: the C port reproduces it, and the index decoding of workloads.c5_surface matches the fixture's inputs."""
+    from fastamericanoptionpricing_b200 import workloads as wl
+    g = load_golden("ref_c5_surface.npz")
+    for j in (0, 100, len(g["flat_index"]) - 1):
+        s = wl.c5_surface(int(g["flat_index"][j]), 1)
+        assert s["K"][0] == g["in_K"][j] and s["T"][0] == g["in_T"][j] and s["sigma"][0] == g["in_sigma"][j]
+    out = co.alo_price_batch("A", *_inputs(g), n=12, l=32, m=64, iter_tol=1e-5, max_iters=20)
+    ps = _check(out, g, tag="c5 c")
+    assert ps.sum() >= 0.95 * len(ps)
