@@ -22,6 +22,7 @@ namespace faop {
 constexpr int NC = 12;        // collocation n
 constexpr int NN = NC + 1;    // nodes
 constexpr int kGroup = 4;     // nodes per transposing reduction
+constexpr int kPointErfcxTier = 2;   // erfcx fit at the quadrature points: 1 = degree 14 (3e-11), 2 = degree 16 (1.4e-12)
 
 template <int SOLVER>
 struct FastWarpSmem {
@@ -190,7 +191,7 @@ __global__ void __launch_bounds__(kFastWarps * 32, 1) alo_fast_A12_kernel(AloArg
                         fast_exp_n<4, true>(ex, E);         // E[2p] = w e^{qu} phi(d+) sqrt(2 pi), E[2p+1] = w e^{ru} phi(d-) sqrt(2 pi)
                         if (SOLVER == 0) {
                             double xa2[2] = {xa[0], xa[2]}, G[2];
-                            half_erfcx_n<2, true>(xa2, G);
+                            half_erfcx_n<2, kPointErfcxTier>(xa2, G);
 #pragma unroll
                             for (int p = 0; p < 2; ++p) {
                                 // put: +w e^{qu} Phi(d+); call: -w e^{qu} Phi(-d+)   (FastAmericanOptionSolverA.py:27-32)
@@ -221,7 +222,7 @@ __global__ void __launch_bounds__(kFastWarps * 32, 1) alo_fast_A12_kernel(AloArg
                             }
                         } else {
                             double G[4];
-                            half_erfcx_n<4, true>(xa, G);
+                            half_erfcx_n<4, kPointErfcxTier>(xa, G);
 #pragma unroll
                             for (int p = 0; p < 2; ++p) {
                                 // w e^{qu} Phi(om d+) and w e^{ru} Phi(om d-)   (FastAmericanOptionSolverB.py:25-39)

@@ -265,7 +265,7 @@ int launch_iv_update(int64_t N, const double* target, const double* price, doubl
 }
 
 // Transcendental-mix microbenchmark: the per-quadrature-point math of the flagship kernel — 12 DFMA of
-// interpolation, sqrt, the d+- arguments, two degree-8 exp, one degree-14 erfcx, the combine — on register operands only,
+// interpolation, sqrt, the d+- arguments, two degree-8 exp, one degree-16 erfcx, the combine — on register operands only,
 // two points in lock step, 16 warps per SM: no shared-memory traffic, no reductions, no node closure.  Its rate in
 // points/s is the speed of light of the point math on this GPU; options/s * sweeps * n * l of the real kernel over that rate
 // says how much the surrounding machinery costs.
@@ -299,7 +299,7 @@ __global__ void __launch_bounds__(512, 1) point_mix_kernel(double* sink, double 
         }
         double E[4], G[2];
         fast_exp_n<4, true>(ex, E);
-        half_erfcx_n<2, true>(xa, G);
+        half_erfcx_n<2, 2>(xa, G);
 #pragma unroll
         for (int p = 0; p < 2; ++p) {
             const double ec = E[2 * p] * G[p];

@@ -106,3 +106,17 @@ def c5_surface(start=0, count=None, nK=1000, nT=1000, nV=100):
 
 
 C5_CFG = dict(C2_CFG)
+
+
+def stress_batch(N=6000, seed=123):
+    """Hard corners on top of the C3 thirds (low vol x long T, long T, q > r): deep ITM/OTM spots, maturities down to 1e-4,
+    r == q, q == 0 (calls take the European shortcut), r ~ 0.  Used by the stress parity test and its live-reference fixture."""
+    b = {k: v[:N].copy() for k, v in c3_batch(N).items()}
+    g = np.random.default_rng(seed)
+    b["S"][0:500] = b["K"][0:500] * g.uniform(0.02, 0.3, 500)
+    b["S"][500:1000] = b["K"][500:1000] * g.uniform(3.0, 20.0, 500)
+    b["T"][1000:1500] = 10 ** g.uniform(-4, -2, 500)
+    b["q"][1500:1800] = b["r"][1500:1800]
+    b["q"][1800:2000] = 0.0
+    b["r"][2000:2100] = 1e-6
+    return b

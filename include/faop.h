@@ -279,7 +279,7 @@ int faop_dev_math_batch(int32_t kind, int64_t N, const double* x, double* out, v
  * figure): launches `launches` saturating DFMA kernels, returns measured TFLOP/s (2 flops/DFMA). */
 int faop_measure_fp64_peak(int launches, double* tflops, double* ms_per_launch, void* cuda_stream);
 /* Transcendental-mix microbenchmark: the flagship kernel's per-quadrature-point math (12 DFMA interpolation, sqrt, two
- * degree-8 exp, one degree-14 erfcx, combine) on register operands, no memory traffic: quadrature points per second.   */
+ * degree-8 exp, one degree-16 erfcx, combine) on register operands, no memory traffic: quadrature points per second.   */
 int faop_measure_point_mix_peak(int launches, double* points_per_s, double* ms_per_launch, void* cuda_stream);
 
 #ifdef __cplusplus

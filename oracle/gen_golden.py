@@ -469,8 +469,21 @@ def gen_c5(pool, count=None):
                                                                  out["iters"].max(), np.isnan(out["price"]).sum()))
 
 
+def gen_stress(pool):
+    """Hard corners through the live reference (Solver A, n=12, l=32, m=64, tol 1e-5, 40 sweeps): a slice of every block of
+    workloads.stress_batch — deep ITM/OTM, tiny maturities (the ill-conditioned QD seeds), r == q, q == 0, r ~ 0."""
+    b = wl.stress_batch(6000)
+    b["t"] = np.zeros(6000)
+    idx = [i for lo in (0, 500, 1000, 1500, 1800, 2000, 2100) for i in range(lo, lo + 12)] + list(range(1400, 1436))
+    cfg = dict(wl.C2_CFG, max_iters=40)
+    out = run_batch(pool, "A", b, cfg, idx)
+    out["index"] = np.array(idx)
+    np.savez(os.path.join(OUT, "ref_stress_A.npz"), **out)
+    print("stress: %d options, nan %d, err>=1e-2 %d" % (len(idx), np.isnan(out["price"]).sum(), (out["err"] >= 1e-2).sum()))
+
+
 GENS = dict(c1=gen_c1, european=gen_european, cheb=gen_cheb, qd=gen_qd, stage=gen_stage, misc=gen_misc, cn=gen_cn,
-            c3=gen_c3, c2=gen_c2, bs=gen_bs, c5=gen_c5)
+            c3=gen_c3, c2=gen_c2, bs=gen_bs, c5=gen_c5, stress=gen_stress)
 
 
 def main():
