@@ -343,18 +343,18 @@ def main():
                              "flop_model": "SURVEY 8d nominal: add/mul 1, FMA 2, div/sqrt 16, exp 40, log 56, Phi 120, phi 42 "
                                            "at the realised mean iteration count",
                              # hardware-side view of the same launch: DFMA x2 + DMUL + DADD thread instructions per option
-                             # counted by ncu (profiles/r1_alo_fast_A12_ncu_full.csv, 1.104 MFLOP at 19.32 sweeps), scaled
+                             # counted by ncu (profiles/r1_alo_fast_A12_ncu_full.csv, 1.131 MFLOP at 19.32 sweeps), scaled
                              # to this run's sweep count; the nominal model prices exp/Phi/sqrt as 40/120/16 flops where
                              # the kernel spends 24/50/12, which is why `frac` can exceed 1
                              "executed": None if args.kernel != 0 else {
-                                 "flops_per_option": 1.104e6 * iters_mean / 19.316,
-                                 "tflops": 1.104e6 * iters_mean / 19.316 * Nopt / (ms_kernel / 1e3) / 1e12,
-                                 "frac": 1.104e6 * iters_mean / 19.316 * Nopt / (ms_kernel / 1e3) / 1e12 / tf_peak,
-                                 "fp64_pipe_active_pct_ncu": 70.1,
+                                 "flops_per_option": 1.131e6 * iters_mean / 19.316,
+                                 "tflops": 1.131e6 * iters_mean / 19.316 * Nopt / (ms_kernel / 1e3) / 1e12,
+                                 "frac": 1.131e6 * iters_mean / 19.316 * Nopt / (ms_kernel / 1e3) / 1e12 / tf_peak,
+                                 "fp64_pipe_active_pct_ncu": 70.7,
                                  # what actually bounds the kernel: an FP64 warp instruction holds the SMSP issue
-                                 # port for two cycles, any other for one.  20.87 k FP64 + 14.92 k other warp instructions per
+                                 # port for two cycles, any other for one.  21.34 k FP64 + 15.12 k other warp instructions per
                                  # option at 19.32 sweeps (ncu source page) over this run's cycles per option and SMSP
-                                 "issue_port_frac": (2 * 20871.7 + 14922.0) * iters_mean / 19.316 /
+                                 "issue_port_frac": (2 * 21335.4 + 15116.2) * iters_mean / 19.316 /
                                                     (ms_kernel * 1e-3 * (clocks["sm_mhz"] or 1965.0) * 1e6 * kSMSP / Nopt),
                                  # quadrature points/s of this launch (options * sweeps * n * l) over the rate of the same
                                  # per-point math on register operands alone, measured in this run (faop_measure_point_mix_peak):

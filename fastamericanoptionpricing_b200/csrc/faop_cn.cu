@@ -22,7 +22,8 @@ namespace faop {
 
 constexpr int kCnThreads = 256;
 constexpr int kCnWarps = kCnThreads / 32;
-constexpr int kCnMaxCountdownSteps = 1 << 24;   // a max_dt of ~0 must not hang the GPU (upstream would loop on)
+// longest countdown the kernels accept: 2^24 steps of max_dt (finite); a max_dt of ~0 must not hang the GPU
+__device__ __forceinline__ double mdt_guard(double max_dt) { return (max_dt > 0) ? fmin(max_dt * 16777216.0, 1.79e308) : 0.0; }
 constexpr unsigned kFullMask = 0xffffffffu;
 
 struct CnArgs {
@@ -140,13 +141,15 @@ __global__ void __launch_bounds__(kCnThreads, (NPT <= 8 ? 2 : 1)) cn_scan_kernel
         const bool sched = a.dts != nullptr;
         const int nsteps = sched ? a.n_steps[opt] : 0;
         double trem = sched ? 0.0 : a.T[opt];
-        if (!(trem < 1.79e308)) trem = 0.0;     // T = inf / NaN would never count down: no steps (upstream would not return either)
+        // T = inf / NaN, or more than 2^24 steps of max_dt, would keep the device busy (almost) forever: no steps at all then
+        // (upstream would not return either); checked once, outside the time loop
+        if (!sched && !(trem <= mdt_guard(a.max_dt[opt]))) trem = 0.0;
         const double mdt = sched ? 0.0 : a.max_dt[opt];
         double dt_prev = -1.0;
         __syncthreads();                          // the previous option's output pass is done with s_seq
         if (lane == 0) s_eL[warp] = X[0];
         if (lane == 31) s_eR[warp] = X[NPT - 1];
-        for (int st = 0; (sched ? st < nsteps : trem > 0) && st < kCnMaxCountdownSteps; ++st) {
+        for (int st = 0; sched ? st < nsteps : trem > 0; ++st) {
             const double dt = sched ? a.dts[opt * a.max_steps + st] : fmin(trem, mdt);
             if (!sched) {
                 if (!(dt > 0)) break;     // max_dt <= 0 never terminates upstream
@@ -425,9 +428,9 @@ __global__ void __launch_bounds__(64) cn_sor_kernel(CnArgs a) {
     const bool sched = a.dts != nullptr;
     const int nsteps = sched ? a.n_steps[opt] : 0;
     double trem = sched ? 0.0 : a.T[opt];
-    if (!(trem < 1.79e308)) trem = 0.0;
+    if (!sched && !(trem <= mdt_guard(a.max_dt[opt]))) trem = 0.0;
     const double mdt = sched ? 0.0 : a.max_dt[opt];
-    for (int st = 0; (sched ? st < nsteps : trem > 0) && st < kCnMaxCountdownSteps; ++st) {
+    for (int st = 0; sched ? st < nsteps : trem > 0; ++st) {
         const double dt = sched ? a.dts[opt * a.max_steps + st] : fmin(trem, mdt);
         if (!sched) {
             if (!(dt > 0)) break;
