@@ -1,0 +1,46 @@
+"""CPU: host-side logic of the batch layer that needs no device — the Crank-Nicolson countdown schedule, the solver
+configuration struct, workload generators."""
+import ctypes
+
+import numpy as np
+
+from fastamericanoptionpricing_b200 import _lib, batch, workloads as wl
+from oracle import alo_oracle as o
+
+
+def test_cn_schedule_vectorised_equals_scalar_countdown():
+    """cn_dt_schedule_batch == the reference's float countdown (CrankNicolsonOptionSolver.py:36-45) option by option, including
+    the ~1e-16-long last step that appears when T is not an exact multiple of max_dt in floating point."""
+    g = np.random.default_rng(7)
+    T = np.concatenate([g.uniform(0.01, 5.0, 200), [3.0, 1.0, 0.25, 0.0]])
+    mdt = np.concatenate([T[:100] / g.integers(1, 400, 100), g.uniform(0.001, 1.0, 100), [3.0 / 300, 1.0 / 12, 1.0, 0.1]])
+    dts, ns = batch.cn_dt_schedule_batch(T, mdt)
+    extra = 0
+    for i in range(len(T)):
+        ref = batch.cn_dt_schedule(T[i], mdt[i])
+        assert ns[i] == len(ref) and np.array_equal(dts[i, :ns[i]], np.array(ref)) and np.all(dts[i, ns[i]:] == 0)
+        assert ref == o.cn_dt_schedule(T[i], mdt[i])
+        if len(ref) and ref[-1] < 1e-9 * mdt[i]:
+            extra += 1
+    assert extra >= 1 and len(batch.cn_dt_schedule(3.0, 3.0 / 300)) == 301      # the survey's example of the extra step
+    assert batch.cn_dt_schedule(0.0, 0.1) == []
+
+
+def test_config_struct_round_trip():
+    cfg = batch.AloConfig("B", 24, 64, 128, 1e-7, 77, use_derivative=True, eta=0.75, kernel=1)
+    c = cfg.c(_lib.FLAG_WS_SCRATCH)
+    assert (c.solver, c.use_derivative, c.n_colloc, c.n_quad, c.n_price_quad, c.max_iters, c.kernel, c.flags) == (1, 1, 24, 64, 128, 77, 1, 1)
+    assert c.iter_tol == 1e-7 and c.eta == 0.75 and batch.AloConfig().c().flags == 0
+    d = batch.AloConfig()          # the reference's constructor defaults (FastAmericanOptionSolverBase.py:19-23, 46-47)
+    assert (d.solver, d.n, d.l, d.m, d.iter_tol, d.max_iters, d.use_derivative, d.eta) == ("A", 12, 24, 48, 1e-5, 200, False, 0.5)
+    assert d.rule_l == d.rule_m == "gauss-legendre"
+    assert ctypes.sizeof(c) == 48
+
+
+def test_stress_workload_blocks():
+    b = wl.stress_batch(3000)
+    assert np.all(b["S"][:500] < 0.31 * b["K"][:500]) and np.all(b["S"][500:1000] > 2.9 * b["K"][500:1000])
+    assert np.all(b["T"][1000:1500] <= 1e-2) and np.array_equal(b["q"][1500:1800], b["r"][1500:1800])
+    assert np.all(b["q"][1800:2000] == 0) and np.all(b["r"][2000:2100] == 1e-6)
+    b2 = wl.stress_batch(3000)
+    assert all(np.array_equal(b[k], b2[k]) for k in b)       # seeded
