@@ -16,5 +16,9 @@ ncu --set full --clock-control none --import-source on -k regex:alo_clen -c 1 -f
 ncu --set full --clock-control none --import-source on -k regex:cn_scan -c 1 -f -o gpurun_out/prof_cn_r1 \
     python tools/profile_cn.py 592 2 > gpurun_out/ncu_cn.log 2>&1
 python tools/throughput_table.py > gpurun_out/throughput_r1.txt 2>&1
-python tools/time_cn.py 8192 > gpurun_out/time_cn.log 2>&1
+python tools/time_cn.py 8192 100000 > gpurun_out/time_cn.log 2>&1
+python tools/time_c3.py > gpurun_out/time_c3.log 2>&1
+python tools/time_c1_latency.py > gpurun_out/c1_latency.txt 2>&1
+python tools/parity_report.py > gpurun_out/parity_report.txt 2>&1
+python tools/parity_full.py > gpurun_out/parity_full.txt 2>&1
 tail -2 gpurun_out/bench_r1.json | cut -c1-400
