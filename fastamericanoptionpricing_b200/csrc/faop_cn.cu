@@ -50,10 +50,12 @@ __device__ double interp_uniform(double S0, int n, double K, XF X) {
     if (!(S0 > S_first)) return X(0);
     if (!(S0 < S_last)) return X(n - 1);
     double dS = grid_point(1, n, K) - grid_point(0, n, K);
-    int j = (int)(S0 / dS);
-    if (j > n - 2) j = n - 2;
-    while (j > 0 && grid_point(j, n, K) > S0) --j;
-    while (j < n - 2 && grid_point(j + 1, n, K) <= S0) ++j;
+    if (!(dS > 0) || !(dS < 1.79e308)) return nan("");     // K = inf / NaN / <= 0: no grid to interpolate on (and no index to search)
+    const double jf = S0 / dS;
+    int j = (jf >= (double)(n - 2)) ? n - 2 : (jf > 0 ? (int)jf : 0);
+    // the uniform-grid guess is off by at most one cell (rounding of i * step): bounded corrections, never a scan
+    for (int c = 0; c < 2 && j > 0 && grid_point(j, n, K) > S0; ++c) --j;
+    for (int c = 0; c < 2 && j < n - 2 && grid_point(j + 1, n, K) <= S0; ++c) ++j;
     double xj = X(j), xj1 = X(j + 1);
     double sj = grid_point(j, n, K), sj1 = grid_point(j + 1, n, K);
     double slope = (xj1 - xj) / (sj1 - sj);

@@ -1003,3 +1003,50 @@ def test_stress_corners_against_live_reference(kernel):
         cfg = AloConfig("A", kw["n"], kw["l"], kw["m"], kw["iter_tol"], kw["max_iters"], kernel=kernel)
         return _np(batch.price_batch(*a, cfg=cfg, B0=B0))
     _stress_checks(price, "stress kernel %d" % kernel)
+
+
+@pytest.mark.timeout(180)
+def test_garbage_inputs_terminate():
+    """NaN / inf / zero / negative parameters in every position: every kernel family returns (NaN or finite output, never an
+    exception, never a hang - all loops are bounded by max_iters, the Newton cap, or the countdown guard), and the well-formed
+    options in the same batch are unaffected."""
+    good = dict(r=0.04, q=0.01, sigma=0.2, K=100.0, T=3.0, S=80.0)
+    bad_values = [float("nan"), float("inf"), -float("inf"), 0.0, -1.0, 1e-320, 1e300]
+    rows = [dict(good)]
+    for k in good:
+        for v in bad_values:
+            d = dict(good)
+            d[k] = v
+            rows.append(d)
+    rows.append(dict(good))
+    a = [np.array([d[k] for d in rows]) for k in ("r", "q", "sigma", "K", "T", "S")]
+    N = len(rows)
+    for put in (1, 0):
+        ip = np.full(N, put, dtype=np.uint8)
+        ref = None
+        for cfgk in (dict(wl.C2_CFG), dict(wl.C2_CFG, kernel=1), dict(wl.C2_CFG, solver="B", max_iters=50), dict(wl.C3_CFG, max_iters=50),
+                     dict(wl.C2_CFG, use_derivative=True), dict(solver="B", n=10, l=20, m=40, iter_tol=1e-5, max_iters=30, use_derivative=True)):
+            out = _np(batch.price_batch(*a, ip, cfg=AloConfig(**cfgk)))
+            assert out["price"].shape == (N,) and (out["iters"] <= cfgk["max_iters"]).all()
+            nan_by_construction = cfgk.get("solver") == "B" and cfgk.get("use_derivative")      # SURVEY App. B#7
+            assert nan_by_construction or np.isfinite(out["price"][0]), cfgk
+            assert np.array_equal(out["price"][:1], out["price"][-1:], equal_nan=True), cfgk   # clean options untouched by their neighbours
+            if cfgk == wl.C2_CFG:
+                ref = out["price"][0]
+        assert abs(ref - (21.1354864713 if put else 7.9)) < (1e-4 if put else 5.0)      # testA.py case at l = 32, m = 64
+        g = batch.greeks_batch(*a, ip, cfg=AloConfig(**wl.C2_CFG))
+        assert np.isfinite(g["delta"][0].item())
+        P = batch.ladder_batch(a[0], a[1], a[2], a[4], a[5], ip, np.array([50.0, 100.0, 150.0]), cfg=AloConfig(**wl.C2_CFG))
+        assert P.shape == (N, 3) and torch.isfinite(P[0]).all()
+        E = batch.european_batch(a[4], a[5], a[0], a[1], a[2], a[3], ip)
+        Q, _ = batch.qd_price_batch(a[4], a[5], a[0], a[1], a[2], a[3], ip)
+        Bs, _ = batch.bjerksund_stensland_batch(a[5], a[0], a[1], a[2], a[3], a[4])
+        assert torch.isfinite(E[0]) and torch.isfinite(Q[0]) and Bs.shape == (N,)
+    for mode in (0, 1, 2):
+        p = batch.cn_put_batch(a[0], a[1], a[2], a[3], a[4], a[5], n_space=64, max_dt=0.05, mode=mode, max_iter=20)
+        assert p.shape == (N,) and torch.isfinite(p[0]) and p[0] == p[-1]
+    four = lambda v: np.full(4, v)      # noqa: E731
+    p = batch.cn_put_batch(four(0.04), four(0.01), four(0.2), four(100.0), four(3.0), four(80.0), n_space=64,
+                           max_dt=np.array([0.0, -1.0, float("nan"), 1e-300]), mode=2)
+    assert p.shape == (4,)
+    torch.cuda.synchronize()
