@@ -168,7 +168,8 @@ def price_batch(r, q, sigma, K, T, S, is_put, t=None, cfg: AloConfig = AloConfig
         # workspace: QD seeds (when no B0 tensor takes them) + the kernels' invariant-table scratch
         c = cfg.c(_lib.FLAG_WS_SCRATCH)
         nb = ctypes.c_size_t()
-        check(lib.faop_workspace_bytes(ctypes.byref(c), N, ctypes.byref(nb)), "faop_workspace_bytes")
+        seeds_elsewhere = B0_in is not None or B0_out is not None       # then the workspace holds the scratch only
+        check(lib.faop_workspace_bytes(ctypes.byref(c), 0 if seeds_elsewhere else N, ctypes.byref(nb)), "faop_workspace_bytes")
         ws = torch.empty(max(nb.value, 256), dtype=torch.uint8, device=dev)
         ierr = torch.empty((N, cfg.max_iters), dtype=torch.float64, device=dev) if want_iter_errs else None
         check(lib.faop_alo_price_batch(ctypes.byref(c), N, _ptr(r), _ptr(q), _ptr(sigma), _ptr(K), _ptr(T), _ptr(tt),

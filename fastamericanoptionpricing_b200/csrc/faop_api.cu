@@ -199,7 +199,8 @@ int faop_alo_price_batch(const faop_cfg* cfg, int64_t N, const double* r, const 
     if (rc) return rc;
     double* scratch = nullptr;
     if (workspace && N > 0 && (cfg->flags & FAOP_FLAG_WS_SCRATCH) && alo_clen_scratch_bytes(*cfg)) {
-        const size_t seed_bytes = sizeof(double) * (size_t)N * (size_t)(cfg->n_colloc + 1);
+        // layout: [seeds, only when they live in the workspace][scratch]
+        const size_t seed_bytes = (B0_in || B0_out) ? 0 : sizeof(double) * (size_t)N * (size_t)(cfg->n_colloc + 1);
         scratch = (double*)((char*)workspace + ((seed_bytes + 255) & ~(size_t)255));
     }
     return price_batch_impl(cfg, N, r, q, sigma, K, T, t, S, is_put, tables_dev, B0_in, price, european, B, B0_out, iters, err,

@@ -97,8 +97,9 @@ int faop_workspace_bytes(const faop_cfg* cfg, int64_t N, size_t* bytes);
  *   B, B0_out nullable: N x (n+1) row-major, node i at tau_i = T (1+cos(i pi/n))^2/4, last node tau=0
  *   iters, err nullable: realised iteration count and final ||B_old-B_new||_2 per option
  *   iter_errs nullable: N x max_iters, the per-iteration errors of self.iter_records (:130), NaN padded
- *   workspace  faop_workspace_bytes(cfg, N) bytes of device memory; may be NULL when B0_in or B0_out is given (the seeds
- *            then live there) at the price of the FAOP_FLAG_WS_SCRATCH speed-up                                  */
+ *   workspace  faop_workspace_bytes(cfg, N) bytes of device memory, laid out [QD seeds][scratch].  When B0_in or B0_out is
+ *            given the seeds live there instead and the scratch starts at offset 0: faop_workspace_bytes(cfg, 0) bytes are
+ *            enough then, and NULL is allowed at the price of the FAOP_FLAG_WS_SCRATCH speed-up                   */
 int faop_alo_price_batch(const faop_cfg* cfg, int64_t N,
                          const double* r, const double* q, const double* sigma, const double* K,
                          const double* T, const double* t, const double* S, const uint8_t* is_put,

@@ -899,7 +899,11 @@ def test_no_out_of_bounds_writes():
         g = dict(price=_Guarded(8 * N), eur=_Guarded(8 * N), B=_Guarded(8 * N * nn), B0=_Guarded(8 * N * nn), it=_Guarded(4 * N),
                  err=_Guarded(8 * N), ierr=_Guarded(8 * N * cfg.max_iters), ws=_Guarded(nb.value))
         tab = batch.tables_for(cfg, torch.device("cuda", torch.cuda.current_device()))
+        nb0 = ctypes.c_size_t()
+        assert lib.faop_workspace_bytes(ctypes.byref(c), 0, ctypes.byref(nb0)) == 0 and nb0.value <= nb.value
         for use_ws_for_seeds in (False, True):
+            # seeds in B0_out: the workspace holds the scratch only and faop_workspace_bytes(cfg, 0) bytes are enough
+            g["ws"] = _Guarded(nb.value if use_ws_for_seeds else max(nb0.value, 8))
             rc = lib.faop_alo_price_batch(ctypes.byref(c), N, P(d[0]), P(d[1]), P(d[2]), P(d[3]), P(d[4]), None, P(d[5]), P(put),
                                           P(tab), None, g["price"].ptr, g["eur"].ptr, g["B"].ptr,
                                           None if use_ws_for_seeds else g["B0"].ptr, g["it"].ptr, g["err"].ptr,
