@@ -57,6 +57,8 @@ _SIGNATURES = {
     "faop_ctx_create": (ctypes.c_int, [ctypes.c_int, _P(c_vp)]),
     "faop_ctx_destroy": (ctypes.c_int, [c_vp]),
     "faop_alo_price_batch_host": (ctypes.c_int, [c_vp, _P(FaopCfg), c_i64] + [c_vp] * 19),
+    "faop_alo_ladder_batch_host": (ctypes.c_int, [c_vp, _P(FaopCfg), c_i64] + [c_vp] * 6 + [c_i32] + [c_vp] * 7),
+    "faop_cn_put_countdown_batch_host": (ctypes.c_int, [c_vp, c_i64, c_i32, c_i32] + [c_vp] * 9),
     "faop_dev_math_batch": (ctypes.c_int, [c_i32, c_i64, c_vp, c_vp, c_vp]),
     "faop_measure_point_mix_peak": (ctypes.c_int, [ctypes.c_int, _P(c_dbl), _P(c_dbl), c_vp]),
     "faop_measure_fp64_peak": (ctypes.c_int, [ctypes.c_int, _P(c_dbl), _P(c_dbl), c_vp]),

@@ -660,4 +660,88 @@ int faop_alo_price_batch_host(faop_ctx* c, const faop_cfg* cfg, int64_t N, const
     return 0;
 }
 
+static int ctx_arena(faop_ctx* c, size_t need) {
+    if (need > c->dev_bytes) {
+        if (c->dev) { cudaFree(c->dev); c->dev = nullptr; c->dev_bytes = 0; }
+        FAOP_CUDA_OK(cudaMalloc(&c->dev, need));
+        c->dev_bytes = need;
+    }
+    return 0;
+}
+
+// Host-buffer form of faop_alo_ladder_batch: G scenarios x nK strikes, host arrays in, price[G * nK] (and iters) out.
+int faop_alo_ladder_batch_host(faop_ctx* c, const faop_cfg* cfg, int64_t G, const double* r, const double* q,
+                               const double* sigma, const double* T, const double* S, const uint8_t* is_put, int32_t nK,
+                               const double* K, const double* y_l, const double* w_l, const double* y_m, const double* w_m,
+                               double* price, int32_t* iters) {
+    if (!c) return FAOP_EINVAL;
+    int rc = check_cfg(cfg);
+    if (rc) return rc;
+    if (G < 0 || nK < 0) return FAOP_EINVAL;
+    if (G == 0 || nK == 0) return 0;
+    if (!r || !q || !sigma || !T || !S || !is_put || !K || !price || !y_l || !w_l || !y_m || !w_m) return FAOP_EINVAL;
+    double Kmin = K[0], Kmax = K[0];
+    for (int32_t k = 1; k < nK; ++k) { Kmin = K[k] < Kmin ? K[k] : Kmin; Kmax = K[k] > Kmax ? K[k] : Kmax; }
+    FAOP_CUDA_OK(cudaSetDevice(c->device));
+    rc = ctx_tables(c, cfg, y_l, w_l, y_m, w_m);
+    if (rc) return rc;
+    size_t wsb = 0;
+    rc = faop_alo_ladder_workspace_bytes(cfg, G, &wsb);
+    if (rc) return rc;
+    const size_t vec = ((size_t)G * sizeof(double) + 255) & ~(size_t)255, kb = ((size_t)nK * sizeof(double) + 255) & ~(size_t)255;
+    const size_t outb = ((size_t)G * nK * sizeof(double) + 255) & ~(size_t)255;
+    rc = ctx_arena(c, 6 * vec + kb + 2 * outb + wsb);
+    if (rc) return rc;
+    char* p = (char*)c->dev;
+    auto take = [&](size_t b) { char* q_ = p; p += b; return q_; };
+    double* d_r = (double*)take(vec); double* d_q = (double*)take(vec); double* d_s = (double*)take(vec);
+    double* d_T = (double*)take(vec); double* d_S = (double*)take(vec); uint8_t* d_put = (uint8_t*)take(vec);
+    double* d_K = (double*)take(kb); double* d_price = (double*)take(outb); int32_t* d_it = (int32_t*)take(outb);
+    void* d_ws = take(wsb);
+    cudaStream_t st = c->stream;
+    const size_t vb = (size_t)G * sizeof(double);
+    FAOP_CUDA_OK(cudaMemcpyAsync(d_r, r, vb, cudaMemcpyHostToDevice, st));
+    FAOP_CUDA_OK(cudaMemcpyAsync(d_q, q, vb, cudaMemcpyHostToDevice, st));
+    FAOP_CUDA_OK(cudaMemcpyAsync(d_s, sigma, vb, cudaMemcpyHostToDevice, st));
+    FAOP_CUDA_OK(cudaMemcpyAsync(d_T, T, vb, cudaMemcpyHostToDevice, st));
+    FAOP_CUDA_OK(cudaMemcpyAsync(d_S, S, vb, cudaMemcpyHostToDevice, st));
+    FAOP_CUDA_OK(cudaMemcpyAsync(d_put, is_put, (size_t)G, cudaMemcpyHostToDevice, st));
+    FAOP_CUDA_OK(cudaMemcpyAsync(d_K, K, (size_t)nK * sizeof(double), cudaMemcpyHostToDevice, st));
+    rc = faop_alo_ladder_batch(cfg, G, d_r, d_q, d_s, d_T, d_S, d_put, nK, d_K, Kmin, Kmax, c->tables_dev, d_price,
+                               iters ? d_it : nullptr, d_ws, wsb, st);
+    if (rc) return rc;
+    FAOP_CUDA_OK(cudaMemcpyAsync(price, d_price, (size_t)G * nK * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (iters) FAOP_CUDA_OK(cudaMemcpyAsync(iters, d_it, (size_t)G * nK * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    FAOP_CUDA_OK(cudaStreamSynchronize(st));
+    return 0;
+}
+
+// Host-buffer form of faop_cn_put_countdown_batch (modes 0 and 2; the SOR mode's N x 6 n_space scratch is the caller's business).
+int faop_cn_put_countdown_batch_host(faop_ctx* c, int64_t N, int32_t n_space, int32_t mode, const double* r, const double* q,
+                                     const double* sigma, const double* K, const double* T, const double* S0,
+                                     const double* max_dt, double* price, double* X_out) {
+    if (!c || N < 0 || (mode != 0 && mode != 2)) return FAOP_EINVAL;
+    if (N == 0) return 0;
+    if (!r || !q || !sigma || !K || !T || !S0 || !max_dt || !price) return FAOP_EINVAL;
+    FAOP_CUDA_OK(cudaSetDevice(c->device));
+    const size_t vec = ((size_t)N * sizeof(double) + 255) & ~(size_t)255;
+    const size_t xb = X_out ? (((size_t)N * n_space * sizeof(double) + 255) & ~(size_t)255) : 0;
+    int rc = ctx_arena(c, 8 * vec + xb);
+    if (rc) return rc;
+    double* d = (double*)c->dev;
+    const size_t st_ = vec / sizeof(double);
+    const double* src[7] = {r, q, sigma, K, T, S0, max_dt};
+    cudaStream_t st = c->stream;
+    for (int a = 0; a < 7; ++a) FAOP_CUDA_OK(cudaMemcpyAsync(d + a * st_, src[a], (size_t)N * sizeof(double), cudaMemcpyHostToDevice, st));
+    double* d_price = d + 7 * st_;
+    double* d_X = X_out ? d + 8 * st_ : nullptr;
+    rc = faop_cn_put_countdown_batch(N, n_space, mode, d, d + st_, d + 2 * st_, d + 3 * st_, d + 4 * st_, d + 5 * st_, d + 6 * st_, 1.2,
+                                     1e-5, 0, d_price, d_X, nullptr, st);
+    if (rc) return rc;
+    FAOP_CUDA_OK(cudaMemcpyAsync(price, d_price, (size_t)N * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (X_out) FAOP_CUDA_OK(cudaMemcpyAsync(X_out, d_X, (size_t)N * n_space * sizeof(double), cudaMemcpyDeviceToHost, st));
+    FAOP_CUDA_OK(cudaStreamSynchronize(st));
+    return 0;
+}
+
 }  // extern "C"

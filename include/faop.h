@@ -266,6 +266,17 @@ int faop_alo_price_batch_host(faop_ctx* ctx, const faop_cfg* cfg, int64_t N,
                               const double* B0_in, double* price, double* european, double* B,
                               double* B0_out, int32_t* iters, double* err);
 
+/* faop_alo_ladder_batch and faop_cn_put_countdown_batch (modes 0 and 2) with HOST arrays through the same context. */
+int faop_alo_ladder_batch_host(faop_ctx* ctx, const faop_cfg* cfg, int64_t G,
+                               const double* r, const double* q, const double* sigma, const double* T, const double* S,
+                               const uint8_t* is_put, int32_t nK, const double* K,
+                               const double* y_l, const double* w_l, const double* y_m, const double* w_m,
+                               double* price /* G x nK */, int32_t* iters /* nullable */);
+int faop_cn_put_countdown_batch_host(faop_ctx* ctx, int64_t N, int32_t n_space, int32_t mode,
+                                     const double* r, const double* q, const double* sigma, const double* K,
+                                     const double* T, const double* S0, const double* max_dt,
+                                     double* price, double* X_out /* nullable, N x n_space */);
+
 /* Diagnostics */
 int faop_version(void);
 /* Kernels launched by this library in this process since load (for bench.py's gpu_launches). */

@@ -33,6 +33,29 @@ int main(void) {
               B[12] != 100.0;
     for (int i = 1; i < N; ++i)          /* American put: decreasing in the spot, above European and intrinsic-ish */
         if (!(price[i] < price[i - 1]) || !(price[i] >= eur[i])) bad = 1;
+    /* strike ladder through the host entry point: scenario 0 = the testA option (its K = 100 rung must reproduce price[0]) */
+    {
+        double lr[2] = {0.04, 0.03}, lq[2] = {0.01, 0.05}, ls[2] = {0.2, 0.3}, lT[2] = {3.0, 1.0}, lS[2] = {80.0, 100.0};
+        unsigned char lput[2] = {1, 0};
+        double Kl[5] = {60, 80, 100, 120, 140}, lp[10];
+        int lit[10];
+        rc = faop_alo_ladder_batch_host(ctx, &cfg, 2, lr, lq, ls, lT, lS, lput, 5, Kl, yl, wl, ym, wm, lp, lit);
+        if (rc) { printf("faop_alo_ladder_batch_host failed: %d\n", rc); return 5; }
+        printf("ladder: put K=100 %.12f (%d sweeps), call rungs %.6f %.6f %.6f %.6f %.6f\n", lp[2], lit[2], lp[5], lp[6], lp[7], lp[8], lp[9]);
+        if (fabs(lp[2] - price[0]) > 1e-9 || lit[2] != iters[0]) bad = 1;
+        for (int k = 1; k < 5; ++k)
+            if (!(lp[k] > lp[k - 1]) || !(lp[5 + k] < lp[5 + k - 1])) bad = 1;      /* puts rise, calls fall with the strike */
+    }
+    /* Crank-Nicolson through the host entry point: the anchor of the reference's __main__ (CrankNicolsonOptionSolver.py:110-128:
+     * r = q = .04, sigma = .2, K = 100, T = 3, S0 = 80, N = 200, max_dt = 1/12, default mode without projection) */
+    {
+        double cr[1] = {0.04}, cq[1] = {0.04}, cs[1] = {0.2}, cK[1] = {100}, cT[1] = {3.0}, cS[1] = {80.0}, cdt[1] = {1.0 / 12.0}, cp[1];
+        static double X[200];
+        rc = faop_cn_put_countdown_batch_host(ctx, 1, 200, 0, cr, cq, cs, cK, cT, cS, cdt, cp, X);
+        if (rc) { printf("faop_cn_put_countdown_batch_host failed: %d\n", rc); return 6; }
+        printf("crank-nicolson: %.12f (X[0] = %.6f)\n", cp[0], X[0]);
+        if (fabs(cp[0] - 22.01470571289995) > 1e-10) bad = 1;
+    }
     faop_ctx_destroy(ctx);
     printf(bad ? "MISMATCH\n" : "ok\n");
     return bad;
