@@ -336,34 +336,57 @@ def greeks_batch(r, q, sigma, K, T, S, is_put, t=None, cfg: AloConfig = AloConfi
         return out
 
 
+def _iv_answer(sig, lo, hi, flo, fhi, side):
+    """The bracket end with the smaller price residual (both ends have been priced); NaN where the target was not bracketed."""
+    best = torch.where(flo.abs() <= fhi.abs(), lo, hi)
+    return torch.where(side >= 0, best, sig)
+
+
 def implied_vol_batch(target, r, q, K, T, S, is_put, cfg: AloConfig = AloConfig(), sigma_lo=0.05, sigma_hi=3.0, iters=48,
-                      tol=1e-12, check_every=4, device=None):
+                      tol=1e-9, f_tol=1e-9, check_every=2, device=None):
     """Implied volatility of American prices: per option the root of price_batch(sigma) - target in [sigma_lo, sigma_hi]
-    by a bracketed Illinois search (bisection when the secant stalls) whose state lives on the device (faop_iv_update_batch); every trial is one full batch
-    solve.  Stops after `iters` trials or when every bracket is narrower than tol (checked every `check_every` trials).
-    Targets outside [price(sigma_lo), price(sigma_hi)] give NaN.  Returns (sigma, trials)."""
+    by a bracketed Illinois search (bisection when the secant stalls) whose state lives on the device
+    (faop_iv_update_batch); every trial is one batch solve of the options still searching.  An option is finished when its
+    bracket is narrower than tol or the price residual at one end of it is below f_tol; finished options leave the batch
+    (checked every `check_every` trials), so a few slow ones do not keep a million converged ones re-solving.  Stops after
+    `iters` trials at the latest.  Targets outside [price(sigma_lo), price(sigma_hi)] give NaN.
+    Returns (sigma, trials) with trials = the number of batch solves of the longest-searching option."""
     lib = _lib.load()
     dev, N, (target, r, q, K, T, S) = _common([target, r, q, K, T, S], device)
     with torch.cuda.device(dev):
         ip = _u8(is_put, dev, N)
-        lo = torch.full((N,), float(sigma_lo), dtype=torch.float64, device=dev)
-        hi = torch.full((N,), float(sigma_hi), dtype=torch.float64, device=dev)
-        flo = torch.full((N,), float("nan"), dtype=torch.float64, device=dev)
-        fhi = torch.full((N,), float("nan"), dtype=torch.float64, device=dev)
-        side = torch.full((N,), -2, dtype=torch.int32, device=dev)
+        result = torch.full((N,), float("nan"), dtype=torch.float64, device=dev)
+        idx = torch.arange(N, device=dev)
+        cur = [target, r, q, K, T, S, ip]
+        n = N
+        lo = torch.full((n,), float(sigma_lo), dtype=torch.float64, device=dev)
+        hi = torch.full((n,), float(sigma_hi), dtype=torch.float64, device=dev)
+        flo = torch.full((n,), float("nan"), dtype=torch.float64, device=dev)
+        fhi = torch.full((n,), float("nan"), dtype=torch.float64, device=dev)
+        side = torch.full((n,), -2, dtype=torch.int32, device=dev)
         sig = lo.clone()
         trials = 0
         for it in range(int(iters) + 2):
+            tg, r_, q_, K_, T_, S_, ip_ = cur
             ok = torch.isfinite(sig)
-            p = price_batch(r, q, torch.where(ok, sig, lo), K, T, S, ip, cfg=cfg, want_boundary=False)["price"]
+            p = price_batch(r_, q_, torch.where(ok, sig, lo), K_, T_, S_, ip_, cfg=cfg, want_boundary=False)["price"]
             trials += 1
-            check(lib.faop_iv_update_batch(N, _ptr(target), _ptr(p), _ptr(sig), _ptr(lo), _ptr(hi), _ptr(flo), _ptr(fhi),
+            check(lib.faop_iv_update_batch(n, _ptr(tg), _ptr(p), _ptr(sig), _ptr(lo), _ptr(hi), _ptr(flo), _ptr(fhi),
                                            _ptr(side), _stream(dev)), "faop_iv_update_batch")
             if it >= 2 and (it - 2) % check_every == check_every - 1:
-                live = side >= 0
-                if not bool(((hi - lo)[live] > tol).any()):
+                live = (side >= 0) & ((hi - lo) > tol) & (torch.minimum(flo.abs(), fhi.abs()) > f_tol)
+                n_live = int(live.sum().item())
+                if n_live == 0:
                     break
-        return sig, trials
+                if n_live <= n // 2:          # compact: the finished options keep their answer, the rest go on alone
+                    result[idx] = _iv_answer(sig, lo, hi, flo, fhi, side)
+                    keep = live.nonzero(as_tuple=True)[0]
+                    idx = idx[keep]
+                    cur = [x[keep].contiguous() for x in cur]
+                    lo, hi, flo, fhi, side, sig = (x[keep].contiguous() for x in (lo, hi, flo, fhi, side, sig))
+                    n = n_live
+        result[idx] = _iv_answer(sig, lo, hi, flo, fhi, side)
+        return result, trials
 
 
 def ladder_batch(r, q, sigma, T, S, is_put, K, cfg: AloConfig = AloConfig(), want_iters=False, device=None, out=None):
