@@ -32,8 +32,7 @@ class CNOptionSolver:
         self.err = 0
         self.iter = 0
 
-    def solve(self, S0):
-        """reference :27-34: returns np.interp(S0, S, X) of the final grid; self.S / self.X hold the grid"""
+    def _run(self, S0):
         if self.Smax != 3 * self.K:
             raise NotImplementedError("the CUDA kernel fixes Smax = 3 K as the reference constructor does")
         mode = _batch.CN_MODE_PROJECTED if self.USE_PROJECTED_THOMAS else (_batch.CN_MODE_SOR if self.USE_PSOR else _batch.CN_MODE_DIRECT)
@@ -42,3 +41,28 @@ class CNOptionSolver:
         self.S = np.linspace(0, self.Smax, self.N)
         self.X = X.cpu().numpy()[0]
         return np.float64(price.item())
+
+    def solve(self, S0):
+        """reference :27-34: returns np.interp(S0, S, X) of the final grid; self.S / self.X hold the grid.  (Upstream prints
+        t / err / iters after every time step, :45; the whole countdown is one kernel here and nothing is printed.)"""
+        return self._run(S0)
+
+    def setInitialCondition(self):
+        """reference :47-52: the grid and the payoff (host arrays; the kernel builds its own copy of both)"""
+        self.S = np.linspace(0, self.Smax, self.N)
+        self.X = np.maximum(self.K - self.S, 0)
+
+    def solvePDE(self):
+        """reference :36-45: the whole countdown from the payoff — the state the reference has right after setInitialCondition(),
+        which is the only state its own solve() ever starts from; fills self.X"""
+        self._run(self.K)
+
+    def applyConstraint(self):
+        """reference :106-107"""
+        self.X = np.maximum(self.X, self.K - self.S)
+
+    def _per_step(self, *a, **k):
+        raise NotImplementedError("setCoeff / solveLinearSystem / solvePSOR are single time steps on the reference's dense N x N "
+                                  "matrix; here the matrix never exists and all steps run inside one kernel (faop_cn_put_countdown_batch)")
+
+    setCoeff = solveLinearSystem = solvePSOR = _per_step

@@ -31,3 +31,18 @@ class FastAmericanOptionSolverA(FastAmericanOptionSolver):
     def K3_integrand(self, tau, B_tau, u, B_u):
         """reference :37-44 (host scalar helper)"""
         return np.exp(self.r * u) / (self.sigma * np.sqrt(tau - u)) * self.PDF_dminus(tau - u, B_tau / B_u)
+
+    def Nprime_integrand(self, tau, B_tau, u, B_u):
+        """reference :55-63 (host scalar helper; the pdf is even, so the put and call branches coincide)"""
+        tau = max(1e-10, tau)
+        s_ = tau - u
+        z = B_tau / B_u
+        return np.exp(self.r * u) * self.dminus(s_, z) / (B_tau * self.sigma * self.sigma * s_) * self.PDF_dminus(s_, z)
+
+    def Dprime_integrand(self, tau, B_tau, u, B_u):
+        """reference :76-83 (host scalar helper)"""
+        tau = max(1e-10, tau)
+        s_ = tau - u
+        z = B_tau / B_u
+        sv = self.sigma * np.sqrt(s_)
+        return np.exp(self.q * u) * self.PDF_dplus(s_, z) / (sv * B_tau) * (1 - self.dplus(s_, z) / sv)

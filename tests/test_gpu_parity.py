@@ -1054,3 +1054,35 @@ def test_garbage_inputs_terminate():
                            max_dt=np.array([0.0, -1.0, float("nan"), 1e-300]), mode=2)
     assert p.shape == (4,)
     torch.cuda.synchronize()
+
+
+def test_dropin_secondary_methods():
+    """Methods of the reference classes that its own scripts rarely touch but a drop-in must still answer: the derivative
+    integrands (A.py:55-83, B.py:59-75), QDplus.compute_miscellaneous and its pieces (QD.py:90-218), CNOptionSolver's
+    setInitialCondition / solvePDE / applyConstraint (CN.py:36-52, 106-107)."""
+    from fastamericanoptionpricing_b200.FastAmericanOptionSolverA import FastAmericanOptionSolverA, qd
+    from fastamericanoptionpricing_b200.FastAmericanOptionSolverB import FastAmericanOptionSolverB
+    from fastamericanoptionpricing_b200.CrankNicolsonOptionSolver import CNOptionSolver
+    from oracle import alo_oracle as o
+    for cls in (FastAmericanOptionSolverA, FastAmericanOptionSolverB):
+        for ot in (qd.OptionType.Put, qd.OptionType.Call):
+            s = cls(0.04, 0.01, 0.2, 100, 3, ot)
+            s.DEBUG = False
+            v = [s.Nprime_integrand(1.5, 80.0, 0.4, 85.0), s.Dprime_integrand(1.5, 80.0, 0.4, 85.0)]
+            assert all(np.isfinite(v)) and v[0] != 0 and v[1] != 0
+    # QD+ internals: compute_miscellaneous -> price pieces consistent with QDplus.price on the device
+    q = qd.QDplus(0.04, 0.02, 0.25, 100.0, qd.OptionType.Put)
+    q.compute_miscellaneous(0.75, 93.0)
+    assert abs(q.v_p - 11.130889999414507) <= 1e-11 and abs(q.v_c - 1.8370779650429843) <= 1e-10 and abs(q.v_b + 5.249805960975274) <= 1e-10
+    assert abs(q.v_qQD + 6.403484382807304) <= 1e-13
+    # Crank-Nicolson pieces
+    c = CNOptionSolver(0.04, 0.04, 0.2, 100, 3.0)
+    c.setInitialCondition()
+    assert len(c.S) == 200 and c.S[-1] == 300.0 and c.X[0] == 100.0 and c.X[-1] == 0.0
+    c.solvePDE()
+    ref = o.cn_solve(0.04, 0.04, 0.2, 100.0, 3.0, 80.0, N=200, max_dt=1 / 12.0, use_psor=False)
+    assert abs(np.interp(80.0, c.S, c.X) - 22.01470571289995) <= 1e-10 and np.isfinite(ref[0] if isinstance(ref, tuple) else ref)
+    c.applyConstraint()
+    assert (c.X >= np.maximum(100.0 - c.S, 0) - 1e-15).all()
+    with pytest.raises(NotImplementedError):
+        c.setCoeff(0.1)

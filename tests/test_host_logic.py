@@ -44,3 +44,26 @@ def test_stress_workload_blocks():
     assert np.all(b["q"][1800:2000] == 0) and np.all(b["r"][2000:2100] == 1e-6)
     b2 = wl.stress_batch(3000)
     assert all(np.array_equal(b[k], b2[k]) for k in b)       # seeded
+
+
+def test_qdplus_internal_helpers_match_reference_values():
+    """QDplus.q_QD / q_QD_dot / c0 / c / b / dlogSdh / h / M / N (reference QDplusAmericanOptionSolver.py:127-218, same signatures).
+    Expected values: QDplus(0.04, 0.02, 0.25, 100, type).compute_miscellaneous(0.75, 93.0) run on the unmodified reference
+    (numpy 2.3.5 / scipy 1.18.1); the European legs it needs are fed in as the reference computed them (they run on the device)."""
+    from fastamericanoptionpricing_b200 import QDplusAmericanOptionSolver as m
+    exp = {m.OptionType.Put: dict(v_p=11.130889999414507, v_qQD=-6.403484382807304, v_dlogSdh=-98.30766711885849, v_c=1.8370779650429843,
+                                  v_c0=0.19775560768558423, v_b=-5.249805960975274),
+           m.OptionType.Call: dict(v_p=5.7017470276485085, v_qQD=6.763484382807303, v_dlogSdh=-208.32127378593694, v_c=-2.802821633276153,
+                                   v_c0=-10.979745079482687, v_b=5.249805960975274)}
+    for ot, e in exp.items():
+        s = m.QDplus(0.04, 0.02, 0.25, 100.0, ot)
+        tau, S = 0.75, 93.0
+        s.v_d1, s.v_d2, s.v_p, s.v_theta = -0.15765446457194918, -0.3741608155180588, e["v_p"], -3.7341196656609483
+        s.v_N, s.v_M, s.v_h = s.N(), s.M(), s.h(tau)
+        assert (s.v_N, s.v_M) == (0.64, 1.28) and abs(s.v_h - 0.029554466451491845) < 1e-17
+        s.v_qQD, s.v_qQDdot = s.q_QD(tau), s.q_QD_dot()
+        assert abs(s.v_qQDdot - 111.29558010352328) < 1e-12
+        s.v_dlogSdh = s.dlogSdh(tau, S)
+        got = dict(v_qQD=s.v_qQD, v_dlogSdh=s.v_dlogSdh, v_c=s.c(tau, S), v_c0=s.c0(tau, S), v_b=s.b(tau, S))
+        for k, v in got.items():
+            assert abs(v - e[k]) <= 1e-12 * max(1.0, abs(e[k])), (ot, k, v, e[k])
