@@ -23,6 +23,11 @@ class FaopSurface(ctypes.Structure):
                 ("S", c_dbl), ("r", c_dbl), ("q", c_dbl), ("nK", c_i32), ("nT", c_i32), ("nV", c_i32), ("is_put", c_i32)]
 
 
+class FaopCnExtra(ctypes.Structure):
+    """Mirror of `faop_cn_extra` (include/faop.h): CNOptionSolver.Smax per option, a start state, err / iter outputs."""
+    _fields_ = [("Smax", c_vp), ("X_in", c_vp), ("err_out", c_vp), ("iter_out", c_vp)]
+
+
 _P = ctypes.POINTER
 _SIGNATURES = {
     "faop_version": (ctypes.c_int, []),
@@ -52,13 +57,14 @@ _SIGNATURES = {
     "faop_cheb_fit_batch": (ctypes.c_int, [c_i64, c_i32, c_vp, c_vp, c_vp]),
     "faop_cheb_eval_batch": (ctypes.c_int, [c_i64, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp]),
     "faop_cn_workspace_bytes": (ctypes.c_int, [c_i64, c_i32, c_i32, _P(c_sz)]),
-    "faop_cn_put_batch": (ctypes.c_int, [c_i64, c_i32, c_i32] + [c_vp] * 7 + [c_i32, c_dbl, c_dbl, c_i32] + [c_vp] * 4),
-    "faop_cn_put_countdown_batch": (ctypes.c_int, [c_i64, c_i32, c_i32] + [c_vp] * 7 + [c_dbl, c_dbl, c_i32] + [c_vp] * 4),
+    "faop_cn_put_batch": (ctypes.c_int, [c_i64, c_i32, c_i32] + [c_vp] * 7 + [c_i32, c_dbl, c_dbl, c_i32, _P(FaopCnExtra)] + [c_vp] * 4),
+    "faop_cn_put_countdown_batch": (ctypes.c_int, [c_i64, c_i32, c_i32] + [c_vp] * 7 + [c_dbl, c_dbl, c_i32, _P(FaopCnExtra)] + [c_vp] * 4),
+    "faop_cn_rows_batch": (ctypes.c_int, [c_i64, c_i32] + [c_vp] * 12),
     "faop_ctx_create": (ctypes.c_int, [ctypes.c_int, _P(c_vp)]),
     "faop_ctx_destroy": (ctypes.c_int, [c_vp]),
     "faop_alo_price_batch_host": (ctypes.c_int, [c_vp, _P(FaopCfg), c_i64] + [c_vp] * 19),
     "faop_alo_ladder_batch_host": (ctypes.c_int, [c_vp, _P(FaopCfg), c_i64] + [c_vp] * 6 + [c_i32] + [c_vp] * 7),
-    "faop_cn_put_countdown_batch_host": (ctypes.c_int, [c_vp, c_i64, c_i32, c_i32] + [c_vp] * 9),
+    "faop_cn_put_countdown_batch_host": (ctypes.c_int, [c_vp, c_i64, c_i32, c_i32] + [c_vp] * 10),
     "faop_dev_math_batch": (ctypes.c_int, [c_i32, c_i64, c_vp, c_vp, c_vp]),
     "faop_measure_point_mix_peak": (ctypes.c_int, [ctypes.c_int, _P(c_dbl), _P(c_dbl), c_vp]),
     "faop_measure_fp64_peak": (ctypes.c_int, [ctypes.c_int, _P(c_dbl), _P(c_dbl), c_vp]),

@@ -580,12 +580,14 @@ CN_MODE_DIRECT, CN_MODE_SOR, CN_MODE_PROJECTED = 0, 1, 2
 
 
 def cn_put_batch(r, q, sigma, K, T, S0, n_space=200, max_dt=1 / 12.0, mode=CN_MODE_PROJECTED, omega=1.2, tol=1e-5,
-                 max_iter=200, want_grid=False, device=None, schedule=None):
+                 max_iter=200, want_grid=False, device=None, schedule=None, Smax=None, X_in=None, want_state=False):
     """CNOptionSolver(r,q,sigma,K,T).solve(S0) for a batch of American puts (CrankNicolsonOptionSolver.py:27-107).
     mode 0 = the reference default (dense solve, no projection), 1 = the reference's SOR+project loop,
     2 = projected tridiagonal sweep.  Returns price (and the final grid values X, N x n_space).
     The time steps are the reference's float countdown from T in steps of max_dt, run on the device
-    (faop_cn_put_countdown_batch); schedule=(dts [N x steps], n_steps [N]) supplies explicit steps instead."""
+    (faop_cn_put_countdown_batch); schedule=(dts [N x steps], n_steps [N]) supplies explicit steps instead.
+    Smax = the CNOptionSolver.Smax attribute per option (:12,48; default 3K); X_in = N x n_space state to start from
+    instead of the payoff; want_state adds (err, iter), the attributes of the last solvePSOR (:103-104), to the result."""
     lib = _lib.load()
     dev, N, (r, q, sigma, K, T, S0) = _common([r, q, sigma, K, T, S0], device)
     with torch.cuda.device(dev):
@@ -594,21 +596,48 @@ def cn_put_batch(r, q, sigma, K, T, S0, n_space=200, max_dt=1 / 12.0, mode=CN_MO
         nb = ctypes.c_size_t()
         check(lib.faop_cn_workspace_bytes(N, n_space, mode, ctypes.byref(nb)), "faop_cn_workspace_bytes")
         ws = torch.empty(max(nb.value, 1), dtype=torch.uint8, device=dev)
+        sm = None if Smax is None else _f64(Smax, dev, N)
+        if sm is not None and sm.numel() != N:
+            raise ValueError("Smax must be a scalar or have one entry per option")
+        xin = None
+        if X_in is not None:
+            xin = torch.as_tensor(X_in, dtype=torch.float64).to(dev).reshape(N, -1).contiguous()
+            if xin.shape[1] != n_space:
+                raise ValueError("X_in must be N x n_space")
+        err = torch.empty(N, dtype=torch.float64, device=dev) if want_state else None
+        it = torch.empty(N, dtype=torch.int32, device=dev) if want_state else None
+        ex = _lib.FaopCnExtra(_ptr(sm), _ptr(xin), _ptr(err), _ptr(it))
         if schedule is None:
             mdt = _f64(np.broadcast_to(np.asarray(max_dt.cpu() if isinstance(max_dt, torch.Tensor) else max_dt, dtype=np.float64),
                                        (N,)).copy(), dev, N)
             check(lib.faop_cn_put_countdown_batch(N, n_space, mode, _ptr(r), _ptr(q), _ptr(sigma), _ptr(K), _ptr(T), _ptr(S0),
-                                                  _ptr(mdt), float(omega), float(tol), int(max_iter), _ptr(price), _ptr(X),
-                                                  _ptr(ws), _stream(dev)), "faop_cn_put_countdown_batch")
+                                                  _ptr(mdt), float(omega), float(tol), int(max_iter), ctypes.byref(ex),
+                                                  _ptr(price), _ptr(X), _ptr(ws), _stream(dev)), "faop_cn_put_countdown_batch")
         else:
             dts, ns = schedule
             dts = np.ascontiguousarray(dts, dtype=np.float64)
             dts_d = torch.from_numpy(dts).to(dev)
             ns_d = torch.from_numpy(np.ascontiguousarray(ns, dtype=np.int32)).to(dev)
             check(lib.faop_cn_put_batch(N, n_space, mode, _ptr(r), _ptr(q), _ptr(sigma), _ptr(K), _ptr(S0), _ptr(dts_d),
-                                        _ptr(ns_d), dts.shape[1], float(omega), float(tol), int(max_iter), _ptr(price), _ptr(X),
-                                        _ptr(ws), _stream(dev)), "faop_cn_put_batch")
-        return (price, X) if want_grid else price
+                                        _ptr(ns_d), dts.shape[1], float(omega), float(tol), int(max_iter), ctypes.byref(ex),
+                                        _ptr(price), _ptr(X), _ptr(ws), _stream(dev)), "faop_cn_put_batch")
+        out = (price, X) if want_grid else price
+        return (out, err, it) if want_state else out
+
+
+def cn_rows_batch(r, q, sigma, K, dt, X, Smax=None, device=None):
+    """CNOptionSolver.setCoeff(dt) (CrankNicolsonOptionSolver.py:55-79) as data: the three diagonals lo, di, up and the
+    right-hand side b (each N x n_space) of one time step from the state X (faop_cn_rows_batch)."""
+    lib = _lib.load()
+    dev, N, (r, q, sigma, K, dt) = _common([r, q, sigma, K, dt], device)
+    with torch.cuda.device(dev):
+        X = torch.as_tensor(X, dtype=torch.float64).to(dev).reshape(N, -1).contiguous()
+        n_space = X.shape[1]
+        sm = None if Smax is None else _f64(Smax, dev, N)
+        out = [torch.empty((N, n_space), dtype=torch.float64, device=dev) for _ in range(4)]
+        check(lib.faop_cn_rows_batch(N, n_space, _ptr(r), _ptr(q), _ptr(sigma), _ptr(K), _ptr(sm), _ptr(dt), _ptr(X),
+                                     *[_ptr(o) for o in out], _stream(dev)), "faop_cn_rows_batch")
+        return out
 
 
 def launch_count():

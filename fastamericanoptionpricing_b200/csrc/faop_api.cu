@@ -719,24 +719,26 @@ int faop_alo_ladder_batch_host(faop_ctx* c, const faop_cfg* cfg, int64_t G, cons
 // Host-buffer form of faop_cn_put_countdown_batch (modes 0 and 2; the SOR mode's N x 6 n_space scratch is the caller's business).
 int faop_cn_put_countdown_batch_host(faop_ctx* c, int64_t N, int32_t n_space, int32_t mode, const double* r, const double* q,
                                      const double* sigma, const double* K, const double* T, const double* S0,
-                                     const double* max_dt, double* price, double* X_out) {
+                                     const double* max_dt, const double* Smax, double* price, double* X_out) {
     if (!c || N < 0 || (mode != 0 && mode != 2)) return FAOP_EINVAL;
     if (N == 0) return 0;
     if (!r || !q || !sigma || !K || !T || !S0 || !max_dt || !price) return FAOP_EINVAL;
     FAOP_CUDA_OK(cudaSetDevice(c->device));
     const size_t vec = ((size_t)N * sizeof(double) + 255) & ~(size_t)255;
     const size_t xb = X_out ? (((size_t)N * n_space * sizeof(double) + 255) & ~(size_t)255) : 0;
-    int rc = ctx_arena(c, 8 * vec + xb);
+    int rc = ctx_arena(c, 9 * vec + xb);
     if (rc) return rc;
     double* d = (double*)c->dev;
     const size_t st_ = vec / sizeof(double);
-    const double* src[7] = {r, q, sigma, K, T, S0, max_dt};
+    const double* src[8] = {r, q, sigma, K, T, S0, max_dt, Smax};
     cudaStream_t st = c->stream;
-    for (int a = 0; a < 7; ++a) FAOP_CUDA_OK(cudaMemcpyAsync(d + a * st_, src[a], (size_t)N * sizeof(double), cudaMemcpyHostToDevice, st));
-    double* d_price = d + 7 * st_;
-    double* d_X = X_out ? d + 8 * st_ : nullptr;
+    for (int a = 0; a < 8; ++a)
+        if (src[a]) FAOP_CUDA_OK(cudaMemcpyAsync(d + a * st_, src[a], (size_t)N * sizeof(double), cudaMemcpyHostToDevice, st));
+    double* d_price = d + 8 * st_;
+    double* d_X = X_out ? d + 9 * st_ : nullptr;
+    faop_cn_extra ex = {Smax ? d + 7 * st_ : nullptr, nullptr, nullptr, nullptr};
     rc = faop_cn_put_countdown_batch(N, n_space, mode, d, d + st_, d + 2 * st_, d + 3 * st_, d + 4 * st_, d + 5 * st_, d + 6 * st_, 1.2,
-                                     1e-5, 0, d_price, d_X, nullptr, st);
+                                     1e-5, 0, &ex, d_price, d_X, nullptr, st);
     if (rc) return rc;
     FAOP_CUDA_OK(cudaMemcpyAsync(price, d_price, (size_t)N * sizeof(double), cudaMemcpyDeviceToHost, st));
     if (X_out) FAOP_CUDA_OK(cudaMemcpyAsync(X_out, d_X, (size_t)N * n_space * sizeof(double), cudaMemcpyDeviceToHost, st));

@@ -32,21 +32,27 @@ struct CnArgs {
     const double *r, *q, *sigma, *K, *S0, *dts;
     const int32_t* n_steps;
     const double *T, *max_dt;   // countdown mode (dts == nullptr): the kernel runs solvePDE's own float countdown
+    const double *Smax;         // nullable: CNOptionSolver.Smax per option (:12, used at :48); nullptr = 3K
+    const double *X_in;         // nullable: N x n_space state to start from instead of the payoff (single-step calls)
     double omega, tol;
     double *price, *X_out, *ws;
+    double *err_out;            // nullable: CNOptionSolver.err / .iter after the last solvePSOR (:103-104), mode 1
+    int32_t *iter_out;
 };
 
-__device__ __forceinline__ double grid_point(int i, int n, double K) {
-    // np.linspace(0, 3K, N): i * step + 0, last point == 3K exactly
-    if (i == n - 1) return 3.0 * K;
-    double step = (3.0 * K - 0.0) / (double)(n - 1);
+__device__ __forceinline__ double cn_smax(const CnArgs& a, int64_t opt) { return a.Smax ? a.Smax[opt] : 3.0 * a.K[opt]; }
+
+__device__ __forceinline__ double grid_point(int i, int n, double Smax) {
+    // np.linspace(0, Smax, N) (:48): i * step + 0, last point == Smax exactly
+    if (i == n - 1) return Smax;
+    double step = (Smax - 0.0) / (double)(n - 1);
     return (double)i * step + 0.0;
 }
 
 // np.interp(S0, S, X) on the uniform grid; X read through a functor
 template <typename XF>
-__device__ double interp_uniform(double S0, int n, double K, XF X) {
-    double S_first = 0.0, S_last = 3.0 * K;
+__device__ double interp_uniform(double S0, int n, double K, XF X) {   // K here = Smax, the upper end of the grid
+    double S_first = 0.0, S_last = K;
     if (!(S0 > S_first)) return X(0);
     if (!(S0 < S_last)) return X(n - 1);
     double dS = grid_point(1, n, K) - grid_point(0, n, K);
@@ -105,7 +111,7 @@ __global__ void __launch_bounds__(kCnThreads, (NPT <= 8 ? 2 : 1)) cn_scan_kernel
     double* s_R = s_Q + NS;
     double* s_O = s_R + NS;
     double* s_seq = s_O + NS;            // natural (node) order scratch (c' recurrence, fallback back-substitution, output)
-    double* s_G = s_seq + NS;            // payoff K - S_i, [j * T + t]
+    double* s_G = s_seq + NS + 2;        // payoff K - S_i, [j * T + t]   (s_seq holds up to NS + 1 nodes: n - 1 <= NS)
     double* s_eL = s_G + NS;             // [warp] X of the warp's first slot / last slot (halo of the neighbours)
     double* s_eR = s_eL + kCnWarps;
     double* s_fwA = s_eR + kCnWarps;     // forward warp totals: A (per dt) and B (per step)
@@ -126,16 +132,17 @@ __global__ void __launch_bounds__(kCnThreads, (NPT <= 8 ? 2 : 1)) cn_scan_kernel
         double X[NPT], Q[NPT], R[NPT];
         double xlast;                    // X_{N-1}
         {
-            const double K = a.K[opt];
+            const double K = a.K[opt], Sm = cn_smax(a, opt);
+            const double* xin = a.X_in ? a.X_in + opt * n : nullptr;
 #pragma unroll
             for (int j = 0; j < NPT; ++j) {
                 const int i = t * NPT + j - off;
-                const double S = grid_point(i >= 0 ? i : 0, n, K);
+                const double S = grid_point(i >= 0 ? i : 0, n, Sm);
                 s_G[j * kCnThreads + t] = (i >= 0) ? K - S : kNegBig;     // payoff (applyConstraint, :106-107); own slots only
-                X[j] = (i >= 0) ? fmax(K - S, 0.0) : 0.0;                  // setInitialCondition, :48-52
+                X[j] = (i >= 0) ? (xin ? xin[i] : fmax(K - S, 0.0)) : 0.0;   // setInitialCondition, :48-52
                 Q[j] = R[j] = 0.0;
             }
-            xlast = fmax(K - grid_point(n - 1, n, K), 0.0);
+            xlast = xin ? xin[n - 1] : fmax(K - grid_point(n - 1, n, Sm), 0.0);
         }
         double Af[5], Ab[5], excA = 0.0, nxtA = 0.0, cR3 = 0.0, cR4 = 0.0, cinv = 0.0;
         // time stepping: either the caller's schedule, or solvePDE's countdown `while t > 0: dt = min(t, max_dt); ...; t -= dt`
@@ -160,9 +167,9 @@ __global__ void __launch_bounds__(kCnThreads, (NPT <= 8 ? 2 : 1)) cn_scan_kernel
             if (dt != dt_prev) {
                 // ---- coefficients for this dt (setCoeff, :55-79) and the c' recurrence of the elimination
                 __syncthreads();   // nobody still reads the previous dt's rows or s_seq
-                const double r = a.r[opt], q = a.q[opt], sg = a.sigma[opt], K = a.K[opt];   // cold path: not kept in registers
+                const double r = a.r[opt], q = a.q[opt], sg = a.sigma[opt], K = cn_smax(a, opt);   // cold path: not kept in registers; K = grid end here
                 const double dS = grid_point(1, n, K) - grid_point(0, n, K);
-                if (t == 0) s_misc[1] = K - 3.0 * K;            // payoff at the last node (floor of X_{N-1})
+                if (t == 0) s_misc[1] = a.K[opt] - K;           // payoff at the last node (floor of X_{N-1})
 #pragma unroll
                 for (int j = 0; j < NPT; ++j) {
                     const int i = t * NPT + j - off;
@@ -369,14 +376,14 @@ __global__ void __launch_bounds__(kCnThreads, (NPT <= 8 ? 2 : 1)) cn_scan_kernel
                 }
                 __syncthreads();
                 if (t == 0) {
-                    const double K = a.K[opt];
+                    const double K = a.K[opt], Sm = cn_smax(a, opt);
                     const double p2 = s_clo[2];
                     const double p3 = fma(cR3, p2, s_clo[1]);
                     const double p4 = fma(cR4, p3, s_clo[0]);
                     double x = dmax((p4 - 4.0 * p3 + 5.0 * p2) * cinv, s_misc[1]);
                     s_seq[n - 1] = x;
                     for (int i = n - 2; i >= 0; --i) {
-                        x = dmax(fma(s_R[at_node(i)], x, s_seq[i]), K - grid_point(i, n, K));
+                        x = dmax(fma(s_R[at_node(i)], x, s_seq[i]), K - grid_point(i, n, Sm));
                         s_seq[i] = x;
                     }
                 }
@@ -406,7 +413,7 @@ __global__ void __launch_bounds__(kCnThreads, (NPT <= 8 ? 2 : 1)) cn_scan_kernel
             if (a.X_out) a.X_out[opt * n + n - 1] = xlast;
         }
         __syncthreads();
-        if (t == 0) a.price[opt] = interp_uniform(a.S0[opt], n, a.K[opt], [&](int i) { return s_seq[i]; });
+        if (t == 0) a.price[opt] = interp_uniform(a.S0[opt], n, cn_smax(a, opt), [&](int i) { return s_seq[i]; });
     }
 }
 
@@ -423,10 +430,12 @@ __global__ void __launch_bounds__(64) cn_sor_kernel(CnArgs a) {
     double* di = lo + (int64_t)n * ld;
     double* up = di + (int64_t)n * ld;
     double* xo = up + (int64_t)n * ld;
-    const double r = a.r[opt], q = a.q[opt], sg = a.sigma[opt], K = a.K[opt];
+    const double r = a.r[opt], q = a.q[opt], sg = a.sigma[opt], K = a.K[opt], Sm = cn_smax(a, opt);
     const double omega = a.omega;
-    for (int i = 0; i < n; ++i) X[i * ld] = fmax(K - grid_point(i, n, K), 0.0);
-    const double dS = grid_point(1, n, K) - grid_point(0, n, K);
+    for (int i = 0; i < n; ++i) X[i * ld] = a.X_in ? a.X_in[opt * n + i] : fmax(K - grid_point(i, n, Sm), 0.0);
+    const double dS = grid_point(1, n, Sm) - grid_point(0, n, Sm);
+    double last_err = 0.0;
+    int last_it = 0;
     const bool sched = a.dts != nullptr;
     const int nsteps = sched ? a.n_steps[opt] : 0;
     double trem = sched ? 0.0 : a.T[opt];
@@ -439,7 +448,7 @@ __global__ void __launch_bounds__(64) cn_sor_kernel(CnArgs a) {
             trem -= dt;
         }
         for (int i = 0; i < n - 1; ++i) {
-            double S = grid_point(i, n, K);
+            double S = grid_point(i, n, Sm);
             double aa = sg * S / dS;
             double alpha = 0.25 * dt * (aa * aa - (r - q) * S / dS);
             double beta = 0.5 * dt * (r + aa * aa);
@@ -469,22 +478,61 @@ __global__ void __launch_bounds__(64) cn_sor_kernel(CnArgs a) {
             for (int jj = 0; jj < 4; ++jj) X[(n - 1) * ld] -= lastc[jj] * X[(n - 4 + jj) * ld] * omega / 2.0;
             double ss = 0.0;
             for (int i = 0; i < n; ++i) {
-                double v = fmax(X[i * ld], K - grid_point(i, n, K));   // applyConstraint on the whole vector
+                double v = fmax(X[i * ld], K - grid_point(i, n, Sm));   // applyConstraint on the whole vector
                 X[i * ld] = v;
                 double dd = xo[i * ld] - v;
                 ss += dd * dd;
             }
             err = sqrt(ss);
         }
+        last_err = err;        // self.err / self.iter, :103-104
+        last_it = it;
     }
+    if (a.err_out) a.err_out[opt] = last_err;
+    if (a.iter_out) a.iter_out[opt] = last_it;
     if (a.X_out) for (int i = 0; i < n; ++i) a.X_out[opt * n + i] = X[i * ld];
-    a.price[opt] = interp_uniform(a.S0[opt], n, K, [&](int i) { return X[i * ld]; });
+    a.price[opt] = interp_uniform(a.S0[opt], n, Sm, [&](int i) { return X[i * ld]; });
+}
+
+// ---------------------------------------------------------------- setCoeff (:55-79) as data: the rows and the right-hand side
+// of ONE time step from a given state, one thread per (option, node).  lo / di / up are the three diagonals (row 0 has only
+// the diagonal; row N-1 is the constant 4-term closure -1, 4, -5, 2 and is reported as lo = -5, di = 2, up = 0, b = 0).
+__global__ void cn_rows_kernel(int64_t N, int n, const double* r, const double* q, const double* sigma, const double* K,
+                               const double* Smax, const double* dt, const double* X, double* lo, double* di, double* up,
+                               double* b) {
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= N * n) return;
+    const int64_t opt = g / n;
+    const int i = (int)(g - opt * n);
+    const double Sm = Smax ? Smax[opt] : 3.0 * K[opt];
+    const double dS = grid_point(1, n, Sm) - grid_point(0, n, Sm);
+    const double* x = X + opt * n;
+    double vlo = 0.0, vdi = 0.0, vup = 0.0, vb = 0.0;
+    if (i == n - 1) {
+        vlo = -5.0; vdi = 2.0;
+    } else {
+        const double S = grid_point(i, n, Sm);
+        const double aa = sigma[opt] * S / dS;
+        const double m = (r[opt] - q[opt]) * S / dS;
+        const double alpha = 0.25 * dt[opt] * (aa * aa - m);
+        const double beta = 0.5 * dt[opt] * (r[opt] + aa * aa);
+        const double gamma = 0.25 * dt[opt] * (aa * aa + m);
+        vdi = 1 + beta;
+        if (i == 0) {
+            vb = x[0] * (1 - beta);
+        } else {
+            vb = alpha * x[i - 1] + (1 - beta) * x[i] + gamma * x[i + 1];
+            vlo = -alpha;
+            vup = -gamma;
+        }
+    }
+    lo[g] = vlo; di[g] = vdi; up[g] = vup; b[g] = vb;
 }
 
 template <int NPT, bool PROJ>
 static int launch_scan(const CnArgs& a, cudaStream_t st) {
     constexpr int NS = kCnThreads * NPT;
-    size_t sm = sizeof(double) * (size_t)(5 * NS + 7 * kCnWarps + kCnWarps * (2 * kCnWarps + 1) + 8);
+    size_t sm = sizeof(double) * (size_t)(5 * NS + 2 + 7 * kCnWarps + kCnWarps * (2 * kCnWarps + 1) + 8);
     FAOP_CUDA_OK(cudaFuncSetAttribute(cn_scan_kernel<NPT, PROJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     int64_t grid = a.N < (int64_t)kSMs * 8 ? a.N : (int64_t)kSMs * 8;
     cn_scan_kernel<NPT, PROJ><<<(unsigned)grid, kCnThreads, sm, st>>>(a);
@@ -515,10 +563,27 @@ int faop_cn_workspace_bytes(int64_t N, int32_t n_space, int32_t mode, size_t* by
     return 0;
 }
 
+static int cn_launch(CnArgs& a, const faop_cn_extra* ex, void* workspace, cudaStream_t st) {
+    a.Smax = ex ? ex->Smax : nullptr;
+    a.X_in = ex ? ex->X_in : nullptr;
+    a.err_out = ex ? ex->err_out : nullptr;
+    a.iter_out = ex ? ex->iter_out : nullptr;
+    a.ws = (double*)workspace;
+    if (a.mode == 1) {
+        cn_sor_kernel<<<(unsigned)((a.N + 63) / 64), 64, 0, st>>>(a);
+        count_launch();
+        return launch_status();
+    }
+    // the direct modes run no SOR loop: err / iter keep the constructor's zeros (:24-25)
+    if (a.err_out) FAOP_CUDA_OK(cudaMemsetAsync(a.err_out, 0, sizeof(double) * (size_t)a.N, st));
+    if (a.iter_out) FAOP_CUDA_OK(cudaMemsetAsync(a.iter_out, 0, sizeof(int32_t) * (size_t)a.N, st));
+    return a.mode == 2 ? launch_scan_npt<true>(a, st) : launch_scan_npt<false>(a, st);
+}
+
 int faop_cn_put_batch(int64_t N, int32_t n_space, int32_t mode, const double* r, const double* q, const double* sigma,
                       const double* K, const double* S0, const double* dts, const int32_t* n_steps, int32_t max_steps,
-                      double omega, double tol, int32_t max_iter, double* price, double* X_out, void* workspace,
-                      void* cuda_stream) {
+                      double omega, double tol, int32_t max_iter, const faop_cn_extra* extra, double* price, double* X_out,
+                      void* workspace, void* cuda_stream) {
     if (N < 0 || n_space < 5 || mode < 0 || mode > 2 || max_steps < 0) return FAOP_EINVAL;
     if (n_space > kCnThreads * 16) return FAOP_ERANGE;
     if (N == 0) return 0;
@@ -528,20 +593,14 @@ int faop_cn_put_batch(int64_t N, int32_t n_space, int32_t mode, const double* r,
     a.N = N; a.n_space = n_space; a.max_steps = max_steps; a.mode = mode; a.max_iter = max_iter;
     a.r = r; a.q = q; a.sigma = sigma; a.K = K; a.S0 = S0; a.dts = dts; a.n_steps = n_steps;
     a.T = nullptr; a.max_dt = nullptr;
-    a.omega = omega; a.tol = tol; a.price = price; a.X_out = X_out; a.ws = (double*)workspace;
-    cudaStream_t st = (cudaStream_t)cuda_stream;
-    if (mode == 1) {
-        cn_sor_kernel<<<(unsigned)((N + 63) / 64), 64, 0, st>>>(a);
-        count_launch();
-        return launch_status();
-    }
-    return mode == 2 ? launch_scan_npt<true>(a, st) : launch_scan_npt<false>(a, st);
+    a.omega = omega; a.tol = tol; a.price = price; a.X_out = X_out;
+    return cn_launch(a, extra, workspace, (cudaStream_t)cuda_stream);
 }
 
 int faop_cn_put_countdown_batch(int64_t N, int32_t n_space, int32_t mode, const double* r, const double* q,
                                 const double* sigma, const double* K, const double* T, const double* S0, const double* max_dt,
-                                double omega, double tol, int32_t max_iter, double* price, double* X_out, void* workspace,
-                                void* cuda_stream) {
+                                double omega, double tol, int32_t max_iter, const faop_cn_extra* extra, double* price,
+                                double* X_out, void* workspace, void* cuda_stream) {
     if (N < 0 || n_space < 5 || mode < 0 || mode > 2) return FAOP_EINVAL;
     if (n_space > kCnThreads * 16) return FAOP_ERANGE;
     if (N == 0) return 0;
@@ -551,14 +610,21 @@ int faop_cn_put_countdown_batch(int64_t N, int32_t n_space, int32_t mode, const 
     a.N = N; a.n_space = n_space; a.max_steps = 0; a.mode = mode; a.max_iter = max_iter;
     a.r = r; a.q = q; a.sigma = sigma; a.K = K; a.S0 = S0; a.dts = nullptr; a.n_steps = nullptr;
     a.T = T; a.max_dt = max_dt;
-    a.omega = omega; a.tol = tol; a.price = price; a.X_out = X_out; a.ws = (double*)workspace;
-    cudaStream_t st = (cudaStream_t)cuda_stream;
-    if (mode == 1) {
-        cn_sor_kernel<<<(unsigned)((N + 63) / 64), 64, 0, st>>>(a);
-        count_launch();
-        return launch_status();
-    }
-    return mode == 2 ? launch_scan_npt<true>(a, st) : launch_scan_npt<false>(a, st);
+    a.omega = omega; a.tol = tol; a.price = price; a.X_out = X_out;
+    return cn_launch(a, extra, workspace, (cudaStream_t)cuda_stream);
+}
+
+int faop_cn_rows_batch(int64_t N, int32_t n_space, const double* r, const double* q, const double* sigma, const double* K,
+                       const double* Smax, const double* dt, const double* X, double* lo, double* di, double* up, double* b,
+                       void* cuda_stream) {
+    if (N < 0 || n_space < 5) return FAOP_EINVAL;
+    if (N == 0) return 0;
+    if (!r || !q || !sigma || !K || !dt || !X || !lo || !di || !up || !b) return FAOP_EINVAL;
+    const int64_t tot = N * n_space;
+    cn_rows_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, (cudaStream_t)cuda_stream>>>(N, n_space, r, q, sigma, K, Smax, dt, X,
+                                                                                      lo, di, up, b);
+    count_launch();
+    return launch_status();
 }
 
 }  // extern "C"

@@ -229,17 +229,27 @@ int faop_cheb_eval_batch(int64_t N, int32_t n, int32_t npts, const double* a, co
                          double* out, void* cuda_stream);
 
 /* ---- Crank-Nicolson (CNOptionSolver, CrankNicolsonOptionSolver.py:5-107), American puts --------
- * One CTA per option; grid S_i = linspace(0, 3K, n_space); the dt schedule of solvePDE's float
- * countdown (:36-45) is built by the caller: dts is N x max_steps, n_steps[i] entries valid.
+ * One CTA per option; grid S_i = linspace(0, Smax, n_space) (:48), Smax = 3K (:12) unless `extra->Smax` says otherwise;
+ * the dt schedule of solvePDE's float countdown (:36-45) is built by the caller: dts is N x max_steps, n_steps[i] entries valid.
  *   mode 0: unprojected direct solve  == the reference default USE_PSOR=False (np.linalg.solve, :81-82)
  *   mode 1: the reference's SOR-sweep-then-project loop (:84-107), operation for operation
  *   mode 2: projected (Brennan-Schwartz) tridiagonal sweep — the throughput mode (not in the reference)
- * X_out nullable: N x n_space final grid values (the reference's self.X).                          */
+ * X_out nullable: N x n_space final grid values (the reference's self.X).
+ * `extra` (nullable, every member nullable) carries the rest of the CNOptionSolver object state: the `Smax` attribute
+ * (:12, consumed at :48) per option; `X_in`, an N x n_space state to start from instead of setInitialCondition's payoff
+ * (what solveLinearSystem / solvePSOR see in self.X when called on their own, :81-104); `err_out` / `iter_out`, the
+ * attributes self.err / self.iter after the last solvePSOR (:103-104; zeros, as the constructor leaves them, in modes 0/2). */
+typedef struct {
+    const double* Smax;
+    const double* X_in;
+    double* err_out;
+    int32_t* iter_out;
+} faop_cn_extra;
 int faop_cn_workspace_bytes(int64_t N, int32_t n_space, int32_t mode, size_t* bytes);
 int faop_cn_put_batch(int64_t N, int32_t n_space, int32_t mode,
                       const double* r, const double* q, const double* sigma, const double* K,
                       const double* S0, const double* dts, const int32_t* n_steps, int32_t max_steps,
-                      double omega, double tol, int32_t max_iter,
+                      double omega, double tol, int32_t max_iter, const faop_cn_extra* extra,
                       double* price, double* X_out, void* workspace, void* cuda_stream);
 
 /* The same solver with the time stepping of CNOptionSolver.solvePDE itself (:36-45): `while t > 0: dt = min(t, max_dt); ...;
@@ -248,8 +258,14 @@ int faop_cn_put_batch(int64_t N, int32_t n_space, int32_t mode,
 int faop_cn_put_countdown_batch(int64_t N, int32_t n_space, int32_t mode,
                                 const double* r, const double* q, const double* sigma, const double* K,
                                 const double* T, const double* S0, const double* max_dt,
-                                double omega, double tol, int32_t max_iter,
+                                double omega, double tol, int32_t max_iter, const faop_cn_extra* extra,
                                 double* price, double* X_out, void* workspace, void* cuda_stream);
+/* CNOptionSolver.setCoeff(dt) (:55-79) as data: the three diagonals and the right-hand side of ONE time step from the state X
+ * (N x n_space each; row n_space-1 is the constant closure -1, 4, -5, 2 | 0, reported as lo = -5, di = 2, up = 0, b = 0).
+ * Smax nullable (3K). */
+int faop_cn_rows_batch(int64_t N, int32_t n_space, const double* r, const double* q, const double* sigma, const double* K,
+                       const double* Smax, const double* dt, const double* X,
+                       double* lo, double* di, double* up, double* b, void* cuda_stream);
 
 /* ---- host-buffer convenience (what a non-torch caller binds) ----------------------------------
  * A context owns a device, a stream, device scratch, pinned staging buffers and the table blobs it
@@ -275,6 +291,7 @@ int faop_alo_ladder_batch_host(faop_ctx* ctx, const faop_cfg* cfg, int64_t G,
 int faop_cn_put_countdown_batch_host(faop_ctx* ctx, int64_t N, int32_t n_space, int32_t mode,
                                      const double* r, const double* q, const double* sigma, const double* K,
                                      const double* T, const double* S0, const double* max_dt,
+                                     const double* Smax /* nullable: 3K */,
                                      double* price, double* X_out /* nullable, N x n_space */);
 
 /* Diagnostics */

@@ -327,13 +327,14 @@ int oracle_european_batch(int64_t N, const double* tau, const double* S, const d
  * mode 1: the reference's SOR-sweep-then-project loop (:84-107) operation for operation
  * mode 2: Brennan-Schwartz projected back-substitution (not in the reference; throughput mode of the CUDA path)
  * dt[] is the host-built schedule of `while t > 0: dt = min(t, max_dt); t -= dt` (:36-45).                          */
-static double cn_one(double r, double q, double sg, double K, double S0, int N, const double* dts, int nsteps,
-                     int mode, double omega, double tol, int max_iter, double* Xout) {
+static double cn_one(double r, double q, double sg, double K, double Smax, double S0, int N, const double* dts, int nsteps,
+                     int mode, double omega, double tol, int max_iter, double* Xout, double* err_out, int* iter_out) {
     double *S = malloc(sizeof(double) * N * 8), *X = S + N, *b = X + N, *lo = b + N, *di = lo + N, *up = di + N, *cp = up + N, *dp = cp + N;
-    /* np.linspace(0, 3K, N): i*step, last point exact */
-    double step = (3 * K - 0.0) / (N - 1);
+    /* np.linspace(0, Smax, N) (:48; Smax = 3K unless the caller changed the attribute, :12): i*step, last point exact */
+    double step = (Smax - 0.0) / (N - 1);
     for (int i = 0; i < N; ++i) S[i] = i * step + 0.0;
-    S[N - 1] = 3 * K;
+    S[N - 1] = Smax;
+    double last_err = 0.0; int last_it = 0;   /* CNOptionSolver.err / .iter after the last solvePSOR (:103-104) */
     for (int i = 0; i < N; ++i) X[i] = fmax(K - S[i], 0.0);
     double dS = S[1] - S[0];
     for (int st = 0; st < nsteps; ++st) {
@@ -365,6 +366,7 @@ static double cn_one(double r, double q, double sg, double K, double S0, int N, 
                 for (int i = 0; i < N; ++i) { X[i] = fmax(X[i], K - S[i]); double d = cp[i] - X[i]; ss += d * d; }
                 err = sqrt(ss);
             }
+            last_err = err; last_it = it;
         } else {
             /* rows 0..N-2 are tridiagonal; forward elimination gives X_i = dp_i - cp_i X_{i+1}.  The 4-term last row
              * (-1, 4, -5, 2 | 0) is closed by writing X_{N-2}, X_{N-3}, X_{N-4} as affine functions of x = X_{N-1}. */
@@ -396,15 +398,20 @@ static double cn_one(double r, double q, double sg, double K, double S0, int N, 
         v = slope * (S0 - S[j]) + X[j];
     }
     if (Xout) memcpy(Xout, X, sizeof(double) * N);
+    if (err_out) *err_out = last_err;
+    if (iter_out) *iter_out = last_it;
     free(S);
     return v;
 }
 
 int oracle_cn_put_batch(int64_t Nopt, int n_space, int mode, const double* r, const double* q, const double* sigma,
-                        const double* K, const double* S0, const double* dts /* Nopt x max_steps */, const int32_t* nsteps,
-                        int max_steps, double omega, double tol, int max_iter, double* price, double* Xout /* nullable */) {
+                        const double* K, const double* Smax /* nullable: 3K */, const double* S0,
+                        const double* dts /* Nopt x max_steps */, const int32_t* nsteps,
+                        int max_steps, double omega, double tol, int max_iter, double* price, double* Xout /* nullable */,
+                        double* err_out /* nullable */, int32_t* iter_out /* nullable */) {
     for (int64_t i = 0; i < Nopt; ++i)
-        price[i] = cn_one(r[i], q[i], sigma[i], K[i], S0[i], n_space, dts + i * max_steps, nsteps[i], mode, omega, tol,
-                          max_iter, Xout ? Xout + i * n_space : NULL);
+        price[i] = cn_one(r[i], q[i], sigma[i], K[i], Smax ? Smax[i] : 3 * K[i], S0[i], n_space, dts + i * max_steps, nsteps[i],
+                          mode, omega, tol, max_iter, Xout ? Xout + i * n_space : NULL, err_out ? err_out + i : NULL,
+                          iter_out ? iter_out + i : NULL);
     return 0;
 }

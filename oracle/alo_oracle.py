@@ -525,7 +525,7 @@ def cn_dt_schedule(T, max_dt):
 
 
 def cn_solve(r, q, sigma, K, T, S0, N=200, max_dt=1 / 12.0, use_psor=False, tol=1e-5, max_iter=200, omega=1.2,
-             projected_thomas=False):
+             projected_thomas=False, Smax=None, state=None):
     """CNOptionSolver.solve, CrankNicolsonOptionSolver.py:27-107, one option (scalars).
 
     use_psor=False : the reference's default dense `np.linalg.solve` per step (NO early-exercise projection, :81-82),
@@ -534,9 +534,11 @@ def cn_solve(r, q, sigma, K, T, S0, N=200, max_dt=1 / 12.0, use_psor=False, tol=
                      including the last-row quirk (leaked index i = N-2, j = N-1 term on itself).
     projected_thomas=True : Brennan-Schwartz projected back-substitution max(., K - S_i) (not in the reference; the
                      CUDA path's throughput mode, cross-checked against spectral prices).
+    Smax: the CNOptionSolver.Smax attribute (:12, consumed at :48), default 3K.  `state`, if a dict, receives err / iter of the
+    last SOR solve (:103-104).
     Returns (price, S grid, X).
     """
-    S = np.linspace(0, 3 * K, N)
+    S = np.linspace(0, 3 * K if Smax is None else Smax, N)
     X = np.maximum(K - S, 0)
     dS = S[1] - S[0]
     payoff = K - S
@@ -574,6 +576,8 @@ def cn_solve(r, q, sigma, K, T, S0, N=200, max_dt=1 / 12.0, use_psor=False, tol=
                     X[N - 1] -= last[j] * X[j] * omega / 2.0
                 X = np.maximum(X, payoff)
                 err = np.linalg.norm(x_old - X)
+            if state is not None:
+                state["err"], state["iter"] = float(err), it
         else:
             # rows 0..N-2 are tridiagonal: forward elimination gives X_i = dp_i - cp_i X_{i+1}; the 4-term last row
             # (-1, 4, -5, 2 | 0) is closed by writing X_{N-2}, X_{N-3}, X_{N-4} as affine functions of x = X_{N-1}

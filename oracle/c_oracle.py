@@ -72,8 +72,10 @@ def european_batch(tau, S, r, q, sigma, K, is_put):
     return out
 
 
-def cn_put_batch(r, q, sigma, K, T, S0, n_space, max_dt, mode, omega=1.2, tol=1e-5, max_iter=200, return_X=False):
-    """mode 0 = unprojected direct solve, 1 = reference SOR+project, 2 = projected Thomas."""
+def cn_put_batch(r, q, sigma, K, T, S0, n_space, max_dt, mode, omega=1.2, tol=1e-5, max_iter=200, return_X=False,
+                 Smax=None, return_state=False):
+    """mode 0 = unprojected direct solve, 1 = reference SOR+project, 2 = projected Thomas.  Smax (default 3K) is the
+    CNOptionSolver.Smax attribute (CrankNicolsonOptionSolver.py:12,48); return_state adds (err, iter) of the last SOR solve."""
     from .alo_oracle import cn_dt_schedule
     r, q, sigma, K, T, S0, max_dt = (_d(np.atleast_1d(a)) for a in np.broadcast_arrays(r, q, sigma, K, T, S0, max_dt))
     N = r.shape[0]
@@ -86,7 +88,13 @@ def cn_put_batch(r, q, sigma, K, T, S0, n_space, max_dt, mode, omega=1.2, tol=1e
         ns[i] = len(s)
     price = np.empty(N)
     X = np.empty((N, n_space)) if return_X else None
+    sm = None if Smax is None else _d(np.broadcast_to(np.asarray(Smax, dtype=np.float64), (N,)).copy())
+    err = np.zeros(N)
+    it = np.zeros(N, dtype=np.int32)
     lib().oracle_cn_put_batch(ctypes.c_int64(N), ctypes.c_int(n_space), ctypes.c_int(mode), _p(r), _p(q), _p(sigma), _p(K),
-                              _p(S0), _p(dts), _p(ns), ctypes.c_int(ms), ctypes.c_double(omega), ctypes.c_double(tol),
-                              ctypes.c_int(max_iter), _p(price), _p(X))
-    return (price, X) if return_X else price
+                              _p(sm), _p(S0), _p(dts), _p(ns), ctypes.c_int(ms), ctypes.c_double(omega), ctypes.c_double(tol),
+                              ctypes.c_int(max_iter), _p(price), _p(X), _p(err), _p(it))
+    out = (price, X) if return_X else price
+    if return_state:
+        return (out, err, it)
+    return out

@@ -357,6 +357,62 @@ def gen_cn(pool):
     print("cn: %d solves; first two %r %r" % (len(jobs), res[0][0], res[1][0]))
 
 
+def _cn_state_one(args):
+    """Non-default Smax (CrankNicolsonOptionSolver.py:12 -> :48), err / iter after a PSOR solve (:103-104), and the per-step
+    surface: setInitialCondition -> setCoeff(dt) (A's three diagonals + closure row, b) -> solveLinearSystem / solvePSOR."""
+    r, q, sig, K, T, S0, N, max_dt, psor, smax_mult, step_dt = args
+    s = refcn.CNOptionSolver(r, q, sig, K, T)
+    s.N = N
+    s.max_dt = max_dt
+    s.USE_PSOR = psor
+    s.Smax = smax_mult * K
+    with contextlib.redirect_stdout(io.StringIO()):
+        p = float(s.solve(S0))
+    X = np.asarray(s.X, dtype=float).flatten()
+    err, it = float(s.err), int(s.iter)
+    # per-step surface on a fresh object
+    u = refcn.CNOptionSolver(r, q, sig, K, T)
+    u.N = N
+    u.Smax = smax_mult * K
+    u.setInitialCondition()
+    u.setCoeff(step_dt)
+    A = np.array(u.A, dtype=float)
+    i = np.arange(N)
+    di = A[i, i].copy()
+    lo = np.zeros(N); lo[1:] = A[i[1:], i[1:] - 1]
+    up = np.zeros(N); up[:-1] = A[i[:-1], i[:-1] + 1]
+    last = A[-1, N - 4:].copy()
+    b = np.array(u.b, dtype=float).flatten()
+    if psor:
+        u.solvePSOR()
+    else:
+        u.solveLinearSystem()
+    X1 = np.asarray(u.X, dtype=float).flatten()
+    # a second step from the new state (the PSOR path keeps a 1-D X; the dense path needs it flattened like solve() never does)
+    return dict(price=p, X=X, err=err, iter=it, di=di, lo=lo, up=up, last=last, b=b, X1=X1, err1=float(u.err), iter1=int(u.iter))
+
+
+def gen_cn_state(pool):
+    g = np.random.default_rng(32)
+    jobs = []
+    base = [(0.04, 0.04, 0.2, 100.0, 3.0, 80.0), (0.04, 0.01, 0.2, 100.0, 3.0, 80.0)]
+    for _ in range(4):
+        base.append((g.uniform(.01, .08), g.uniform(0, .06), g.uniform(.15, .5), g.uniform(60, 140), g.uniform(.25, 3), g.uniform(70, 130)))
+    for (r, q, sig, K, T, S0) in base:
+        for psor in (False, True):
+            for mult in (3.0, 4.5, 2.0, 7.25):
+                jobs.append((r, q, sig, K, T, S0, 160, 1 / 12.0, psor, mult, 0.05))
+    res = pool.map(_cn_state_one, jobs, chunksize=1)
+    cols = list(zip(*jobs))
+    out = dict(in_r=np.array(cols[0]), in_q=np.array(cols[1]), in_sigma=np.array(cols[2]), in_K=np.array(cols[3]),
+               in_T=np.array(cols[4]), in_S0=np.array(cols[5]), N=np.array(cols[6]), max_dt=np.array(cols[7]),
+               use_psor=np.array(cols[8]), smax_mult=np.array(cols[9]), step_dt=np.array(cols[10]), versions=np.array(VERSIONS))
+    for k in res[0]:
+        out[k] = np.array([r_[k] for r_ in res])
+    np.savez(os.path.join(OUT, "ref_cn_state.npz"), **out)
+    print("cn_state: %d solves; price[0..3] %r" % (len(jobs), [r_["price"] for r_ in res[:4]]))
+
+
 def _stage_one(args):
     solver, r, q, sig, K, T, is_put, n, l, m = args
     cls = refA.FastAmericanOptionSolverA if solver == "A" else refB.FastAmericanOptionSolverB
@@ -482,7 +538,7 @@ def gen_stress(pool):
     print("stress: %d options, nan %d, err>=1e-2 %d" % (len(idx), np.isnan(out["price"]).sum(), (out["err"] >= 1e-2).sum()))
 
 
-GENS = dict(c1=gen_c1, european=gen_european, cheb=gen_cheb, qd=gen_qd, stage=gen_stage, misc=gen_misc, cn=gen_cn,
+GENS = dict(c1=gen_c1, european=gen_european, cheb=gen_cheb, qd=gen_qd, stage=gen_stage, misc=gen_misc, cn=gen_cn, cn_state=gen_cn_state,
             c3=gen_c3, c2=gen_c2, bs=gen_bs, c5=gen_c5, stress=gen_stress)
 
 

@@ -51,7 +51,7 @@ int main(void) {
     {
         double cr[1] = {0.04}, cq[1] = {0.04}, cs[1] = {0.2}, cK[1] = {100}, cT[1] = {3.0}, cS[1] = {80.0}, cdt[1] = {1.0 / 12.0}, cp[1];
         static double X[200];
-        rc = faop_cn_put_countdown_batch_host(ctx, 1, 200, 0, cr, cq, cs, cK, cT, cS, cdt, cp, X);
+        rc = faop_cn_put_countdown_batch_host(ctx, 1, 200, 0, cr, cq, cs, cK, cT, cS, cdt, NULL /* Smax = 3K */, cp, X);
         if (rc) { printf("faop_cn_put_countdown_batch_host failed: %d\n", rc); return 6; }
         printf("crank-nicolson: %.12f (X[0] = %.6f)\n", cp[0], X[0]);
         if (fabs(cp[0] - 22.01470571289995) > 1e-10) bad = 1;

@@ -150,9 +150,9 @@ def test_bad_arguments_are_codes_not_crashes():
     assert lib.faop_alo_surface_dedup_batch(ctypes.byref(cd), ctypes.byref(s), N(0), N(10), z, z, z, z, 0, z) == -2
     assert lib.faop_alo_greeks_known_boundary_batch(ctypes.byref(c), N(4), *([z] * 10), 1e-3, 1e-4, z, z, z, z, z) == -1
     assert lib.faop_iv_update_batch(N(4), *([z] * 9)) == -1 and lib.faop_iv_update_batch(N(0), *([z] * 9)) == 0
-    assert lib.faop_cn_put_countdown_batch(N(4), 200, 3, *([z] * 7), 1.2, 1e-5, 10, z, z, z, z) == -1       # mode out of range
-    assert lib.faop_cn_put_countdown_batch(N(4), 5000, 2, *([z] * 7), 1.2, 1e-5, 10, z, z, z, z) == -2      # grid beyond the compiled limit
-    assert lib.faop_cn_put_countdown_batch(N(4), 200, 2, *([z] * 7), 1.2, 1e-5, 10, z, z, z, z) == -1
+    assert lib.faop_cn_put_countdown_batch(N(4), 200, 3, *([z] * 7), 1.2, 1e-5, 10, None, z, z, z, z) == -1       # mode out of range
+    assert lib.faop_cn_put_countdown_batch(N(4), 5000, 2, *([z] * 7), 1.2, 1e-5, 10, None, z, z, z, z) == -2      # grid beyond the compiled limit
+    assert lib.faop_cn_put_countdown_batch(N(4), 200, 2, *([z] * 7), 1.2, 1e-5, 10, None, z, z, z, z) == -1
     assert lib.faop_bjerksund_stensland_batch(N(2), *([z] * 12)) == -1 and lib.faop_bs_phi_batch(N(2), *([z] * 10)) == -1
     # the scratch flag only changes the size for configurations that use it
     plain, flagged = ctypes.c_size_t(), ctypes.c_size_t()

@@ -206,6 +206,29 @@ def test_cn_oracle():
     assert abs(p2[0] - 23.209084798867803) <= 5e-4
 
 
+def test_cn_oracle_smax_and_state():
+    """CNOptionSolver.Smax (CrankNicolsonOptionSolver.py:12,48) != 3K and the err / iter attributes of the last solvePSOR
+    (:103-104), against the live reference (ref_cn_state.npz)."""
+    c = load_golden("ref_cn_state.npz")
+    for i in range(len(c["price"])):
+        a = [float(c["in_" + k][i]) for k in ("r", "q", "sigma", "K", "T", "S0")]
+        N, max_dt, psor = int(c["N"][i]), float(c["max_dt"][i]), bool(c["use_psor"][i])
+        Smax = float(c["smax_mult"][i]) * a[3]
+        (p, X), err, it = co.cn_put_batch(*a, n_space=N, max_dt=max_dt, mode=1 if psor else 0, return_X=True, Smax=Smax,
+                                          return_state=True)
+        tol = 1e-9 if psor else 1e-10
+        assert abs(p[0] - c["price"][i]) <= tol, (i, p[0], c["price"][i])
+        assert np.max(np.abs(X[0] - c["X"][i])) <= 10 * tol
+        if psor:
+            assert it[0] == c["iter"][i] and abs(err[0] - c["err"][i]) <= 1e-9
+        if i in (5, 30):    # the pure-Python restatement (slow): one PSOR row with Smax = 4.5 K, one with 2 K
+            assert psor
+            st = {}
+            p, S, X = o.cn_solve(*a, N=N, max_dt=max_dt, use_psor=psor, Smax=Smax, state=st)
+            assert abs(p - c["price"][i]) <= tol and S[-1] == Smax
+            assert st["iter"] == c["iter"][i] and abs(st["err"] - c["err"][i]) <= 1e-9
+
+
 def test_bjerksund_stensland_golden():
     """BksdStld (BjerksundStenslandSolver.py:4-43) run with the globals it reads (own K/T, foreign K/T, and the
     module's own __main__ numbers, SURVEY 4: call 4.342423011041589, put 23.062019527897103)."""

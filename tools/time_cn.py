@@ -18,7 +18,7 @@ for mode in (2, 0):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     rc = lib.faop_cn_put_countdown_batch(n, 2000, mode, *[ctypes.c_void_p(x.data_ptr()) for x in a], ctypes.c_void_p(mdt.data_ptr()),
-                                         1.2, 1e-5, 200, ctypes.c_void_p(price.data_ptr()), None, None,
+                                         1.2, 1e-5, 200, None, ctypes.c_void_p(price.data_ptr()), None, None,
                                          ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
