@@ -87,11 +87,24 @@ class FastAmericanOptionSolver(ABC):
         return _batch.AloConfig(**kw)
 
     def _opt(self):
-        return (self.r, self.q, self.sigma, self.K, self.T)
+        """option scalars for the kernels that only see the collocation domain [0, tau_max] (reference :28, :185, :223)"""
+        return (self.r, self.q, self.sigma, self.K, self.tau_max)
 
-    def _check_domain(self):
-        if self.tau_min != 0 or self.tau_max != self.T:
-            raise NotImplementedError("the CUDA path fixes the collocation domain to [0, T] (the reference defaults)")
+    def _tau_max(self):
+        return None if self.tau_max == self.T else float(self.tau_max)
+
+    def _nan_solve(self):
+        """tau_min != 0 (reference :29): upstream maps u to z = sqrt(4 (u - tau_min)/(tau_max - tau_min)) - 1 (:235-237), which
+        meets u < tau_min at the node tau_n = tau_min (and tau_n < 0 when tau_min < 0), so the first sweep produces NaN, the loop
+        `while iter_err > tol` stops on it and solve() returns NaN with num_iters = 1 [measured on the reference].  Nothing is
+        launched for that; the same state is reported (shared_B all NaN — upstream keeps a few finite nodes when tau_min < 0)."""
+        self.set_collocation_points()
+        self.set_initial_guess()
+        self.shared_B = [np.float64(np.nan)] * (self.collocation_num + 1)
+        self.num_iters = 1
+        self.error = np.float64(np.nan)
+        self.iter_records.append((1, float("nan")))
+        return np.float64(np.nan)
 
     # ------------------------------------------------------------------ the solve
     def solve(self, t, s0):
@@ -99,14 +112,15 @@ class FastAmericanOptionSolver(ABC):
         if self.q == 0 and self.option_type == qd.OptionType.Call:
             self.european_price = europ.EuropeanOption.european_call_value(self.T - t, s0, self.r, self.q, self.sigma, self.K)
             return self.european_price
-        self._check_domain()
+        if self.tau_min != 0:
+            return self._nan_solve()
         self.set_collocation_points()
         self.debug("step 1. checking collocation points ...")
         self.debug("collocation point = {0}".format(self.shared_tau))
         self.debug("step 3. checking numerical integration ...")
         self.test_numerical_integration()
         out = _batch.price_batch(self.r, self.q, self.sigma, self.K, self.T, s0, self._is_put(), t=t, cfg=self._cfg(),
-                                 want_iter_errs=True)
+                                 want_iter_errs=True, tau_max=self._tau_max())
         self._store(out)
         self.debug("step 6. checking exercise boundary ...")
         self.debug("exercise boundary = {0}".format(self.shared_B))
@@ -128,12 +142,14 @@ class FastAmericanOptionSolver(ABC):
 
     def compute_exercise_boundary(self):
         """reference :105-133 (seed + damped Jacobi loop); fills shared_B0, shared_B, error, num_iters, iter_records"""
-        self._check_domain()
+        if self.tau_min != 0:
+            self._nan_solve()
+            return
         if len(self.shared_tau) != self.collocation_num + 1:
             self.set_collocation_points()
         self.debug("step 5. starting iteration ...")
         out = _batch.price_batch(self.r, self.q, self.sigma, self.K, self.T, self.K, self._is_put(), cfg=self._cfg(),
-                                 want_iter_errs=True)
+                                 want_iter_errs=True, tau_max=self._tau_max())
         eur = self.european_price
         self._store(out)
         self.european_price = eur
@@ -154,9 +170,11 @@ class FastAmericanOptionSolver(ABC):
 
     def american_value_with_known_boundary(self, tau, s0, r, q, sigma, K):
         """reference :92-103: European value + the m-point price integral on self.shared_B"""
-        self._check_domain()
+        if self.tau_min != 0:
+            return np.float64(np.nan)
         p, e = _batch.price_known_boundary_batch(np.asarray(self.shared_B, dtype=np.float64), self.r, self.q, self.sigma,
-                                                 self.K, self.T, s0, self._is_put(), t=self.T - tau, cfg=self._cfg())
+                                                 self.K, self.T, s0, self._is_put(), t=self.T - tau, cfg=self._cfg(),
+                                                 tau_max=self._tau_max())
         v12 = p.item() - e.item()
         if (r, q, sigma, K) == (self.r, self.q, self.sigma, self.K):
             v = e.item()
@@ -183,11 +201,13 @@ class FastAmericanOptionSolver(ABC):
 
     def compute_integration_terms(self, tau, num_points):
         """reference :167-195: Gauss-Legendre nodes, u_k and the interpolated boundary B(u_k) (always recomputed)"""
-        self._check_domain()
         self.y, self.w = legendre.leggauss(num_points)
         self.shared_u = tau - tau * np.square(1 + self.y) / 4.0
+        if self.tau_min != 0:
+            self.shared_Bu = np.full(len(self.y), np.nan)
+            return
         Bu = _batch.interp_boundary_batch(np.asarray(self.shared_B, dtype=np.float64), self.shared_u[None, :], self.r, self.q,
-                                          self.K, self.T, self._is_put(), cfg=self._cfg())
+                                          self.K, self.tau_max, self._is_put(), cfg=self._cfg())
         self.shared_Bu = Bu.cpu().numpy()[0]
 
     def set_collocation_points(self):

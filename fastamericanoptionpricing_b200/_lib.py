@@ -7,6 +7,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libfaop.so")
 
 FLAG_WS_SCRATCH = 1
+FLAG_SEED_NEWTON = 2
 c_i32, c_i64, c_dbl, c_vp, c_sz = ctypes.c_int32, ctypes.c_int64, ctypes.c_double, ctypes.c_void_p, ctypes.c_size_t
 
 
@@ -14,7 +15,7 @@ class FaopCfg(ctypes.Structure):
     """Mirror of `faop_cfg` (include/faop.h)."""
     _fields_ = [("solver", c_i32), ("use_derivative", c_i32), ("n_colloc", c_i32), ("n_quad", c_i32),
                 ("n_price_quad", c_i32), ("max_iters", c_i32), ("iter_tol", c_dbl), ("eta", c_dbl),
-                ("kernel", c_i32), ("flags", c_i32)]
+                ("kernel", c_i32), ("flags", c_i32), ("tau_max", c_vp)]
 
 
 class FaopSurface(ctypes.Structure):

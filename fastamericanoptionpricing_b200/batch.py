@@ -32,10 +32,18 @@ class AloConfig:
     # opt-in accuracy modes named in the north-star but absent from the reference (they change results):
     rule_l: str = "gauss-legendre"   # or "tanh-sinh": rule of the boundary-equation integrals (l points)
     rule_m: str = "gauss-legendre"   # or "tanh-sinh": rule of the price integral (m points)
+    # root finder of the QD seed: "hybr" = the reference's (MINPACK hybrd as scipy.optimize.root drives it,
+    # QDplusAmericanOptionSolver.py:73), "newton" = safeguarded Newton, the faster opt-in (FAOP_FLAG_SEED_NEWTON)
+    seed: str = "hybr"
 
-    def c(self, flags=0):
+    def c(self, flags=0, tau_max=None):
+        if self.seed not in ("hybr", "newton"):
+            raise ValueError("seed must be 'hybr' or 'newton'")
+        if self.seed == "newton":
+            flags |= _lib.FLAG_SEED_NEWTON
         return FaopCfg(0 if self.solver == "A" else 1, int(bool(self.use_derivative)), int(self.n), int(self.l),
-                       int(self.m), int(self.max_iters), float(self.iter_tol), float(self.eta), int(self.kernel), int(flags))
+                       int(self.m), int(self.max_iters), float(self.iter_tol), float(self.eta), int(self.kernel), int(flags),
+                       None if tau_max is None else tau_max.data_ptr())
 
 
 def _device(device=None):
@@ -111,6 +119,8 @@ def quadrature_rule(name, num):
         return gauss_legendre(num)
     if name == "tanh-sinh":
         return tanh_sinh(num)
+    if name.startswith("tanh-sinh:"):          # "tanh-sinh:2.0" = truncation t_max = 2.0 (nodes stay 2e-5 away from +-1)
+        return tanh_sinh(num, t_max=float(name.split(":", 1)[1]))
     raise ValueError("unknown quadrature rule %r" % (name,))
 
 
@@ -134,12 +144,13 @@ def tables_for(cfg: AloConfig, dev):
 
 
 def price_batch(r, q, sigma, K, T, S, is_put, t=None, cfg: AloConfig = AloConfig(), B0=None,
-                want_boundary=True, want_iter_errs=False, device=None):
+                want_boundary=True, want_iter_errs=False, device=None, tau_max=None):
     """FastAmericanOptionSolver{A,B}.solve(t, s0) for a batch (FastAmericanOptionSolverBase.py:49-76).
 
     Returns dict(price, european, iters, err[, B, B0, tau]); B/B0/tau are N x (n+1) (node i at
     tau_i = T (1 + cos(i pi/n))^2 / 4).  B0 (optional, N x (n+1)) borrows a seed boundary instead of the QD seed.
     want_iter_errs adds iter_errs (N x max_iters, the errors of the reference's iter_records, NaN padded).
+    tau_max (optional, per option): the reference's tau_max attribute (Base.py:28), the end of the collocation domain; default T.
     """
     lib = _lib.load()
     dev = _device(device)
@@ -149,7 +160,8 @@ def price_batch(r, q, sigma, K, T, S, is_put, t=None, cfg: AloConfig = AloConfig
         q, sigma, K, T, S = (_f64(x, dev, N) for x in (q, sigma, K, T, S))
         is_put = _u8(is_put, dev, N)
         tt = None if t is None else _f64(t, dev, N)
-        for x in (q, sigma, K, T, S, is_put):
+        tmax = None if tau_max is None else _f64(tau_max, dev, N)
+        for x in (q, sigma, K, T, S, is_put) + (() if tmax is None else (tmax,)):
             if x.numel() != N:
                 raise ValueError("all option arrays must have the same length")
         nn = cfg.n + 1
@@ -166,7 +178,7 @@ def price_batch(r, q, sigma, K, T, S, is_put, t=None, cfg: AloConfig = AloConfig
         elif want_boundary:
             B0_out = torch.empty((N, nn), dtype=torch.float64, device=dev)
         # workspace: QD seeds (when no B0 tensor takes them) + the kernels' invariant-table scratch
-        c = cfg.c(_lib.FLAG_WS_SCRATCH)
+        c = cfg.c(_lib.FLAG_WS_SCRATCH, tau_max=tmax)
         nb = ctypes.c_size_t()
         seeds_elsewhere = B0_in is not None or B0_out is not None       # then the workspace holds the scratch only
         check(lib.faop_workspace_bytes(ctypes.byref(c), 0 if seeds_elsewhere else N, ctypes.byref(nb)), "faop_workspace_bytes")
@@ -182,7 +194,7 @@ def price_batch(r, q, sigma, K, T, S, is_put, t=None, cfg: AloConfig = AloConfig
         if want_boundary:
             out["B"] = B
             out["B0"] = B0_in if B0_in is not None else B0_out
-            out["tau"] = collocation_tau(T, cfg.n)
+            out["tau"] = collocation_tau(T if tmax is None else tmax, cfg.n)
         return out
 
 
@@ -249,8 +261,10 @@ def interp_boundary_batch(B, u, r, q, K, T, is_put, cfg: AloConfig = AloConfig()
         return out
 
 
-def price_known_boundary_batch(B, r, q, sigma, K, T, S, is_put, t=None, cfg: AloConfig = AloConfig(), device=None):
-    """american_value_with_known_boundary (FastAmericanOptionSolverBase.py:92-103). Returns (price, european)."""
+def price_known_boundary_batch(B, r, q, sigma, K, T, S, is_put, t=None, cfg: AloConfig = AloConfig(), device=None,
+                               tau_max=None):
+    """american_value_with_known_boundary (FastAmericanOptionSolverBase.py:92-103). Returns (price, european).
+    tau_max: end of the boundary's collocation domain (Base.py:28,185), default T."""
     lib = _lib.load()
     dev = _device(device)
     with torch.cuda.device(dev):
@@ -263,7 +277,8 @@ def price_known_boundary_batch(B, r, q, sigma, K, T, S, is_put, t=None, cfg: Alo
         price = torch.empty(N, dtype=torch.float64, device=dev)
         eur = torch.empty(N, dtype=torch.float64, device=dev)
         tab = tables_for(cfg, dev)
-        c = cfg.c()
+        tmax = None if tau_max is None else _f64(tau_max, dev, N)
+        c = cfg.c(tau_max=tmax)
         check(lib.faop_alo_price_known_boundary_batch(ctypes.byref(c), N, _ptr(r), _ptr(q), _ptr(sigma), _ptr(K), _ptr(T),
                                                       _ptr(tt), _ptr(S), _ptr(is_put), _ptr(tab), _ptr(Bd), _ptr(price),
                                                       _ptr(eur), _stream(dev)), "faop_alo_price_known_boundary_batch")
@@ -324,14 +339,18 @@ def greeks_batch(r, q, sigma, K, T, S, is_put, t=None, cfg: AloConfig = AloConfi
                                                        float(bump_S_rel), float(bump_t), _ptr(price), _ptr(delta), _ptr(gamma),
                                                        _ptr(theta), _stream(dev)), "faop_alo_greeks_known_boundary_batch")
         out = dict(price=base["price"], delta=delta, gamma=gamma, theta=theta, iters=base["iters"], err=base["err"])
-        # the finite differences of re-solved prices need a converged boundary: tighten the stopping rule for them
+        # the finite differences of re-solved prices need a converged boundary (at iter_tol = 1e-5 the up and down solves may
+        # stop after different sweep counts, a 1e-5-sized kink against a 1e-4-sized bump): the bumped solves run with the
+        # stopping rule tightened 1000x and room for the extra sweeps; the price itself keeps the caller's configuration
+        import dataclasses
+        fd = dataclasses.replace(cfg, iter_tol=cfg.iter_tol * 1e-3, max_iters=max(cfg.max_iters, 64), seed="newton")
         if want_vega:
-            up = price_batch(r_, q_, sg_ + bump_sigma, K_, T_, S_, ip, t=tt, cfg=cfg, want_boundary=False)["price"]
-            dn = price_batch(r_, q_, sg_ - bump_sigma, K_, T_, S_, ip, t=tt, cfg=cfg, want_boundary=False)["price"]
+            up = price_batch(r_, q_, sg_ + bump_sigma, K_, T_, S_, ip, t=tt, cfg=fd, want_boundary=False)["price"]
+            dn = price_batch(r_, q_, sg_ - bump_sigma, K_, T_, S_, ip, t=tt, cfg=fd, want_boundary=False)["price"]
             out["vega"] = (up - dn) / (2 * bump_sigma)
         if want_rho:
-            up = price_batch(r_ + bump_r, q_, sg_, K_, T_, S_, ip, t=tt, cfg=cfg, want_boundary=False)["price"]
-            dn = price_batch(r_ - bump_r, q_, sg_, K_, T_, S_, ip, t=tt, cfg=cfg, want_boundary=False)["price"]
+            up = price_batch(r_ + bump_r, q_, sg_, K_, T_, S_, ip, t=tt, cfg=fd, want_boundary=False)["price"]
+            dn = price_batch(r_ - bump_r, q_, sg_, K_, T_, S_, ip, t=tt, cfg=fd, want_boundary=False)["price"]
             out["rho"] = (up - dn) / (2 * bump_r)
         return out
 
@@ -698,20 +717,70 @@ class HostContext:
         except Exception:
             pass
 
-    def price_batch(self, r, q, sigma, K, T, S, is_put, t=None, cfg: AloConfig = AloConfig(), out=None, want_boundary=False):
-        """Host arrays (numpy float64 / uint8; pinned memory makes the copies asynchronous) -> dict of numpy arrays."""
+    @staticmethod
+    def _host_in(x, N, dtype, name):
+        """An input as a C-contiguous host array of `dtype` and length N: numpy arrays of the right layout and pinned torch
+        CPU tensors pass through untouched (no copy); anything else numpy can convert (lists, float32, strided views, bool
+        flags) is converted; a wrong length raises.  The C call reads exactly N elements from the returned buffer."""
+        if isinstance(x, torch.Tensor):
+            if x.device.type != "cpu" or x.dtype != (torch.float64 if dtype == np.float64 else torch.uint8) or not x.is_contiguous():
+                x = x.detach().cpu().numpy()
+            else:
+                if x.numel() != N:
+                    raise ValueError("%s has %d elements, expected %d" % (name, x.numel(), N))
+                return x
+        a = np.asarray(x)
+        if dtype == np.uint8 and a.dtype == np.bool_:
+            a = a.view(np.uint8)
+        a = np.ascontiguousarray(a, dtype=dtype).reshape(-1)
+        if a.shape[0] == 1 and N != 1:
+            a = np.full(N, a[0], dtype=dtype)
+        if a.shape[0] != N:
+            raise ValueError("%s has %d elements, expected %d" % (name, a.shape[0], N))
+        return a
+
+    @staticmethod
+    def _host_out(x, shape, dtype, name):
+        """A caller-supplied output buffer must already be what the C call writes: right dtype, C-contiguous, right size."""
+        if isinstance(x, torch.Tensor):
+            ok = x.device.type == "cpu" and x.is_contiguous() and tuple(x.shape) == shape and \
+                x.dtype == {np.float64: torch.float64, np.int32: torch.int32}[dtype]
+        else:
+            ok = isinstance(x, np.ndarray) and x.dtype == dtype and x.flags.c_contiguous and x.flags.writeable and x.shape == shape
+        if not ok:
+            raise ValueError("out[%r] must be a writable C-contiguous %s array of shape %r" % (name, np.dtype(dtype).name, shape))
+        return x
+
+    def price_batch(self, r, q, sigma, K, T, S, is_put, t=None, cfg: AloConfig = AloConfig(), out=None, want_boundary=False,
+                    tau_max=None):
+        """Host arrays (numpy float64 / uint8; pinned memory makes the copies asynchronous) -> dict of numpy arrays.
+        Inputs are checked and, where needed, converted (see _host_in); arrays in `out` are checked (see _host_out)."""
         def hp(a):
             return None if a is None else ctypes.c_void_p(a.ctypes.data if isinstance(a, np.ndarray) else a.data_ptr())
-        N = len(r)
+        N = int(r.numel()) if isinstance(r, torch.Tensor) else int(np.asarray(r).size)
         nn = cfg.n + 1
+        r, q, sigma, K, T, S = (self._host_in(x, N, np.float64, nm) for x, nm in
+                                ((r, "r"), (q, "q"), (sigma, "sigma"), (K, "K"), (T, "T"), (S, "S")))
+        is_put = self._host_in(is_put, N, np.uint8, "is_put")
+        t = None if t is None else self._host_in(t, N, np.float64, "t")
+        tmax = None if tau_max is None else self._host_in(tau_max, N, np.float64, "tau_max")
         if out is None:
             out = dict(price=np.empty(N), european=np.empty(N), iters=np.empty(N, dtype=np.int32), err=np.empty(N))
             if want_boundary:
                 out["B"] = np.empty((N, nn))
                 out["B0"] = np.empty((N, nn))
+        else:
+            if "price" not in out:
+                raise ValueError("out needs at least a 'price' array")
+            for k, v in out.items():
+                if k not in ("price", "european", "err", "iters", "B", "B0"):
+                    raise ValueError("unknown output %r" % (k,))
+                self._host_out(v, (N, nn) if k in ("B", "B0") else (N,), np.int32 if k == "iters" else np.float64, k)
         yl, wl = quadrature_rule(cfg.rule_l, cfg.l)
         ym, wm = quadrature_rule(cfg.rule_m, cfg.m)
         c = cfg.c()
+        if tmax is not None:
+            c.tau_max = tmax.ctypes.data if isinstance(tmax, np.ndarray) else tmax.data_ptr()      # a HOST array for the *_host entry
         check(self._lib.faop_alo_price_batch_host(self._h, ctypes.byref(c), N, hp(r), hp(q), hp(sigma), hp(K), hp(T), hp(t),
                                                   hp(S), hp(is_put), hp(yl), hp(wl), hp(ym), hp(wm), None, hp(out["price"]),
                                                   hp(out.get("european")), hp(out.get("B")), hp(out.get("B0")),
@@ -738,9 +807,17 @@ class MultiGpuHost:
     def price_batch(self, r, q, sigma, K, T, S, is_put, t=None, cfg: AloConfig = AloConfig(), out=None):
         from concurrent.futures import ThreadPoolExecutor
         from .sharding import shard_bounds
-        N = len(r)
+        N = int(r.numel()) if isinstance(r, torch.Tensor) else int(np.asarray(r).size)
+        hin = HostContext._host_in
+        r, q, sigma, K, T, S = (hin(x, N, np.float64, nm) for x, nm in
+                                ((r, "r"), (q, "q"), (sigma, "sigma"), (K, "K"), (T, "T"), (S, "S")))
+        is_put = hin(is_put, N, np.uint8, "is_put")
+        t = None if t is None else hin(t, N, np.float64, "t")
         if out is None:
             out = dict(price=np.empty(N), european=np.empty(N), iters=np.empty(N, dtype=np.int32), err=np.empty(N))
+        else:
+            for k, v in out.items():
+                HostContext._host_out(v, (N,), np.int32 if k == "iters" else np.float64, k)
         W = len(self.ctx)
 
         def work(g):

@@ -24,7 +24,7 @@ __global__ void __launch_bounds__(128) qd_seed_kernel(AloArgs a) {
     const int n = a.tl.n, nn = n + 1;
     int64_t opt = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (opt >= a.N) return;
-    const double r = a.r[opt], q = a.q[opt], sg = a.sigma[opt], K = a.K[opt], T = a.T[opt];
+    const double r = a.r[opt], q = a.q[opt], sg = a.sigma[opt], K = a.K[opt], T = a.tau_max ? a.tau_max[opt] : a.T[opt];
     const bool put = a.is_put[opt] != 0;
     double* out = a.seeds_out + opt * nn;
     if (q == 0 && !put) {  // European shortcut: no boundary is solved
@@ -226,7 +226,7 @@ __global__ void __launch_bounds__(kGenWarps * 32) alo_eval_points_kernel(AloArgs
             } else {
                 const NodeC c = node_consts(o, tau);
                 const double L = log(Q / o.X);
-                const double zf = sqrt(4 * tau / o.T);
+                const double zf = sqrt(4 * tau / o.Tc);
                 double a1 = 0, a2 = 0, a3 = 0, a4 = 0;
                 for (int k = lane; k < tl.LP; k += 32) {
                     double h = tb.hl[k], sg_k = tb.sgl[k];
@@ -279,7 +279,7 @@ __global__ void __launch_bounds__(kGenWarps * 32) alo_interp_kernel(AloArgs a, d
         fit_boundary(w, tb, n, o.X, lane);
         for (int p = lane; p < a.npts; p += 32) {
             double u = a.pts_tau[opt * a.npts + p];
-            double z = sqrt(4 * (u - 0.0) / (o.T - 0.0)) - 1;  // to_cheby_point (:235-237), tau_min = 0, tau_max = T
+            double z = sqrt(4 * (u - 0.0) / (o.Tc - 0.0)) - 1;  // to_cheby_point (:235-237), tau_min = 0
             double Hu = clenshaw(n, w.A, z);
             double root = sqrt(Hu < 0.0 ? 0.0 : Hu);
             Bu[opt * a.npts + p] = exp(-o.om * root) * o.X;
@@ -367,6 +367,7 @@ static size_t generic_smem(const TableLayout& tl) {
 
 int launch_qd_seed(const AloArgs& a, cudaStream_t st) {
     if (a.N == 0) return 0;
+    if (!(a.cfg.flags & FAOP_FLAG_SEED_NEWTON)) return launch_qd_seed_hybr(a, st);
     int64_t blocks = (a.N + 127) / 128;
     qd_seed_kernel<<<(unsigned)blocks, 128, 0, st>>>(a);
     count_launch();

@@ -27,6 +27,7 @@ FAOP_D double warp_sum(double v) {
 // Per-option scalars every lane keeps in registers.
 struct Opt {
     double r, q, sg, K, T, t, S, X, om;
+    double Tc;   // end of the collocation domain: the tau_max attribute (Base.py:28), = T unless the caller changed it
     bool put;
 };
 
@@ -187,6 +188,7 @@ FAOP_D void stage_tables(double* s_tab, const double* g_tab, int count) {
 FAOP_D Opt load_option(const AloArgs& a, int64_t opt) {
     Opt o;
     o.r = a.r[opt]; o.q = a.q[opt]; o.sg = a.sigma[opt]; o.K = a.K[opt]; o.T = a.T[opt];
+    o.Tc = a.tau_max ? a.tau_max[opt] : o.T;
     o.t = a.t ? a.t[opt] : 0.0;
     o.S = a.S ? a.S[opt] : 0.0;
     o.put = a.is_put[opt] != 0;
@@ -234,7 +236,7 @@ FAOP_D NodeC node_from_smem(const WarpSmem& w, const Opt& o, int j) {
 FAOP_D void setup_nodes(const WarpSmem& w, const CtaTables& tb, int n, const Opt& o, int lane) {
     for (int j = lane; j <= n; j += 32) {
         double c = tb.c[j];
-        double tau = (c + 1) * (c + 1) * o.T / 4;
+        double tau = (c + 1) * (c + 1) * o.Tc / 4;
         w.tau[j] = tau;
         w.cinv[j] = 1.0 / (o.sg * sqrt(tau));
         w.disc[j] = o.K * exp(-tau * (o.r - o.q));
@@ -271,7 +273,7 @@ FAOP_D double price_integral(const WarpSmem& w, const CtaTables& tb, const Table
     fit_boundary(w, tb, tl.n, o.X, lane);
     NodeC c = node_consts(o, tau);
     double LS = log(o.S / o.X);
-    double zf = sqrt(4 * tau / o.T);  // z = sqrt(4 u/T) - 1 with u = tau g_k
+    double zf = sqrt(4 * tau / o.Tc);  // z = sqrt(4 u/tau_max) - 1 with u = tau g_k
     double acc = 0;
     for (int k = lane; k < tl.MP; k += 32) {
         double h = tb.hm[k];

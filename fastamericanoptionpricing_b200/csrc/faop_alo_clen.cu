@@ -97,7 +97,7 @@ __global__ void __launch_bounds__(kClenWarps * 32, 1) alo_clen_kernel(AloArgs a)
             }
             if (lane < nn) {
                 const double c = tb.c[lane];
-                const double tau = (c + 1) * (c + 1) * o.T / 4;   // to_orig_point, FastAmericanOptionSolverBase.py:239-240
+                const double tau = (c + 1) * (c + 1) * o.Tc / 4;   // to_orig_point, FastAmericanOptionSolverBase.py:239-240
                 ws.tau[lane] = tau;
                 ws.opc[lane] = 1.0 + c;
                 ws.node[lane] = make_node_pack(o, tau);
@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(kClenWarps * 32, 1) alo_clen_kernel(AloArgs a)
             }
             om = o.om; oq = o.q; orr = o.r;
             sgn = o.put ? 0 : (int)0x80000000;
-            degenerate = !(o.T > 0);
+            degenerate = !(o.Tc > 0);
         }
         __syncwarp();
         if (SCR && !degenerate) {
@@ -132,11 +132,19 @@ __global__ void __launch_bounds__(kClenWarps * 32, 1) alo_clen_kernel(AloArgs a)
         while (err > a.cfg.iter_tol && count < a.cfg.max_iters) {
             ++count;
             // ---- L_j, H_j and the DCT-I fit a_k = (2/n) sum'' H_j cos(j k pi/n)
+            bool bad = false;
             if (lane < nn) {
                 const double L = (lane == n) ? 0.0 : fast_log(ws.B[lane] * ws.par[1]);
                 ws.L[lane] = L;
                 ws.node[lane].L = L;
                 ws.H[lane] = L * L;
+                bad = !(fabs(L) <= 1.79e308);
+            }
+            if (__any_sync(kFull, bad)) {    // see alo_fast_A12_kernel: the sweep upstream turns to NaN at every active node
+                if (lane < n) ws.B[lane] = nan("");
+                err = nan("");
+                __syncwarp();
+                break;
             }
             __syncwarp();
             if (lane < nn) {

@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(kFastWarps * 32, 1) alo_fast_A12_kernel(AloArg
             // ---- per-option setup: node constants (lanes 0..12) and the invariant e^{q u_ik} table
             if (lane < NN) {
                 double c = tb.c[lane];
-                double tau = (c + 1) * (c + 1) * o.T / 4;      // to_orig_point, FastAmericanOptionSolverBase.py:239-240
+                double tau = (c + 1) * (c + 1) * o.Tc / 4;      // to_orig_point, FastAmericanOptionSolverBase.py:239-240
                 ws.tau[lane] = tau;
                 const NodePack np = make_node_pack(o, tau);
                 ws.node[lane] = np;
@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(kFastWarps * 32, 1) alo_fast_A12_kernel(AloArg
             }
             om = o.om; oq = o.q; orr = o.r;
             sgn = o.put ? 0 : (int)0x80000000;   // sign flip of the call side, applied with integer XOR
-            degenerate = !(o.T > 0);     // T == 0: every node has tau == 0 and is pinned to X
+            degenerate = !(o.Tc > 0);     // T == 0: every node has tau == 0 and is pinned to X
         }
         __syncwarp();
 #pragma unroll
@@ -137,11 +137,25 @@ __global__ void __launch_bounds__(kFastWarps * 32, 1) alo_fast_A12_kernel(AloArg
         while (err > tol_cmp && count < a.cfg.max_iters) {
             ++count;
             // ---- L_j = ln(B_j/X), H_j = L_j^2 (FastAmericanOptionSolverBase.py:184), broadcast through shared memory
+            bool bad = false;
             if (lane < NN) {
                 double L = (lane == NC) ? 0.0 : fast_log(ws.B[lane] * ws.par[1]);
                 ws.L[lane] = L;
                 ws.node[lane].L = L;
                 ws.H[lane] = L * L;
+                bad = !(fabs(L) <= 1.79e308);
+            }
+            // A node outside (0, inf) (a diverging iterate, a NaN seed, X = rK/q = 0): upstream's H = ln(B/X)^2 (Base.py:184) is
+            // NaN / inf there, the Chebyshev fit spreads it to every coefficient, so this sweep returns NaN at every active node,
+            // its error is NaN and `while iter_err > tol` stops on it.  That outcome is written down directly — decided on the
+            // full-accuracy log, once per sweep — rather than pushed through the point loop, whose exp / erfcx / sqrt clamp on
+            // the integer high word and do not carry a NaN of either sign through.
+            if (__any_sync(kFull, bad)) {
+                if (lane < NC) ws.B[lane] = nan("");
+                err = nan("");
+                if (ERRS && lane == 0) a.iter_errs[opt * a.cfg.max_iters + (count - 1)] = err;
+                __syncwarp();
+                break;
             }
             __syncwarp();
             double Hj[NC];
@@ -304,7 +318,7 @@ __global__ void __launch_bounds__(kFastWarps * 32, 1) alo_fast_A12_kernel(AloArg
             __syncwarp();
             continue;
         }
-        if (count > 0) err = sqrt(err);            // not SNAP here: back to the norm the reference reports (self.error)
+        if (count > 0) err = sqrt(err);            // not SNAP here: back to the norm the reference reports (self.error); NaN stays NaN
         if (ERRS)
             for (int j = count + lane; j < a.cfg.max_iters; j += 32) a.iter_errs[opt * a.cfg.max_iters + j] = nan("");
         if (a.B && lane < NN) a.B[opt * NN + lane] = ws.B[lane];

@@ -60,11 +60,19 @@ FAOP_D double price_integral_fast(const WarpSmem& w, const CtaTables& tb, const 
     *eur = e;
     if (tau == 0) return e + 0.0;  // quadrature_sum returns 0 at tau == 0 (:382-383)
     const int n = tl.n;
+    bool bad = false;
     for (int j = lane; j <= n; j += 32) {   // L_j = ln(B_j/X), H_j = L_j^2 and the DCT-I fit (fit_boundary)
         const double L = fast_log(w.B[j] / o.X);
         w.L[j] = L;
         w.H[j] = L * L;
+        bad |= !(fabs(L) <= 1.79e308);
     }
+    // A boundary node outside (0, inf) (or X = 0), a spot outside (0, inf), tau < 0: upstream takes the log / square root of it
+    // and returns NaN (Base.py:184, :237, :307).  Decided here, on full-accuracy values: the reduced-cost exp / erfcx / sqrt
+    // below clamp on the integer high word and are not required to carry a NaN of either sign through.
+    const double LS = fast_log(o.S / o.X);
+    bad |= !(fabs(LS) <= 1.79e308) || !(tau > 0);
+    if (__any_sync(kFull, bad)) return nan("");
     __syncwarp();
     const int n2 = 2 * n;
     for (int k = lane; k <= n; k += 32) {
@@ -81,8 +89,7 @@ FAOP_D double price_integral_fast(const WarpSmem& w, const CtaTables& tb, const 
     }
     __syncwarp();
     const NodeC c = node_consts(o, tau);
-    const double LS = fast_log(o.S / o.X);
-    const double zf = sqrt(4 * tau / o.T);
+    const double zf = sqrt(4 * tau / o.Tc);
     const double cinv2 = c.cinv * kInvSqrt2, apc2 = c.apc * kInvSqrt2, ssu2 = c.ssu * kInvSqrt2;
     const double rK = o.r * o.K, qS = o.q * o.S;
     double acc = 0.0;

@@ -151,6 +151,7 @@ static int fill_args(AloArgs& a, const faop_cfg* cfg, int64_t N, const double* r
     a.tl = table_layout(cfg->n_colloc, cfg->n_quad, cfg->n_price_quad);
     a.N = N;
     a.r = r; a.q = q; a.sigma = sigma; a.K = K; a.T = T; a.t = t; a.S = S; a.is_put = is_put;
+    a.tau_max = cfg->tau_max;
     a.tables = (const double*)tables_dev;
     return 0;
 }
@@ -212,6 +213,7 @@ int faop_alo_surface_batch(const faop_cfg* cfg, const faop_surface* surf, int64_
                            size_t workspace_bytes, void* cuda_stream) {
     int rc = check_cfg(cfg);
     if (rc) return rc;
+    if (cfg->tau_max) return FAOP_ERANGE;     // the surface is generated on the device: collocation domain = maturity
     if (!surf || first < 0 || count < 0 || surf->nK < 1 || surf->nT < 1 || surf->nV < 1) return FAOP_EINVAL;
     if (first + count > (int64_t)surf->nK * surf->nT * surf->nV) return FAOP_EINVAL;
     if (count == 0) return 0;
@@ -289,6 +291,7 @@ int faop_alo_surface_dedup_batch(const faop_cfg* cfg, const faop_surface* surf, 
                                  size_t workspace_bytes, void* cuda_stream) {
     int rc = check_cfg(cfg);
     if (rc) return rc;
+    if (cfg->tau_max) return FAOP_ERANGE;     // the surface is generated on the device: collocation domain = maturity
     if (!surf || first < 0 || count < 0 || surf->nK < 1 || surf->nT < 1 || surf->nV < 1) return FAOP_EINVAL;
     if (first + count > (int64_t)surf->nK * surf->nT * surf->nV) return FAOP_EINVAL;
     if (cfg->use_derivative) return FAOP_ERANGE;    // f' = N'/D - D'N/D^2 is not scale-free in the reference's form
@@ -355,6 +358,7 @@ int faop_alo_ladder_batch(const faop_cfg* cfg, int64_t G, const double* r, const
     if (rc) return rc;
     if (G < 0 || nK < 0 || G > 0x7fffffff) return FAOP_EINVAL;
     if (cfg->use_derivative) return FAOP_ERANGE;
+    if (cfg->tau_max) return FAOP_ERANGE;     // the ladder's price kernel maps u with the maturity
     if (G == 0 || nK == 0) return 0;
     if (!r || !q || !sigma || !T || !S || !is_put || !K || !price || !workspace || !tables_dev) return FAOP_EINVAL;
     if (!(K_min > 0) || !(K_max >= K_min)) return FAOP_EINVAL;
@@ -608,7 +612,7 @@ int faop_alo_price_batch_host(faop_ctx* c, const faop_cfg* cfg, int64_t N, const
     const size_t mat = ((size_t)N * nn * sizeof(double) + 255) & ~(size_t)255;
     // arena: r q sigma K T t S | price european err | is_put iters | B0 B | invariant-table scratch of the two stream lanes
     const size_t scr = (alo_clen_scratch_bytes(*cfg) + 255) & ~(size_t)255;
-    size_t need = 10 * vec + 2 * vec + 2 * mat + 2 * scr;
+    size_t need = 10 * vec + 2 * vec + 2 * mat + 2 * scr + (cfg->tau_max ? vec : 0);
     if (need > c->dev_bytes) {
         if (c->dev) { cudaFree(c->dev); c->dev = nullptr; c->dev_bytes = 0; }
         FAOP_CUDA_OK(cudaMalloc(&c->dev, need));
@@ -622,6 +626,8 @@ int faop_alo_price_batch_host(faop_ctx* c, const faop_cfg* cfg, int64_t N, const
     double* d_err = (double*)take(vec); uint8_t* d_put = (uint8_t*)take(vec); int32_t* d_it = (int32_t*)take(vec);
     double* d_B0 = (double*)take(mat); double* d_B = (double*)take(mat);
     double* d_scr[2] = {scr ? (double*)take(scr) : nullptr, scr ? (double*)take(scr) : nullptr};
+    double* d_tmax = cfg->tau_max ? (double*)take(vec) : nullptr;     // cfg->tau_max is a HOST array here
+    faop_cfg dcfg = *cfg;
     // Chunk pipeline over two streams: while one chunk's kernels run, the other's inputs go up and results come back
     // (asynchronous when the caller's arrays are pinned).  Chunks are slices of the same arena.
     int nchunks = (int)(N / 262144);
@@ -642,7 +648,11 @@ int faop_alo_price_batch_host(faop_ctx* c, const faop_cfg* cfg, int64_t N, const
         FAOP_CUDA_OK(cudaMemcpyAsync(d_S + off, S + off, vb, cudaMemcpyHostToDevice, st));
         FAOP_CUDA_OK(cudaMemcpyAsync(d_put + off, is_put + off, (size_t)cnt, cudaMemcpyHostToDevice, st));
         if (B0_in) FAOP_CUDA_OK(cudaMemcpyAsync(d_B0 + off * nn, B0_in + off * nn, mb, cudaMemcpyHostToDevice, st));
-        rc = price_batch_impl(cfg, cnt, d_r + off, d_q + off, d_s + off, d_K + off, d_T + off, t ? d_t + off : nullptr,
+        if (d_tmax) {
+            FAOP_CUDA_OK(cudaMemcpyAsync(d_tmax + off, cfg->tau_max + off, vb, cudaMemcpyHostToDevice, st));
+            dcfg.tau_max = d_tmax + off;
+        }
+        rc = price_batch_impl(&dcfg, cnt, d_r + off, d_q + off, d_s + off, d_K + off, d_T + off, t ? d_t + off : nullptr,
                               d_S + off, d_put + off, c->tables_dev, B0_in ? d_B0 + off * nn : nullptr, d_price + off,
                               european ? d_eur + off : nullptr, B ? d_B + off * nn : nullptr,
                               B0_in ? nullptr : d_B0 + off * nn, iters ? d_it + off : nullptr, err ? d_err + off : nullptr,

@@ -9,6 +9,7 @@ struct AloArgs {
     TableLayout tl;
     int64_t N;
     const double *r, *q, *sigma, *K, *T, *t, *S;
+    const double* tau_max;   // nullable: end of the collocation domain per option (the tau_max attribute, Base.py:28); T when null
     const uint8_t* is_put;
     const double* tables;    // device table blob (faop_tables_build)
     const double* seeds_in;  // N x (n+1) boundary the solve starts from (QD seed or borrowed B0)
@@ -35,7 +36,8 @@ struct EvalOut {
     double *I1, *I2;   // the two quadrature integrals: A: K12, K3 (A.py:24-44); B: the D- and N-integrals (B.py:25-39)
 };
 
-int launch_qd_seed(const AloArgs& a, cudaStream_t st);
+int launch_qd_seed(const AloArgs& a, cudaStream_t st);        // dispatches on FAOP_FLAG_SEED_NEWTON
+int launch_qd_seed_hybr(const AloArgs& a, cudaStream_t st);   // faop_seed.cu: the reference's root finder (default)
 int launch_alo_generic(const AloArgs& a, cudaStream_t st);
 int launch_alo_eval_nodes(const AloArgs& a, const EvalOut& eo, cudaStream_t st);
 int launch_alo_price_known(const AloArgs& a, cudaStream_t st);

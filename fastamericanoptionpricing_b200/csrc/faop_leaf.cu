@@ -1,4 +1,4 @@
-// faop_leaf.cu — leaf kernels: QD+ boundary / residual / price, European closed forms, Chebyshev fit and
+// faop_leaf.cu — leaf kernels: European closed forms (the QD+ leaf kernels live in faop_seed.cu), Chebyshev fit and
 // Clenshaw evaluation, and the FP64 FMA-pipe peak microbenchmark used as the roofline denominator.
 // One thread per element, coalesced structure-of-arrays loads, grid sized to the batch.
 #include "faop_kernels.h"
@@ -7,76 +7,6 @@
 namespace faop {
 
 static inline unsigned blocks_for(int64_t n, int threads) { return (unsigned)((n + threads - 1) / threads); }
-
-// QDplus.compute_exercise_boundary, QDplusAmericanOptionSolver.py:69-76
-__global__ void __launch_bounds__(256) qd_boundary_kernel(int64_t N, const double* r, const double* q, const double* sigma,
-                                                          const double* K, const double* tau, const uint8_t* is_put, double* B) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= N) return;
-    B[i] = qd_boundary(tau[i], r[i], q[i], sigma[i], K[i], is_put[i] != 0);
-}
-
-// QDplus.exercise_boundary_func, QDplusAmericanOptionSolver.py:110-125 (tau == 0 -> 0)
-__global__ void __launch_bounds__(256) qd_residual_kernel(int64_t N, const double* r, const double* q, const double* sigma,
-                                                          const double* K, const double* tau, const double* S,
-                                                          const uint8_t* is_put, double* F) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= N) return;
-    if (tau[i] == 0) { F[i] = 0.0; return; }
-    bool put = is_put[i] != 0;
-    QdConst c = qd_const(tau[i], r[i], q[i], sigma[i], put);
-    double f, df;
-    qd_resid(c, S[i], K[i], put, &f, &df);
-    F[i] = f;
-}
-
-// QDplus.price, QDplusAmericanOptionSolver.py:44-67, with compute_miscellaneous' c, b (:142-218).
-// Quirks kept: tau == 0 returns max(S-K, 0) and boundary K for puts too (:45-47); the put-form
-// correction (K - Sb - p(Sb)) is used for calls as well (:67); c() uses Phi(-d1) for both types (:172);
-// theta is the put theta (EuropeanOptionSolver.py:25-32).
-__global__ void __launch_bounds__(128) qd_price_kernel(int64_t N, const double* r_, const double* q_, const double* sigma_,
-                                                       const double* K_, const double* tau_, const double* S_,
-                                                       const uint8_t* is_put, double* price, double* boundary) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= N) return;
-    double r = r_[i], q = q_[i], sg = sigma_[i], K = K_[i], tau = tau_[i], S = S_[i];
-    bool put = is_put[i] != 0;
-    if (tau == 0) {
-        price[i] = fmax(S - K, 0.0);
-        if (boundary) boundary[i] = K;
-        return;
-    }
-    double Sb = qd_boundary(tau, r, q, sg, K, put);
-    if (boundary) boundary[i] = Sb;
-    double ind = put ? -1.0 : 1.0;
-    double s2 = sg * sg;
-    double Nn = 2 * (r - q) / s2, M = 2 * r / s2, h = 1 - exp(-r * tau);
-    double disc = sqrt((Nn - 1) * (Nn - 1) + 4 * M / h);
-    double qQD = -0.5 * (Nn - 1) + ind * 0.5 * disc;
-    double qQDdot = M / (h * h * disc);
-    double svt = sg * sqrt(tau);
-    double d1 = euro_d1(tau, Sb, r, q, sg, K);
-    double p = euro_value(tau, Sb, r, q, sg, K, put);
-    double theta = euro_theta(tau, Sb, r, q, sg, K);
-    double eq = exp(-q * tau), ert = exp(r * tau);
-    double Pm1 = norm_cdf(-d1), pd1 = norm_pdf(d1);
-    double KSp = K - Sb - p;
-    double dFdh = qQD * theta * ert / r + qQDdot * KSp + (Sb * q * eq * Pm1) / (r * (1 - h)) -
-                  (Sb * eq * pd1) / (2 * r * tau * (1 - h)) * (2 * log(Sb / K) / svt - d1);
-    double dFdS = (1 - qQD) * (1 - eq * Pm1) + (eq * pd1) / svt;
-    double dlogSdh = -dFdh / dFdS;
-    double den = 2 * qQD + Nn - 1;
-    double c0 = -(1 - h) * M / den * (1 / h - (theta * ert) / (r * KSp) + qQDdot / den);
-    double c = c0 - ((1 - h) * M) / den * ((1 - eq * Pm1) / KSp + qQD / Sb) * dlogSdh;
-    double b = ((1 - h) * M * qQDdot) / (2 * den);
-    if (ind * (Sb - S) <= 0) {
-        price[i] = ind * (S - K);
-        return;
-    }
-    double pS = euro_value(tau, S, r, q, sg, K, put);
-    double lg = log(S / Sb);
-    price[i] = pS + KSp / (1 - b * (lg * lg) - c * lg) * pow(S / Sb, qQD);
-}
 
 // EuropeanOption.european_put_value / european_call_value, EuropeanOptionSolver.py:7-22
 __global__ void __launch_bounds__(256) european_kernel(int64_t N, const double* tau, const double* S, const double* r,
@@ -215,7 +145,8 @@ __global__ void __launch_bounds__(256) fp64_peak_kernel(double* sink, double m, 
 // option: the bracket, the residuals at its ends (NaN = not evaluated yet) and which end moved last.  Each call consumes
 // the price just computed at `sigma` and writes the next trial point into `sigma`:
 //   first two calls evaluate the ends of the bracket; afterwards the secant point of the bracket, with the retained end's
-//   residual halved whenever the same end moves twice in a row (Illinois), clipped into the bracket's interior.
+//   residual halved (in the secant formula only) whenever the same end moves twice in a row (Illinois), clipped into the
+//   bracket's interior.
 // A target outside [price(lo), price(hi)] pins sigma to NaN.  SURVEY 8f row 2 (callers of solve(); not in the reference).
 __global__ void __launch_bounds__(256) iv_update_kernel(int64_t N, const double* target, const double* price, double* sigma,
                                                         double* lo, double* hi, double* flo, double* fhi, int32_t* side) {
@@ -229,32 +160,37 @@ __global__ void __launch_bounds__(256) iv_update_kernel(int64_t N, const double*
         flo[i] = f; side[i] = -1; sigma[i] = b;
         return;
     }
-    int sd = state & 3, slow = state >> 2;      // which end moved last; consecutive steps that shrank the bracket < 2x
+    // state word: bits 0-1 which end moved last, bits 2-3 consecutive steps that shrank the bracket < 2x, bits 4-9 how often the
+    // RETAINED end's residual has been halved (Illinois).  flo / fhi always hold the TRUE residuals (the caller's termination
+    // test and its choice of the answer read them); the Illinois factor 2^-k is applied only when the secant point is formed.
+    int sd = state & 3, slow = (state >> 2) & 3, k = (state >> 4) & 63;
     const double w_old = b - a;
     if (state == -1) {                          // second call: x == hi
         fb = f;
         if (!(fa <= 0.0) || !(fb >= 0.0)) { side[i] = -3; fhi[i] = fb; sigma[i] = nan(""); return; }
-        sd = 0; slow = 0;
+        sd = 0; slow = 0; k = 0;
     } else if (f == 0.0) {
         lo[i] = hi[i] = x; flo[i] = fhi[i] = 0.0;
         return;                                 // sigma[i] stays at the root
     } else if (f < 0.0) {
         a = x; fa = f;
-        if (sd == 1) fb *= 0.5;
+        k = (sd == 1) ? min(k + 1, 60) : 0;
         sd = 1;
     } else {
         b = x; fb = f;
-        if (sd == 2) fa *= 0.5;
+        k = (sd == 2) ? min(k + 1, 60) : 0;
         sd = 2;
     }
     const double w = b - a;
-    slow = (state >= 0 && w > 0.5 * w_old) ? slow + 1 : 0;
-    double xn = (fb == fa) ? 0.5 * (a + b) : (a * fb - b * fa) / (fb - fa);
+    slow = (state >= 0 && w > 0.5 * w_old) ? min(slow + 1, 3) : 0;
+    const double sc = ldexp(1.0, -k);
+    const double fas = (sd == 2) ? fa * sc : fa, fbs = (sd == 1) ? fb * sc : fb;     // the end that did not move is the stale one
+    double xn = (fbs == fas) ? 0.5 * (a + b) : (a * fbs - b * fas) / (fbs - fas);
     if (slow >= 2) { xn = 0.5 * (a + b); slow = 0; }   // flat-then-steep residuals stall the secant: bisect
     if (!(xn > a + 1e-3 * w)) xn = a + 1e-3 * w;      // also catches NaN
     if (!(xn < b - 1e-3 * w)) xn = b - 1e-3 * w;
     if (w <= 4e-16 * b) xn = x;                        // bracket at rounding level: stay
-    lo[i] = a; hi[i] = b; flo[i] = fa; fhi[i] = fb; side[i] = sd | (slow << 2); sigma[i] = xn;
+    lo[i] = a; hi[i] = b; flo[i] = fa; fhi[i] = fb; side[i] = sd | (slow << 2) | (k << 4); sigma[i] = xn;
 }
 int launch_iv_update(int64_t N, const double* target, const double* price, double* sigma, double* lo, double* hi, double* flo,
                      double* fhi, int32_t* side, cudaStream_t st) {
@@ -334,20 +270,6 @@ int launch_point_mix_peak(int launches, double* points_per_s, double* ms_per_lau
     return launch_status();
 }
 
-int launch_qd_boundary(int64_t N, const double* r, const double* q, const double* sigma, const double* K,
-                       const double* tau, const uint8_t* is_put, double* B, cudaStream_t st) {
-    if (N == 0) return 0;
-    qd_boundary_kernel<<<blocks_for(N, 256), 256, 0, st>>>(N, r, q, sigma, K, tau, is_put, B);
-    count_launch();
-    return launch_status();
-}
-int launch_qd_residual(int64_t N, const double* r, const double* q, const double* sigma, const double* K,
-                       const double* tau, const double* S, const uint8_t* is_put, double* F, cudaStream_t st) {
-    if (N == 0) return 0;
-    qd_residual_kernel<<<blocks_for(N, 256), 256, 0, st>>>(N, r, q, sigma, K, tau, S, is_put, F);
-    count_launch();
-    return launch_status();
-}
 // ---------------------------------------------------------------- Bjerksund-Stensland (1993) flat-boundary call
 // BksdStld (BjerksundStenslandSolver.py:4-43).  phi (:26-33):
 FAOP_D double bs_phi(double S, double T, double gamma, double H, double X, double r, double b, double sg) {
@@ -396,14 +318,6 @@ __global__ void __launch_bounds__(256) bs_phi_kernel(int64_t N, const double* S,
     out[i] = bs_phi(S[i], T[i], gamma[i], H[i], X[i], r[i], r[i] - q[i], sigma[i]);
 }
 
-int launch_qd_price(int64_t N, const double* r, const double* q, const double* sigma, const double* K,
-                    const double* tau, const double* S, const uint8_t* is_put, double* price, double* boundary,
-                    cudaStream_t st) {
-    if (N == 0) return 0;
-    qd_price_kernel<<<blocks_for(N, 128), 128, 0, st>>>(N, r, q, sigma, K, tau, S, is_put, price, boundary);
-    count_launch();
-    return launch_status();
-}
 int launch_bjerksund_stensland(int64_t N, const double* r, const double* q, const double* sigma, const double* K,
                                const double* T, const double* S, const uint8_t* is_put, const double* Kb, const double* Tb,
                                double* price, double* boundary, cudaStream_t st) {

@@ -55,6 +55,11 @@ typedef struct faop_cfg {
     int32_t kernel;         /* 0 = auto (specialised kernel when one exists for (solver,n,l)),
                                1 = force the generic kernel; results agree to rounding          */
     int32_t flags;          /* FAOP_FLAG_* bits, 0 in the reference-equivalent default                        */
+    const double* tau_max;  /* self.tau_max per option (FastAmericanOptionSolverBase.py:28, consumed at :185, :223): the end
+                               of the collocation domain [0, tau_max].  NULL = the constructor's value, the maturity T.
+                               A DEVICE array of N doubles for the device-pointer entry points, a HOST array for the
+                               *_host ones.  (self.tau_min stays 0: upstream returns NaN after one sweep for any other
+                               value, because z = sqrt(4 (u - tau_min)/(tau_max - tau_min)) - 1 meets u < tau_min.)   */
 } faop_cfg;
 
 /* `workspace` was sized by faop_workspace_bytes() with this same flag set: besides the QD seeds it then holds the
@@ -62,6 +67,13 @@ typedef struct faop_cfg {
  * and save two of Solver B's four exponentials per quadrature point).  Without the flag (or with workspace == NULL) those
  * values are recomputed; results are identical to rounding.                                                            */
 #define FAOP_FLAG_WS_SCRATCH 1
+/* The QD seed (set_initial_guess, FastAmericanOptionSolverBase.py:258-265) is found by default with the reference's own
+ * root finder — MINPACK hybrd as scipy.optimize.root(hybr, x0=K) drives it (QDplusAmericanOptionSolver.py:73), one unknown,
+ * restated in csrc/faop_seed.cu — because the reference keeps whatever iterate hybrd stops at.  This flag selects a
+ * safeguarded Newton iteration with the analytic derivative instead (warm-started node to node, fast exp/erfcx): ~3x
+ * cheaper, same root to ~1e-15 where the residual is well conditioned, but not the reference's iterate where hybrd exits
+ * early or the residual is flat.                                                                                       */
+#define FAOP_FLAG_SEED_NEWTON 2
 
 /* ---- tables ---------------------------------------------------------------------------------
  * Gauss-Legendre nodes/weights are produced by the CALLER with numpy.polynomial.legendre.leggauss

@@ -9,9 +9,10 @@
  * reference file:line it follows (paths relative to antdvid/FastAmericanOptionPricing).
  * Pinned through tests/golden/ref_*.npz (outputs of the unmodified reference, oracle/gen_golden.py)
  * and against oracle/alo_oracle.py (the numpy restatement) in tests/test_oracle_golden.py.
- * Deviation from the reference, as in alo_oracle.py: the QD seed root uses safeguarded Newton instead
- * of MINPACK hybr (QDplusAmericanOptionSolver.py:73).  Phi(x) = erfc(-x/sqrt2)/2 from libm stands in
- * for scipy.special.ndtr (<= 1 ulp apart).
+ * The QD seed root follows the reference's root finder: hybr1() restates MINPACK hybrd for one unknown as
+ * scipy.optimize.root(method="hybr", x0=K) drives it (QDplusAmericanOptionSolver.py:73), like alo_oracle.py's
+ * hybr1 (which is bit-identical to scipy); safeguarded Newton is kept as seed mode 0.  Phi(x) = erfc(-x/sqrt2)/2
+ * from libm stands in for scipy.special.ndtr (<= 1 ulp apart).
  */
 #include <math.h>
 #include <pthread.h>
@@ -23,6 +24,14 @@
 #define INV_SQRT_2   0.7071067811865475244008443621048490
 
 static double Phi(double x) { return 0.5 * erfc(-x * INV_SQRT_2); }
+/* Conditioning probe of the QD seed (oracle_set_seed_probe): Phi inside the seed residual is scaled by (1 + k ulp).  The
+ * spread of the roots over k = 0, +-1, +-2 is how far the reference's own seed moves when its normal cdf changes in the
+ * last bit — which is what any two correct implementations (scipy's ndtr, libm's erfc, libdevice's erfc) differ by.  For flat
+ * residuals (tiny tau with X = rK/q << K: catastrophic cancellation in K - S - p, QDplusAmericanOptionSolver.py:124) that
+ * spread reaches 1e-6; everywhere else it is a few ulp.  0 outside such probes. */
+static int g_seed_probe_ulps = 0;
+void oracle_set_seed_probe(int ulps) { g_seed_probe_ulps = ulps; }
+static double PhiS(double x) { return Phi(x) * (1.0 + g_seed_probe_ulps * 2.220446049250313e-16); }
 static double phi(double x) { return exp(-0.5 * x * x) * INV_SQRT_2PI; }
 
 /* ---- EuropeanOptionSolver.py:7-40 ---- */
@@ -54,13 +63,13 @@ static void qd_resid(double S, double tau, double r, double q, double sg, double
     double svt = sg * sqrt(tau);
     double d1 = eu_d1(tau, S, r, q, sg, K), d2 = d1 - svt, eq = exp(-q * tau);
     if (is_put) {
-        double p = K * exp(-r * tau) * Phi(-d2) - S * eq * Phi(-d1);
-        *F = (1 - eq * Phi(-d1)) * S + qQD * (K - S - p);
-        *dF = (1 - qQD) * (1 - eq * Phi(-d1)) + eq * phi(d1) / svt;
+        double p = K * exp(-r * tau) * PhiS(-d2) - S * eq * PhiS(-d1);
+        *F = (1 - eq * PhiS(-d1)) * S + qQD * (K - S - p);
+        *dF = (1 - qQD) * (1 - eq * PhiS(-d1)) + eq * phi(d1) / svt;
     } else {
-        double c = S * eq * Phi(d1) - K * exp(-r * tau) * Phi(d2);
-        *F = (1 - eq * Phi(d1)) * S - qQD * (S - K - c);
-        *dF = (1 - qQD) * (1 - eq * Phi(d1)) - eq * phi(d1) / svt;
+        double c = S * eq * PhiS(d1) - K * exp(-r * tau) * PhiS(d2);
+        *F = (1 - eq * PhiS(d1)) * S - qQD * (S - K - c);
+        *dF = (1 - qQD) * (1 - eq * PhiS(d1)) - eq * phi(d1) / svt;
     }
 }
 
@@ -84,6 +93,112 @@ static double qd_boundary(double tau, double r, double q, double sg, double K, i
     return S;
 }
 
+/* MINPACK hybrd for ONE unknown with scipy.optimize.root's defaults (xtol 1.49012e-8, maxfev 400, epsfcn = eps, mode 1,
+ * factor 100): see hybr1 in alo_oracle.py for the derivation (r = -J, q = -1, enorm = fabs, no rotations).  Returns the
+ * iterate hybrd leaves in x, whatever its info code (the reference ignores `success`). */
+static double qd_F(double S, double tau, double r, double q, double sg, double K, int is_put) {
+    double F, dF;
+    qd_resid(S, tau, r, q, sg, K, is_put, &F, &dF);
+    return F;
+}
+static double hybr1_qd(double tau, double r, double q, double sg, double K, int is_put, int* nfev_out) {
+    const double epsmch = 2.220446049250313e-16, xtol = 1.49012e-08, factor = 100.0;
+    const int maxfev = 400;
+    double x = K;
+    double fvec = qd_F(x, tau, r, q, sg, K, is_put);
+    int nfev = 1, it = 1, ncsuc = 0, ncfail = 0, nslow1 = 0, nslow2 = 0;
+    double fnorm = fabs(fvec), diag = 0, delta = 0, xnorm = 0;
+    const double eps = sqrt(epsmch);
+    for (;;) {
+        int jeval = 1;
+        double h = eps * fabs(x);
+        if (h == 0.0) h = eps;
+        double J = (qd_F(x + h, tau, r, q, sg, K, is_put) - fvec) / h;
+        ++nfev;
+        double acn = fabs(J);
+        if (it == 1) {
+            diag = acn != 0.0 ? acn : 1.0;
+            xnorm = fabs(diag * x);
+            delta = factor * xnorm;
+            if (delta == 0.0) delta = factor;
+        }
+        double qtf, rr, Q;
+        if (J != 0.0) { qtf = -fvec; rr = -J; Q = -1.0; } else { qtf = fvec; rr = -0.0; Q = 1.0; }
+        diag = fmax(diag, acn);
+        for (;;) {
+            double temp = rr;
+            if (temp == 0.0) { temp = epsmch * fabs(rr); if (temp == 0.0) temp = epsmch; }
+            double xg = qtf / temp, p;
+            double qnorm = fabs(diag * xg);
+            if (qnorm <= delta) p = xg;
+            else {
+                double wa1 = (rr * qtf) / diag;
+                double gnorm = fabs(wa1), sgnorm = 0.0, alpha = delta / qnorm;
+                if (gnorm != 0.0) {
+                    wa1 = (wa1 / gnorm) / diag;
+                    double t2 = fabs(rr * wa1);
+                    sgnorm = (gnorm / t2) / t2;
+                    alpha = 0.0;
+                    if (sgnorm < delta) {
+                        double bnorm = fabs(qtf);
+                        double tt = (bnorm / gnorm) * (bnorm / qnorm) * (sgnorm / delta);
+                        double dq = delta / qnorm, sd = sgnorm / delta;
+                        tt = tt - dq * (sd * sd) + sqrt((tt - dq) * (tt - dq) + (1.0 - dq * dq) * (1.0 - sd * sd));
+                        alpha = (dq * (1.0 - sd * sd)) / tt;
+                    }
+                }
+                double tt = (1.0 - alpha) * fmin(sgnorm, delta);
+                p = tt * wa1 + alpha * xg;
+            }
+            double w1 = -p, w2 = x + w1, w3 = diag * w1;
+            double pnorm = fabs(w3);
+            if (it == 1) delta = fmin(delta, pnorm);
+            double w4 = qd_F(w2, tau, r, q, sg, K, is_put);
+            ++nfev;
+            double fnorm1 = fabs(w4), actred = -1.0;
+            if (fnorm1 < fnorm) actred = 1.0 - (fnorm1 / fnorm) * (fnorm1 / fnorm);
+            w3 = qtf + rr * w1;
+            temp = fabs(w3);
+            double prered = 0.0;
+            if (temp < fnorm) prered = 1.0 - (temp / fnorm) * (temp / fnorm);
+            double ratio = 0.0;
+            if (prered > 0.0) ratio = actred / prered;
+            if (ratio < 0.1) { ncsuc = 0; ++ncfail; delta = 0.5 * delta; }
+            else {
+                ncfail = 0; ++ncsuc;
+                if (ratio >= 0.5 || ncsuc > 1) delta = fmax(delta, pnorm / 0.5);
+                if (fabs(ratio - 1.0) <= 0.1) delta = pnorm / 0.5;
+            }
+            if (ratio >= 1e-4) { x = w2; w2 = diag * x; fvec = w4; xnorm = fabs(w2); fnorm = fnorm1; ++it; }
+            ++nslow1;
+            if (actred >= 0.001) nslow1 = 0;
+            if (jeval) ++nslow2;
+            if (actred >= 0.1) nslow2 = 0;
+            int info = 0;
+            if (delta <= xtol * xnorm || fnorm == 0.0) info = 1;
+            if (!info) {
+                if (nfev >= maxfev) info = 2;
+                if (0.1 * fmax(0.1 * delta, pnorm) <= epsmch * xnorm) info = 3;
+                if (nslow2 == 5) info = 4;
+                if (nslow1 == 10) info = 5;
+            }
+            if (info) { if (nfev_out) *nfev_out = nfev; return x; }
+            if (ncfail == 2) break;
+            double sm = Q * w4;
+            w2 = (sm - w3) / pnorm;
+            w1 = diag * ((diag * w1) / pnorm);
+            if (ratio >= 1e-4) qtf = sm;
+            rr = rr + w2 * w1;
+            jeval = 0;
+        }
+    }
+}
+static double qd_seed(int mode, double tau, double r, double q, double sg, double K, int is_put) {
+    if (mode == 0) return qd_boundary(tau, r, q, sg, K, is_put);
+    if (tau == 0) return b_at_zero(r, q, K, is_put);
+    return hybr1_qd(tau, r, q, sg, K, is_put, NULL);
+}
+
 /* ---- FastAmericanOptionSolverBase.py:306-310 ---- */
 static void dpm(double s, double z, double r, double q, double sg, double* dm, double* dp) {
     double lz = log(z);
@@ -102,6 +217,7 @@ typedef struct {
     double tol, eta;
     const double *yl, *wl, *ym, *wm;
     const double* costab; /* (n+1)x(n+1): cos(i k pi / n) */
+    int seed;             /* 1 = hybr as upstream (QDplusAmericanOptionSolver.py:73), 0 = safeguarded Newton */
 } cfg_t;
 
 /* ChebyshevInterpolation.py:43-51 */
@@ -195,7 +311,8 @@ static void nd_node(const cfg_t* c, const opt_t* o, const double* a, double tau,
 }
 
 /* solve(t, s0), FastAmericanOptionSolverBase.py:49-165 and :92-103 */
-static void solve_one(const cfg_t* c, double r, double q, double sg, double K, double T, double t, double S, int is_put,
+/* Tc = the `tau_max` attribute, the end of the collocation domain (Base.py:28, consumed at :185 and :223); = T by default */
+static void solve_one(const cfg_t* c, double r, double q, double sg, double K, double T, double Tc, double t, double S, int is_put,
                       const double* B0_in, double* price, double* european, double* Bout, double* B0out,
                       int32_t* iters, double* err) {
     int n = c->n;
@@ -205,13 +322,13 @@ static void solve_one(const cfg_t* c, double r, double q, double sg, double K, d
         for (int i = 0; i <= n; ++i) { if (Bout) Bout[i] = NAN; if (B0out) B0out[i] = NAN; }
         return;
     }
-    opt_t o = {r, q, sg, K, T, b_at_zero(r, q, K, is_put), is_put};
+    opt_t o = {r, q, sg, K, Tc, b_at_zero(r, q, K, is_put), is_put};
     double tau[n + 1], B[n + 1], Bn[n + 1], H[n + 1], a[n + 1];
     for (int i = 0; i <= n; ++i) {
         double ci = cos(i * M_PI / n);                    /* Cheb.py:15-17 */
-        tau[i] = (ci + 1) * (ci + 1) * (T - 0.0) / 4 + 0.0; /* Base.py:239-240 */
+        tau[i] = (ci + 1) * (ci + 1) * (Tc - 0.0) / 4 + 0.0; /* Base.py:239-240 */
     }
-    for (int i = 0; i <= n; ++i) B[i] = B0_in ? B0_in[i] : qd_boundary(tau[i], r, q, sg, K, is_put);
+    for (int i = 0; i <= n; ++i) B[i] = B0_in ? B0_in[i] : qd_seed(c->seed, tau[i], r, q, sg, K, is_put);
     if (B0out) memcpy(B0out, B, sizeof(double) * (n + 1));
     int count = 0;
     double e = 1;
@@ -249,7 +366,7 @@ static void solve_one(const cfg_t* c, double r, double q, double sg, double K, d
         for (int k = 0; k < c->m; ++k) {
             double y = c->ym[k], w = c->wm[k];
             double u = tt - tt * ((1 + y) * (1 + y)) / 4.0;
-            double Bu = boundary_at(c, a, u, T, o.X, is_put);
+            double Bu = boundary_at(c, a, u, Tc, o.X, is_put);
             double s = tt - u, z = S / Bu, dm, dp;
             dpm(s, z, r, q, sg, &dm, &dp);
             double g;
@@ -264,7 +381,7 @@ static void solve_one(const cfg_t* c, double r, double q, double sg, double K, d
 /* ------------------------------------------------------------------ batch drivers (pthreads) */
 typedef struct {
     cfg_t c; int64_t N;
-    const double *r, *q, *sg, *K, *T, *t, *S; const uint8_t* is_put; const double* B0_in;
+    const double *r, *q, *sg, *K, *T, *t, *S, *tau_max; const uint8_t* is_put; const double* B0_in;
     double *price, *european, *B, *B0out; int32_t* iters; double* err;
     int64_t next; pthread_mutex_t mu;
 } job_t;
@@ -279,7 +396,8 @@ static void* worker(void* p) {
         if (b >= j->N) break;
         int64_t e = b + 64 < j->N ? b + 64 : j->N;
         for (int64_t i = b; i < e; ++i)
-            solve_one(&j->c, j->r[i], j->q[i], j->sg[i], j->K[i], j->T[i], j->t ? j->t[i] : 0.0, j->S[i], j->is_put[i],
+            solve_one(&j->c, j->r[i], j->q[i], j->sg[i], j->K[i], j->T[i], j->tau_max ? j->tau_max[i] : j->T[i],
+                      j->t ? j->t[i] : 0.0, j->S[i], j->is_put[i],
                       j->B0_in ? j->B0_in + i * nn : NULL, &j->price[i], &j->european[i],
                       j->B ? j->B + i * nn : NULL, j->B0out ? j->B0out + i * nn : NULL, &j->iters[i], &j->err[i]);
     }
@@ -291,12 +409,13 @@ int oracle_alo_price_batch(int solver, int use_derivative, int n, int l, int m, 
                            const double* T, const double* t, const double* S, const uint8_t* is_put,
                            const double* y_l, const double* w_l, const double* y_m, const double* w_m,
                            const double* B0_in, double* price, double* european, double* B, double* B0_out,
-                           int32_t* iters, double* err, int nthreads) {
+                           int32_t* iters, double* err, int nthreads, int seed_mode, const double* tau_max /* nullable: T */) {
     job_t j;
     memset(&j, 0, sizeof j);
     double* ct = (double*)malloc(sizeof(double) * (n + 1) * (n + 1));
     for (int i = 0; i <= n; ++i) for (int k = 0; k <= n; ++k) ct[i * (n + 1) + k] = cos(i * k * M_PI / n);
-    cfg_t c = {solver, use_derivative, n, l, m, max_iters, tol, eta, y_l, w_l, y_m, w_m, ct};
+    cfg_t c = {solver, use_derivative, n, l, m, max_iters, tol, eta, y_l, w_l, y_m, w_m, ct, seed_mode};
+    j.tau_max = tau_max;
     j.c = c; j.N = N; j.r = r; j.q = q; j.sg = sigma; j.K = K; j.T = T; j.t = t; j.S = S; j.is_put = is_put;
     j.B0_in = B0_in; j.price = price; j.european = european; j.B = B; j.B0out = B0_out; j.iters = iters; j.err = err;
     pthread_mutex_init(&j.mu, NULL);
@@ -310,8 +429,13 @@ int oracle_alo_price_batch(int solver, int use_derivative, int n, int l, int m, 
 }
 
 int oracle_qd_boundary_batch(int64_t N, const double* r, const double* q, const double* sigma, const double* K,
-                             const double* tau, const uint8_t* is_put, double* B) {
-    for (int64_t i = 0; i < N; ++i) B[i] = qd_boundary(tau[i], r[i], q[i], sigma[i], K[i], is_put[i]);
+                             const double* tau, const uint8_t* is_put, double* B, int seed_mode, int32_t* nfev /* nullable */) {
+    for (int64_t i = 0; i < N; ++i) {
+        int nf = 0;
+        if (seed_mode == 1 && tau[i] != 0) B[i] = hybr1_qd(tau[i], r[i], q[i], sigma[i], K[i], is_put[i], &nf);
+        else B[i] = qd_seed(seed_mode, tau[i], r[i], q[i], sigma[i], K[i], is_put[i]);
+        if (nfev) nfev[i] = nf;
+    }
     return 0;
 }
 

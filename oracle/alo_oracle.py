@@ -13,10 +13,11 @@ Clenshaw per node, sequential quadrature sums, the same stopping rule.
 Pinned against the live reference: tests/golden/ref_*.npz were produced by
 oracle/gen_golden.py running the unmodified reference in the dev container
 (numpy 2.3.5 / scipy 1.18.1); tests/test_oracle_golden.py checks this file against them.
-Known, documented deviation: the QD seed root is found by a safeguarded Newton iteration
-instead of MINPACK hybr (reference QDplusAmericanOptionSolver.py:73, xtol 1.49e-8); both
-land on the same root to <= ~1e-11 relative and the damped fixed point contracts that
-difference by 2^-J.
+The QD seed root follows the reference's root finder: `hybr1` below restates MINPACK hybrd for one
+unknown exactly as scipy.optimize.root(method="hybr", x0=K) drives it (reference
+QDplusAmericanOptionSolver.py:73) and returns the same iterate bit for bit
+(tests/test_oracle_golden.py::test_hybr1_equals_scipy_root); a safeguarded Newton iteration on the
+same residual is kept as `method="newton"` (the CUDA path's opt-in fast seed).
 
 Third-party arithmetic the reference leans on (versions unpinned upstream):
 scipy.stats.norm.cdf -> scipy.special.ndtr (used here directly), norm.pdf ->
@@ -207,16 +208,166 @@ def qd_residual(S, tau, r, q, sigma, K, is_put, want_deriv=False):
         return F, np.where(is_put, dp, dc)
 
 
-def qd_boundary(tau, r, q, sigma, K, is_put, max_newton=100):
+_EPSMCH = float(np.finfo(float).eps)
+
+
+def hybr1(f, x0, xtol=1.49012e-08, factor=100.0, maxfev=400, epsfcn=_EPSMCH):
+    """MINPACK `hybrd` (Powell hybrid: forward-difference Jacobian, dogleg step inside a trust region, Broyden rank-one
+    updates) specialised to ONE unknown, with the settings scipy.optimize.root(fun, x0, method="hybr") passes by default:
+    xtol = 1.49012e-8, maxfev = 200 (n+1), ml = mu = n-1, epsfcn = machine eps, mode = 1 (diag from the first Jacobian),
+    factor = 100.  That call is how the reference finds its QD seed (QDplusAmericanOptionSolver.py:73); MINPACK is a
+    third-party dependency absent from /root/reference (scipy 1.18.1 ships a C translation), so this restates the published
+    algorithm.  With n = 1 the QR factorisation is r = -J, q = -1 (Householder of a 1 x 1 matrix), every enorm is |.|, r1updt
+    and r1mpyq apply no rotation.  Returns (x, nfev, info); x is what `root(...).x[0]` holds whatever `info` says (the
+    reference never looks at `success`).  Bit-identical to scipy on 12 000 seed problems
+    (tests/test_oracle_golden.py::test_hybr1_equals_scipy_root checks a sample); scipy's own nfev counts two extra shape-probing calls."""
+    sqrt = np.sqrt
+    x = float(x0)
+    fvec = f(x)
+    nfev = 1
+    fnorm = abs(fvec)
+    it = 1
+    ncsuc = ncfail = nslow1 = nslow2 = 0
+    diag = delta = xnorm = 0.0
+    eps = float(sqrt(max(epsfcn, _EPSMCH)))
+    while True:
+        jeval = True
+        h = eps * abs(x)                          # fdjac1
+        if h == 0.0:
+            h = eps
+        J = (f(x + h) - fvec) / h
+        nfev += 1
+        acn = abs(J)                              # qrfac: rdiag = -J, acnorm = |J|
+        if it == 1:
+            diag = acn if acn != 0.0 else 1.0
+            xnorm = abs(diag * x)
+            delta = factor * xnorm
+            if delta == 0.0:
+                delta = factor
+        if J != 0.0:
+            qtf, r, Q = -fvec, -J, -1.0           # (q transpose) fvec with q = -1
+        else:
+            qtf, r, Q = fvec, -0.0, 1.0
+        diag = max(diag, acn)
+        while True:
+            temp = r                              # dogleg: Gauss-Newton direction
+            if temp == 0.0:
+                temp = _EPSMCH * abs(r)
+                if temp == 0.0:
+                    temp = _EPSMCH
+            xg = qtf / temp
+            qnorm = abs(diag * xg)
+            if qnorm <= delta:
+                p = xg
+            else:                                 # scaled gradient direction / dogleg point
+                wa1 = (r * qtf) / diag
+                gnorm = abs(wa1)
+                sgnorm = 0.0
+                alpha = delta / qnorm
+                if gnorm != 0.0:
+                    wa1 = (wa1 / gnorm) / diag
+                    t2 = abs(r * wa1)
+                    sgnorm = (gnorm / t2) / t2
+                    alpha = 0.0
+                    if sgnorm < delta:
+                        bnorm = abs(qtf)
+                        tt = (bnorm / gnorm) * (bnorm / qnorm) * (sgnorm / delta)
+                        tt = tt - (delta / qnorm) * (sgnorm / delta) ** 2 + float(sqrt(
+                            (tt - (delta / qnorm)) ** 2 + (1.0 - (delta / qnorm) ** 2) * (1.0 - (sgnorm / delta) ** 2)))
+                        alpha = ((delta / qnorm) * (1.0 - (sgnorm / delta) ** 2)) / tt
+                tt = (1.0 - alpha) * min(sgnorm, delta)
+                p = tt * wa1 + alpha * xg
+            w1 = -p
+            w2 = x + w1
+            w3 = diag * w1
+            pnorm = abs(w3)
+            if it == 1:
+                delta = min(delta, pnorm)
+            w4 = f(w2)
+            nfev += 1
+            fnorm1 = abs(w4)
+            actred = -1.0
+            if fnorm1 < fnorm:
+                actred = 1.0 - (fnorm1 / fnorm) ** 2
+            w3 = qtf + r * w1
+            temp = abs(w3)
+            prered = 0.0
+            if temp < fnorm:
+                prered = 1.0 - (temp / fnorm) ** 2
+            ratio = 0.0
+            if prered > 0.0:
+                ratio = actred / prered
+            if ratio < 0.1:
+                ncsuc = 0
+                ncfail += 1
+                delta = 0.5 * delta
+            else:
+                ncfail = 0
+                ncsuc += 1
+                if ratio >= 0.5 or ncsuc > 1:
+                    delta = max(delta, pnorm / 0.5)
+                if abs(ratio - 1.0) <= 0.1:
+                    delta = pnorm / 0.5
+            if ratio >= 1e-4:                     # successful iteration
+                x = w2
+                w2 = diag * x
+                fvec = w4
+                xnorm = abs(w2)
+                fnorm = fnorm1
+                it += 1
+            nslow1 += 1
+            if actred >= 0.001:
+                nslow1 = 0
+            if jeval:
+                nslow2 += 1
+            if actred >= 0.1:
+                nslow2 = 0
+            if delta <= xtol * xnorm or fnorm == 0.0:
+                return x, nfev, 1
+            info = 0
+            if nfev >= maxfev:
+                info = 2
+            if 0.1 * max(0.1 * delta, pnorm) <= _EPSMCH * xnorm:
+                info = 3
+            if nslow2 == 5:
+                info = 4
+            if nslow1 == 10:
+                info = 5
+            if info != 0:
+                return x, nfev, info
+            if ncfail == 2:
+                break                             # recompute the Jacobian by forward differences
+            sm = Q * w4                           # Broyden rank-one update of r = -J (and of qtf)
+            w2 = (sm - w3) / pnorm
+            w1 = diag * ((diag * w1) / pnorm)
+            if ratio >= 1e-4:
+                qtf = sm
+            r = r + w2 * w1
+            jeval = False
+
+
+def qd_boundary(tau, r, q, sigma, K, is_put, max_newton=100, method="hybr"):
     """QDplusAmericanOptionSolver.py:69-76: root of the QD residual started from x0 = K; tau == 0 -> B_at_zero.
 
-    The reference calls scipy.optimize.root (MINPACK hybr); this restatement uses Newton with the
-    analytic derivative, a positivity safeguard (halve towards 0 / step-limit), a relative stop of 1e-10 (quadratic
-    convergence makes the accepted iterate exact to rounding) and a stall test for flat residuals.
+    method="hybr" (default): the reference's own root finder, scipy.optimize.root(hybr, x0=K), restated by `hybr1`, one
+    scalar problem per element.  method="newton": Newton with the analytic derivative, a positivity safeguard (halve towards
+    0 / step-limit), a relative stop of 1e-10 (quadratic convergence makes the accepted iterate exact to rounding) and a stall
+    test for flat residuals — vectorised, the CUDA path's opt-in fast seed.
     All arguments broadcast; returns an array.
     """
     tau, r, q, sigma, K = np.broadcast_arrays(*[np.asarray(a, dtype=float) for a in (tau, r, q, sigma, K)])
     is_put = np.broadcast_to(np.asarray(is_put, dtype=bool), tau.shape)
+    if method == "hybr":
+        out = np.empty(tau.shape)
+        X0 = B_at_zero(r, q, K, is_put)
+        with np.errstate(all="ignore"):
+            for ix in np.ndindex(tau.shape):
+                if tau[ix] == 0:
+                    out[ix] = X0[ix]
+                    continue
+                a = (tau[ix], r[ix], q[ix], sigma[ix], K[ix], is_put[ix])
+                out[ix] = hybr1(lambda S: float(qd_residual(np.float64(S), *a)), K[ix])[0]
+        return out
     S = K.astype(float).copy()
     act = tau > 0
     prev = np.full(S.shape, np.inf)
@@ -402,22 +553,24 @@ def f_and_fprime(solver, use_derivative, B, tau, T, r, q, sigma, K, X, is_put, y
 
 
 def solve_boundary(solver, r, q, sigma, K, T, is_put, n, l, iter_tol=1e-5, max_iters=200,
-                   use_derivative=False, eta=0.5, B0=None):
+                   use_derivative=False, eta=0.5, B0=None, seed="hybr", rule_l=None):
     """compute_exercise_boundary + iterate_once(_foreach_tau), FastAmericanOptionSolverBase.py:105-165.
 
     Jacobi sweep on all nodes from the previous iterate, B_i += eta (B_i - f)/(f' - 1) with f' = 0 unless
     use_derivative, node tau == 0 pinned to X, stop when ||B_old - B_new||_2 <= tol or count == max_iters.
+    T is the end of the collocation domain, i.e. the `tau_max` attribute (= maturity unless changed, Base.py:28, used at :185, :223).
+    seed: root finder of the QD seed ("hybr" as upstream, or "newton"); rule_l: (y, w) on [-1, 1] replacing leggauss(l) (opt-in).
     Returns dict(tau, B0, B, iters, err, iter_errs).
     """
     r, q, sigma, K, T = (np.ascontiguousarray(a, dtype=float) for a in (r, q, sigma, K, T))
     is_put = np.ascontiguousarray(is_put, dtype=bool)
     P = r.shape[0]
-    y, w = leggauss(l)                                                # Base.py:175
+    y, w = leggauss(l) if rule_l is None else (np.asarray(rule_l[0], dtype=float), np.asarray(rule_l[1], dtype=float))   # Base.py:175
     c = cheb_points(n)
     tau = to_orig_point(c[None, :], 0.0, T[:, None])                  # Base.py:221-223
     X = B_at_zero(r, q, K, is_put)
     if B0 is None:
-        B0 = qd_boundary(tau, r[:, None], q[:, None], sigma[:, None], K[:, None], is_put[:, None])   # Base.py:258-265
+        B0 = qd_boundary(tau, r[:, None], q[:, None], sigma[:, None], K[:, None], is_put[:, None], method=seed)   # Base.py:258-265
     B = np.array(B0, dtype=float, copy=True)
     iters = np.zeros(P, dtype=np.int64)
     err = np.ones(P)
@@ -444,17 +597,19 @@ def solve_boundary(solver, r, q, sigma, K, T, is_put, n, l, iter_tol=1e-5, max_i
     return dict(tau=tau, B0=np.asarray(B0, dtype=float), B=B, iters=iters, err=err, iter_errs=iter_errs, X=X)
 
 
-def price_with_boundary(B, T, t, S, r, q, sigma, K, is_put, m):
-    """american_value_with_known_boundary + v_integrand_12, FastAmericanOptionSolverBase.py:92-103, 211-219."""
+def price_with_boundary(B, T, t, S, r, q, sigma, K, is_put, m, tau_max=None, rule_m=None):
+    """american_value_with_known_boundary + v_integrand_12, FastAmericanOptionSolverBase.py:92-103, 211-219.
+    tau_max: end of the boundary's collocation domain (Base.py:28,185), default T; rule_m: (y, w) replacing leggauss(m)."""
     r, q, sigma, K, T, t, S = (np.ascontiguousarray(a, dtype=float) for a in (r, q, sigma, K, T, t, S))
     is_put = np.ascontiguousarray(is_put, dtype=bool)
     X = B_at_zero(r, q, K, is_put)
     tau = T - t
+    Tc = T if tau_max is None else np.ascontiguousarray(np.broadcast_to(np.asarray(tau_max, dtype=float), T.shape))
     eur = np.where(is_put, european_put_value(tau, S, r, q, sigma, K), european_call_value(tau, S, r, q, sigma, K))
-    y, w = leggauss(m)
+    y, w = leggauss(m) if rule_m is None else (np.asarray(rule_m[0], dtype=float), np.asarray(rule_m[1], dtype=float))
     with np.errstate(all="ignore"):
         H = np.square(np.log(B / X[:, None]))
-        u, Bu = interp_boundary(H, tau[:, None], T, X, is_put, y)
+        u, Bu = interp_boundary(H, tau[:, None], Tc, X, is_put, y)
         u, Bu = u[:, 0, :], Bu[:, 0, :]
         tt, SS, rr, qq, ss, KK = (a[:, None] for a in (tau, S, r, q, sigma, K))
         s = tt - u
@@ -470,8 +625,10 @@ def price_with_boundary(B, T, t, S, r, q, sigma, K, is_put, m):
 
 
 def alo_price_batch(solver, r, q, sigma, K, T, S, is_put, t=None, n=12, l=24, m=48, iter_tol=1e-5, max_iters=200,
-                    use_derivative=False, eta=0.5, B0=None, chunk=4096):
+                    use_derivative=False, eta=0.5, B0=None, chunk=4096, seed="hybr", rule_l=None, rule_m=None, tau_max=None):
     """FastAmericanOptionSolver.solve(t, s0) for a batch, FastAmericanOptionSolverBase.py:49-76.
+    seed / rule_l / rule_m / tau_max: see solve_boundary and price_with_boundary (tau_min stays 0: any other value makes
+    upstream return NaN after one sweep, because z = sqrt(4 (u - tau_min)/(tau_max - tau_min)) - 1 meets u < tau_min).
 
     q == 0 calls take the European shortcut (:50-53): price = european call, iters = 0, err = 1e6 (the
     constructor's initial values, :41-43), boundary arrays NaN.
@@ -489,11 +646,13 @@ def alo_price_batch(solver, r, q, sigma, K, T, S, is_put, t=None, n=12, l=24, m=
         out["price"][short] = e
         out["european"][short] = e
     idx = np.nonzero(~short)[0]
+    Tc = T if tau_max is None else np.broadcast_to(np.asarray(tau_max, dtype=float), (P,)).copy()
     for c0 in range(0, len(idx), chunk):
         ix = idx[c0:c0 + chunk]
-        sb = solve_boundary(solver, r[ix], q[ix], sigma[ix], K[ix], T[ix], is_put[ix], n, l, iter_tol, max_iters,
-                            use_derivative, eta, None if B0 is None else np.asarray(B0)[ix])
-        price, eur = price_with_boundary(sb["B"], T[ix], t[ix], S[ix], r[ix], q[ix], sigma[ix], K[ix], is_put[ix], m)
+        sb = solve_boundary(solver, r[ix], q[ix], sigma[ix], K[ix], Tc[ix], is_put[ix], n, l, iter_tol, max_iters,
+                            use_derivative, eta, None if B0 is None else np.asarray(B0)[ix], seed=seed, rule_l=rule_l)
+        price, eur = price_with_boundary(sb["B"], T[ix], t[ix], S[ix], r[ix], q[ix], sigma[ix], K[ix], is_put[ix], m,
+                                         tau_max=Tc[ix], rule_m=rule_m)
         out["price"][ix] = price
         out["european"][ix] = eur
         for k in ("B", "B0", "tau", "iters", "err", "iter_errs"):

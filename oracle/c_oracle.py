@@ -34,13 +34,17 @@ def _d(a):
 
 
 def alo_price_batch(solver, r, q, sigma, K, T, S, is_put, t=None, n=12, l=24, m=48, iter_tol=1e-5, max_iters=200,
-                    use_derivative=False, eta=0.5, B0=None, nthreads=None):
+                    use_derivative=False, eta=0.5, B0=None, nthreads=None, seed="hybr", rule_l=None, rule_m=None, tau_max=None):
+    """seed: "hybr" (the reference's root finder, default) or "newton"; rule_l / rule_m: (y, w) on [-1, 1] replacing
+    leggauss(l) / leggauss(m) (sizes l, m); tau_max: per-option end of the collocation domain (Base.py:28), default T."""
     r, q, sigma, K, T, S = (_d(np.atleast_1d(a)) for a in (r, q, sigma, K, T, S))
     N = r.shape[0]
     ip = np.ascontiguousarray(np.atleast_1d(is_put), dtype=np.uint8)
     t = np.zeros(N) if t is None else _d(np.broadcast_to(np.asarray(t, dtype=float), (N,)))
-    yl, wl = leggauss(l)
-    ym, wm = leggauss(m)
+    yl, wl = leggauss(l) if rule_l is None else rule_l
+    ym, wm = leggauss(m) if rule_m is None else rule_m
+    assert len(yl) == l and len(ym) == m
+    tm = None if tau_max is None else _d(np.broadcast_to(np.asarray(tau_max, dtype=float), (N,)).copy())
     out = dict(price=np.empty(N), european=np.empty(N), B=np.empty((N, n + 1)), B0=np.empty((N, n + 1)),
                iters=np.empty(N, dtype=np.int32), err=np.empty(N))
     B0c = None if B0 is None else _d(B0)
@@ -51,17 +55,19 @@ def alo_price_batch(solver, r, q, sigma, K, T, S, is_put, t=None, n=12, l=24, m=
         ctypes.c_int(m), ctypes.c_int(max_iters), ctypes.c_double(iter_tol), ctypes.c_double(eta), ctypes.c_int64(N),
         _p(r), _p(q), _p(sigma), _p(K), _p(T), _p(t), _p(S), _p(ip), _p(_d(yl)), _p(_d(wl)), _p(_d(ym)), _p(_d(wm)),
         _p(B0c), _p(out["price"]), _p(out["european"]), _p(out["B"]), _p(out["B0"]), _p(out["iters"]), _p(out["err"]),
-        ctypes.c_int(nthreads))
+        ctypes.c_int(nthreads), ctypes.c_int(1 if seed == "hybr" else 0), _p(tm))
     assert rc == 0
     return out
 
 
-def qd_boundary_batch(tau, r, q, sigma, K, is_put):
+def qd_boundary_batch(tau, r, q, sigma, K, is_put, seed="hybr", return_nfev=False):
     tau, r, q, sigma, K = (_d(a) for a in np.broadcast_arrays(tau, r, q, sigma, K))
     ip = np.ascontiguousarray(np.broadcast_to(is_put, tau.shape), dtype=np.uint8)
     B = np.empty(tau.shape)
-    lib().oracle_qd_boundary_batch(ctypes.c_int64(tau.size), _p(r), _p(q), _p(sigma), _p(K), _p(tau), _p(ip), _p(B))
-    return B
+    nf = np.zeros(tau.shape, dtype=np.int32)
+    lib().oracle_qd_boundary_batch(ctypes.c_int64(tau.size), _p(r), _p(q), _p(sigma), _p(K), _p(tau), _p(ip), _p(B),
+                                   ctypes.c_int(1 if seed == "hybr" else 0), _p(nf))
+    return (B, nf) if return_nfev else B
 
 
 def european_batch(tau, S, r, q, sigma, K, is_put):
@@ -98,3 +104,25 @@ def cn_put_batch(r, q, sigma, K, T, S0, n_space, max_dt, mode, omega=1.2, tol=1e
     if return_state:
         return (out, err, it)
     return out
+
+
+def seed_conditioning(T, r, q, sigma, K, is_put, n, tau_max=None):
+    """How far the reference's own QD seed (hybr from x0 = K at every collocation node) moves when the normal cdf inside its
+    residual changes by 1-2 ulp: max over nodes and over probes k = +-1, +-2 of |B0_k / B0_0 - 1|, per option.  A few 1e-16
+    where the residual is well conditioned; up to ~1e-6 where K - S - p cancels catastrophically (tiny maturities with
+    X = rK/q << K) — there the reference's seed is an accident of its own rounding and no other implementation (scipy on another
+    CPU included) can reproduce it better than this number."""
+    T, r, q, sigma, K = (_d(np.atleast_1d(a)) for a in (T if tau_max is None else tau_max, r, q, sigma, K))
+    c = np.cos(np.arange(n + 1) * np.pi / n)
+    tau = np.square(c + 1)[None, :] * T[:, None] / 4
+    a = (tau, r[:, None], q[:, None], sigma[:, None], K[:, None], np.atleast_1d(is_put).astype(bool)[:, None])
+    try:
+        base = qd_boundary_batch(*a)
+        spread = np.zeros(T.shape[0])
+        for k in (1, -1, 2, -2):
+            lib().oracle_set_seed_probe(ctypes.c_int(k))
+            with np.errstate(all="ignore"):
+                spread = np.fmax(spread, np.nanmax(np.abs(qd_boundary_batch(*a) / base - 1), axis=1))
+    finally:
+        lib().oracle_set_seed_probe(ctypes.c_int(0))
+    return spread

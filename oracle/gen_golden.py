@@ -76,6 +76,9 @@ def _otype(is_put):
 
 def solve_one(args):
     """One reference solve. args = (solver, r,q,sigma,K,T,S,t,is_put, n,l,m,tol,max_iters,deriv)."""
+    tau_max = tau_min = None
+    if len(args) == 17:            # gen_domain: the tau_max / tau_min attributes (Base.py:28-29)
+        args, (tau_max, tau_min) = args[:15], args[15:]
     (solver, r, q, sigma, K, T, S, t, is_put, n, l, m, tol, max_iters, deriv) = args
     cls = refA.FastAmericanOptionSolverA if solver == "A" else refB.FastAmericanOptionSolverB
     s = cls(float(r), float(q), float(sigma), float(K), float(T), _otype(is_put))
@@ -86,6 +89,10 @@ def solve_one(args):
     s.iter_tol = float(tol)
     s.max_iters = int(max_iters)
     s.use_derivative = bool(deriv)
+    if tau_max is not None:
+        s.tau_max = float(tau_max)
+    if tau_min is not None:
+        s.tau_min = float(tau_min)
     t0 = time.perf_counter()
     price = float(s.solve(float(t), float(S)))
     dt = time.perf_counter() - t0
@@ -319,6 +326,44 @@ def gen_cheb(pool):
     print("cheb ok")
 
 
+def gen_domain(pool):
+    """The collocation-domain knobs tau_max / tau_min (FastAmericanOptionSolverBase.py:28-29, consumed at :185 and :223):
+    tau_max above and below the maturity, with t != 0, Solver A and B, puts and calls; tau_min != 0 (upstream: NaN, 1 sweep)."""
+    base = [
+        (0.04, 0.01, 0.2, 100.0, 3.0, 80.0, 0.0, True),
+        (0.04, 0.01, 0.2, 100.0, 3.0, 80.0, 1.0, True),
+        (0.04, 0.06, 0.2, 100.0, 3.0, 120.0, 0.0, False),
+        (0.03, 0.07, 0.3, 90.0, 0.5, 85.0, 0.1, True),
+        (0.06, 0.02, 0.25, 100.0, 1.0, 110.0, 0.0, False),
+        (0.05, 0.05, 0.3, 100.0, 2.0, 100.0, 0.5, True),
+    ]
+    jobs = []
+    for (r, q, sig, K, T, S, t, put) in base:
+        for solver, n, l, m in (("A", 12, 32, 64), ("B", 12, 24, 48), ("A", 16, 40, 50)):
+            for mult in (1.5, 0.7, 1.0000001):
+                jobs.append((solver, r, q, sig, K, T, S, t, put, n, l, m, 1e-5, 60, False, mult * T, 0.0))
+    for (r, q, sig, K, T, S, t, put) in base[:3]:
+        jobs.append(("A", r, q, sig, K, T, S, t, put, 12, 24, 48, 1e-5, 60, False, T, 0.1))
+        jobs.append(("A", r, q, sig, K, T, S, t, put, 12, 24, 48, 1e-5, 60, False, T, -0.1))
+    res = pool.map(solve_one, jobs, chunksize=1)
+    nmax = max(j[9] for j in jobs) + 1
+
+    def pad(a):
+        o = np.full(nmax, np.nan)
+        o[:len(a)] = a
+        return o
+    names = ("solver", "in_r", "in_q", "in_sigma", "in_K", "in_T", "in_S", "in_t", "in_is_put", "n", "l", "m", "iter_tol",
+             "max_iters", "use_derivative", "tau_max", "tau_min")
+    out = {k: np.array([j[i] for j in jobs]) for i, k in enumerate(names)}
+    for k in ("price", "european", "iters", "err"):
+        out[k] = np.array([r_[k] for r_ in res])
+    for k in ("B", "B0", "tau"):
+        out[k] = np.array([pad(r_[k]) for r_ in res])
+    out["versions"] = np.array(VERSIONS)
+    np.savez(os.path.join(OUT, "ref_domain.npz"), **out)
+    print("domain: %d solves, nan prices %d (expected %d)" % (len(jobs), np.isnan(out["price"]).sum(), 6))
+
+
 def _cn_one(args):
     r, q, sig, K, T, S0, N, max_dt, psor, tol, max_iter, omega = args
     s = refcn.CNOptionSolver(r, q, sig, K, T)
@@ -538,7 +583,7 @@ def gen_stress(pool):
     print("stress: %d options, nan %d, err>=1e-2 %d" % (len(idx), np.isnan(out["price"]).sum(), (out["err"] >= 1e-2).sum()))
 
 
-GENS = dict(c1=gen_c1, european=gen_european, cheb=gen_cheb, qd=gen_qd, stage=gen_stage, misc=gen_misc, cn=gen_cn, cn_state=gen_cn_state,
+GENS = dict(c1=gen_c1, european=gen_european, cheb=gen_cheb, qd=gen_qd, stage=gen_stage, misc=gen_misc, cn=gen_cn, cn_state=gen_cn_state, domain=gen_domain,
             c3=gen_c3, c2=gen_c2, bs=gen_bs, c5=gen_c5, stress=gen_stress)
 
 

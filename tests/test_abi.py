@@ -28,7 +28,8 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_cfg_struct_layout_matches_header():
-    assert ctypes.sizeof(_lib.FaopCfg) == 6 * 4 + 2 * 8 + 2 * 4
+    assert ctypes.sizeof(_lib.FaopCfg) == 6 * 4 + 2 * 8 + 2 * 4 + 8 and _lib.FaopCfg.tau_max.offset == 48
+    assert ctypes.sizeof(_lib.FaopCnExtra) == 4 * 8
     assert ctypes.sizeof(_lib.FaopSurface) == 9 * 8 + 4 * 4
 
 

@@ -22,6 +22,19 @@ def _inputs(g, ix=slice(None)):
     return [g["in_" + k][ix] for k in ("r", "q", "sigma", "K", "T", "S", "is_put")]
 
 
+def _flips_are_ties(out, ref, ps, tol, tag=""):
+    """Options whose sweep count differs from the checker's: every one must be a tie of the stopping rule
+    `while iter_err > iter_tol` (Base.py:119) — the error of the side that stopped one sweep earlier lies within 1e-9 absolute
+    (1e-4 relative) of iter_tol, the size of the rounding-level difference between two correct boundary iterates — and the
+    counts differ by exactly one.  Returns how many there were."""
+    flip = ps & (out["iters"] != ref["iters"])
+    for i in np.nonzero(flip)[0]:
+        early = out if out["iters"][i] < ref["iters"][i] else ref
+        assert abs(int(out["iters"][i]) - int(ref["iters"][i])) == 1, (tag, i, out["iters"][i], ref["iters"][i])
+        assert abs(early["err"][i] - tol) <= 1e-4 * tol, (tag, i, early["err"][i])
+    return int(flip.sum())
+
+
 def _check(out, g, ix=slice(None), strict_iters=True, tag=""):
     ps = parity_set({k: g[k][ix] for k in ("price", "err")})
     nn = out["B"].shape[1]
@@ -44,7 +57,7 @@ def test_c1_testA(kernel):
     assert abs(out["european"][0] - 17.78865238332743) <= 1e-12
     assert out["iters"][0] == 19 and abs(out["err"][0] - 6.763708524497298e-06) < 1e-12
     assert np.max(np.abs(out["tau"] - g["tau"])) <= 1e-15
-    assert np.max(np.abs(out["B0"] / g["B0"] - 1)) <= 1e-9
+    assert np.max(np.abs(out["B0"] / g["B0"] - 1)) <= 1e-11         # hybrd restated on the device: the reference's own iterate
 
 
 @pytest.mark.parametrize("kernel", KERNELS)
@@ -54,7 +67,11 @@ def test_c2_golden(kernel):
     out = _np(batch.price_batch(*_inputs(g), cfg=cfg))
     ps = _check(out, g, tag="c2")
     assert ps.sum() >= 4000 and len(g["price"]) == 4096      # the first 4,096 C2 options through the live reference
-    assert np.nanmax(np.abs(out["B0"] / g["B0"] - 1)[ps]) <= 1e-8        # Newton vs MINPACK hybr (xtol 1.49e-8)
+    seed = np.abs(out["B0"] / g["B0"] - 1)[ps]      # hybrd on both sides; libdevice vs scipy/numpy in the residual's last bits
+    assert np.nanmax(seed) <= 1e-8 and np.nanmedian(seed) <= 1e-12
+    if kernel == 0:     # the opt-in Newton seed (FAOP_FLAG_SEED_NEWTON) meets the same bars on this workload
+        outn = _np(batch.price_batch(*_inputs(g), cfg=AloConfig(kernel=kernel, seed="newton", **wl.C2_CFG)))
+        _check(outn, g, tag="c2 newton seed")
     assert np.max(np.abs(out["european"] - g["european"])) <= 1e-11
     assert np.max(np.abs(out["err"] / g["err"] - 1)[ps]) <= 1e-6
     # borrowed reference seeds isolate the iteration itself
@@ -71,11 +88,11 @@ def test_c3_golden(kernel):
     out = _np(batch.price_batch(*_inputs(g), cfg=cfg, B0=g["B0"]))
     ps = _check(out, g, tag="c3 borrowed")
     assert ps.all()
+    # own seeds: every option, both bars, identical sweep counts — including the extreme call (q ~ 3e-4, X = rK/q ~ 270 K) on
+    # which hybrd exits on slow progress far from the root: the device runs the same hybrd and stops at the same iterate
     out = _np(batch.price_batch(*_inputs(g), cfg=cfg))
-    seed_ok = np.nanmax(np.abs(out["B0"] / g["B0"] - 1), axis=1) <= 1e-6     # hybr misses one extreme call's root
-    assert seed_ok.sum() >= len(seed_ok) - 3
-    _check({k: v[seed_ok] for k, v in out.items()}, {k: g[k][seed_ok] for k in ("price", "err", "B", "iters")}, tag="c3")
-    assert np.max(np.abs(out["price"] - g["price"])) <= PRICE_ABS_TOL
+    ps = _check(out, g, tag="c3 own seeds")
+    assert ps.all() and np.nanmax(np.abs(out["B0"] / g["B0"] - 1)) <= 1e-8
 
 
 @pytest.mark.parametrize("kernel", KERNELS)
@@ -89,7 +106,11 @@ def test_misc_variants(kernel):
         ix = np.nonzero(sel)[0]
         cfg = AloConfig(str(k[0]), int(k[1]), int(k[2]), int(k[3]), float(k[4]), int(k[5]), bool(k[6]), kernel=kernel)
         out = _np(batch.price_batch(*_inputs(m, ix), t=m["in_t"][ix], cfg=cfg))
-        if str(k[0]) == "B" and bool(k[6]):      # reference diverges to NaN: NaN-for-NaN, loosely
+        if str(k[0]) == "B" and bool(k[6]):      # reference diverges to NaN: NaN for NaN
+            # exact wherever the reference is NaN within its first 8 sweeps (the blow-up is a few sweeps of f' ~ 1, not chaos);
+            # beyond that the NaN onset depends on the last bits of a diverging iterate
+            early = np.isnan(m["price"][ix]) & (m["iters"][ix] <= 8)
+            assert early.sum() >= 8 and np.isnan(out["price"][early]).all() and np.array_equal(out["iters"][early], m["iters"][ix][early])
             assert (np.isnan(out["price"]) == np.isnan(m["price"][ix])).mean() >= 0.9
             continue
         _check(out, m, ix, tag="misc %s" % (k,))
@@ -129,11 +150,11 @@ def test_qd_leaf():
     q = load_golden("ref_qd.npz")
     B = batch.qd_boundary_batch(q["in_tau"], q["in_r"], q["in_q"], q["in_sigma"], q["in_K"], q["in_is_put"]).cpu().numpy()
     rel = np.abs(B / q["B"] - 1)
-    assert rel.max() <= 1e-8 and np.median(rel) <= 1e-13
+    assert rel.max() <= 1e-8 and np.median(rel) <= 1e-14      # hybrd on the device against the reference's scipy call
     from oracle import c_oracle as co
     Bo = co.qd_boundary_batch(q["in_tau"], q["in_r"], q["in_q"], q["in_sigma"], q["in_K"], q["in_is_put"])
-    # same Newton rule on both sides; flat residuals (tiny tau, r >> q calls) pin the root only to ~1e-10
-    assert np.max(np.abs(B / Bo - 1)) <= 1e-9 and np.median(np.abs(B / Bo - 1)) <= 1e-14
+    # hybrd on both sides; flat residuals (tiny tau, r >> q calls) amplify the last bits of erfc / exp
+    assert np.max(np.abs(B / Bo - 1)) <= 1e-8 and np.median(np.abs(B / Bo - 1)) <= 1e-14
     Bc = batch.qd_boundary_batch(q["curve_tau"], float(q["curve_r"]), float(q["curve_q"]), float(q["curve_sigma"]),
                                  float(q["curve_K"]), True).cpu().numpy()
     assert np.max(np.abs(Bc / q["curve_B"] - 1)) <= 1e-11
@@ -146,7 +167,7 @@ def test_qd_leaf():
     n = len(q["price"])
     P, Bd = batch.qd_price_batch(q["in_tau"][:n], q["price_S"], q["in_r"][:n], q["in_q"][:n], q["in_sigma"][:n], q["in_K"][:n],
                                  q["in_is_put"][:n])
-    assert np.max(np.abs(P.cpu().numpy() - q["price"]) / np.maximum(1.0, np.abs(q["price"]))) <= 1e-6
+    assert np.max(np.abs(P.cpu().numpy() - q["price"]) / np.maximum(1.0, np.abs(q["price"]))) <= 1e-8
     assert np.max(np.abs(Bd.cpu().numpy() / q["price_boundary"] - 1)) <= 1e-8
     P, Bd = batch.qd_price_batch(0.000870786986, 30.543317986992072, float(q["curve_r"]), float(q["curve_q"]),
                                  float(q["curve_sigma"]), float(q["curve_K"]), True)
@@ -216,7 +237,6 @@ def test_device_math():
     assert torch.isnan(batch.dev_math_batch(6, [float("nan")])).all()
     a = np.concatenate([10 ** g.uniform(-300, 300, 100000), g.uniform(0.5, 2.0, 200000), 1 + g.uniform(-1e-6, 1e-6, 1000), [1.0]])
     got = batch.dev_math_batch(10, a).cpu().numpy()
-    assert np.max(np.abs(got - np.log(a)) / np.maximum(np.abs(np.log(a)), 1e-300)) <= 5e-15 or True
     err = np.abs(got - np.log(a))
     assert np.max(err / np.maximum(np.abs(np.log(a)), 2.3e-16)) <= 4.0     # <= 4 ulp-ish (absolute 2.3e-16 floor near ln 1)
     bad = batch.dev_math_batch(10, [0.0, -1.0, float("inf"), float("nan"), 1e-310]).cpu().numpy()
@@ -251,7 +271,7 @@ def test_vs_c_oracle_32k():
         assert ps.sum() >= 0.99 * N
         assert np.max(np.abs(out["price"] - ref["price"])[ps]) <= PRICE_ABS_TOL
         assert np.nanmax(np.abs(out["B"] / ref["B"] - 1)[ps]) <= BOUNDARY_REL_TOL
-        assert (out["iters"][ps] != ref["iters"][ps]).sum() <= 1          # a rounding-level flip at the 1e-5 threshold
+        assert _flips_are_ties(out, ref, ps, 1e-5, "c2 32k") <= 3           # rounding-level ties at the 1e-5 threshold only
         assert np.array_equal(np.isnan(out["price"]), np.isnan(ref["price"]))
 
 
@@ -276,7 +296,7 @@ def test_solver_b_vs_c_oracle():
             tag = (cfgk["n"], kernel, flag)
             assert np.max(np.abs(out["price"] - ref["price"])[ps]) <= PRICE_ABS_TOL, tag
             assert np.nanmax(np.abs(out["B"] / ref["B"] - 1)[ps]) <= BOUNDARY_REL_TOL, tag
-            assert (out["iters"][ps] != ref["iters"][ps]).sum() <= 2, tag
+            assert _flips_are_ties(out, ref, ps, cfgk["iter_tol"], tag) <= 3, tag
             assert np.array_equal(np.isnan(out["price"]), np.isnan(ref["price"])), tag
 
 
@@ -295,7 +315,7 @@ def test_solver_a_derivative_vs_c_oracle():
         out = _np(batch.price_batch(*a, cfg=AloConfig(kernel=kernel, **cfgk)))
         assert np.max(np.abs(out["price"] - ref["price"])[ps]) <= PRICE_ABS_TOL, kernel
         assert np.nanmax(np.abs(out["B"] / ref["B"] - 1)[ps]) <= BOUNDARY_REL_TOL, kernel
-        assert (out["iters"][ps] != ref["iters"][ps]).sum() <= 2, kernel
+        assert _flips_are_ties(out, ref, ps, cfgk["iter_tol"], kernel) <= 3, kernel
         assert (np.isnan(out["price"]) != np.isnan(ref["price"])).sum() <= 2, kernel
 
 
@@ -588,12 +608,13 @@ def test_stress_ranges_vs_c_oracle():
     """Outside the comfortable ranges: low vol x long T (Solver A diverges there), q > r, deep ITM/OTM spots,
     tiny maturities, r == q, r or q == 0.  On the parity set the bars hold; elsewhere CUDA and oracle must agree on 'diverged'.
 
-    Seeds: for tiny maturities with q >> r (X = rK/q << K) the QD residual (QDplusAmericanOptionSolver.py:110-125) cancels
-    catastrophically in K - S - p and its root is only defined to ~1e-9..1e-6 relative in FP64 -- MINPACK hybr, the oracle's
-    cold-started Newton and the kernel's warm-started Newton each stop somewhere inside that band (checked against a 40-digit
-    root), and with the absolute stopping rule (Base.py:119) only ~8 sweeps run, so the seed noise survives in the boundary.
-    Hence two passes: with the oracle's seeds borrowed (B0_in) the bars are unconditional; with the kernel's own seeds the
-    boundary may differ by the seed difference and no more (the damped sweep contracts it)."""
+    Seeds: both sides run the reference's root finder (hybrd restated).  For tiny maturities with q >> r (X = rK/q << K) the QD
+    residual (QDplusAmericanOptionSolver.py:110-125) cancels catastrophically in K - S - p, so the iterate hybrd stops at moves
+    by up to ~1e-6 when the normal cdf changes in its last bit, and with the absolute stopping rule (Base.py:119) only ~8 sweeps
+    run, so part of that survives in the boundary.  Two passes: with the oracle's seeds borrowed (B0_in) the bars are
+    unconditional; with own seeds the bars are widened by the oracle-side conditioning of the REFERENCE's seed (co.seed_conditioning:
+    the spread of its hybrd iterate under 1-2 ulp probes of Phi), damped by the 1/2 per sweep of the fixed point — a term that is
+    below the bars themselves for all but a few percent of this (deliberately hostile) batch."""
     from oracle import c_oracle as co
     N = 6000
     b = wl.stress_batch(N)
@@ -608,6 +629,9 @@ def test_stress_ranges_vs_c_oracle():
         ps = np.isfinite(ref["price"]) & (ref["err"] < 1e-2) & sane
         assert ps.sum() >= 0.6 * N, (solver, n, ps.sum())
         bad_ref = ~ps
+        cond = co.seed_conditioning(b["T"], b["r"], b["q"], b["sigma"], b["K"], b["is_put"], n)
+        allow = (4 * cond * 0.5 ** np.minimum(ref["iters"], 60))[ps]
+        assert (allow > BOUNDARY_REL_TOL).mean() <= 0.08, (solver, n, (allow > BOUNDARY_REL_TOL).mean())
         for kernel in (0, 1):
             for borrowed in (True, False):
                 cfg = AloConfig(solver, n, l, m, 1e-5, mi, kernel=kernel)
@@ -619,11 +643,11 @@ def test_stress_ranges_vs_c_oracle():
                     slackB = slackP = 0.0
                 else:
                     seed = np.nanmax(np.abs(out["B0"] / ref["B0"] - 1)[ps], axis=1)
-                    assert np.median(seed) <= 1e-12 and (seed > 1e-10).mean() <= 0.10, (tag, np.median(seed))
-                    slackB, slackP = seed[:, None], seed * b["K"][ps]
+                    assert np.median(seed) <= 1e-13, (tag, np.median(seed))
+                    slackB, slackP = allow[:, None], allow * b["K"][ps]
                 assert (dP <= PRICE_ABS_TOL + slackP).all(), (tag, dP.max())
                 assert (np.nan_to_num(dB) <= BOUNDARY_REL_TOL + slackB).all() and not np.isnan(dB).any(), (tag, np.nanmax(dB))
-                assert (out["iters"][ps] != ref["iters"][ps]).mean() <= 1e-3, tag
+                assert _flips_are_ties(out, ref, ps, 1e-5, tag) <= 1e-3 * ps.sum(), tag
                 # outside the parity set both sides report failure the same way: not converged, or not finite
                 with np.errstate(invalid="ignore"):
                     sane_out = ((out["B"] > 1e-3 * b["K"][:, None]) & (out["B"] < 1e3 * b["K"][:, None])).all(axis=1)
@@ -764,9 +788,11 @@ def test_greeks_vs_oracle_differences():
     g = {k: v.cpu().numpy() for k, v in g.items()}
     kw = dict(n=cfg.n, l=cfg.l, m=cfg.m, iter_tol=cfg.iter_tol, max_iters=cfg.max_iters)
 
-    def ref(**over):
+    def ref(fd=False, **over):
         x = {**b, **over}
-        return co.alo_price_batch("A", x["r"], x["q"], x["sigma"], x["K"], x["T"], x["S"], x["is_put"], t=x.get("t"), **kw)
+        # the bumped re-solves of vega / rho run with the stopping rule tightened 1000x (batch.greeks_batch)
+        k2 = dict(kw, iter_tol=cfg.iter_tol * 1e-3, max_iters=max(cfg.max_iters, 64)) if fd else kw
+        return co.alo_price_batch("A", x["r"], x["q"], x["sigma"], x["K"], x["T"], x["S"], x["is_put"], t=x.get("t"), **k2)
 
     v0 = ref()
     ok = np.isfinite(v0["price"]) & (v0["err"] < 1e-2) & ~((b["q"] == 0) & ~b["is_put"])
@@ -777,8 +803,8 @@ def test_greeks_vs_oracle_differences():
     assert np.abs(g["delta"] - (vp - vm) / (2 * h))[ok].max() <= 1e-8
     assert np.abs(g["gamma"] - (vp - 2 * v0["price"] + vm) / h ** 2)[ok].max() <= 1e-6
     assert np.abs(g["theta"] - (vt - v0["price"]) / ht)[ok].max() <= 1e-5
-    vega = (ref(sigma=b["sigma"] + hv)["price"] - ref(sigma=b["sigma"] - hv)["price"]) / (2 * hv)
-    rho = (ref(r=b["r"] + hr)["price"] - ref(r=b["r"] - hr)["price"]) / (2 * hr)
+    vega = (ref(True, sigma=b["sigma"] + hv)["price"] - ref(True, sigma=b["sigma"] - hv)["price"]) / (2 * hv)
+    rho = (ref(True, r=b["r"] + hr)["price"] - ref(True, r=b["r"] - hr)["price"]) / (2 * hr)
     assert np.abs(g["vega"] - vega)[ok].max() <= 1e-5 and np.abs(g["rho"] - rho)[ok].max() <= 1e-4
     # signs (the integral form is not clamped at intrinsic inside the exercise region, as in the reference, so |delta| may
     # pass 1 there by a discretisation-level amount)
@@ -851,6 +877,139 @@ def test_tanh_sinh_and_undamped_newton_opt_in():
     assert both.sum() > 0.8 * N
     assert np.nanmax(np.abs(dn["B"] / gl["B"] - 1)[both]) <= 1e-7 and np.abs(dn["price"] - gl["price"])[both].max() <= 1e-7
     # (for Solver A the undamped step is not faster than the reference's damping: ~45 against ~34 sweeps to 1e-9 here)
+
+
+def test_opt_in_modes_vs_oracle():
+    """SURVEY 8f row 4 against an independent checker: the C oracle takes the same rule tables and the same eta, so the opt-in
+    modes are compared CUDA-vs-oracle (not CUDA-vs-CUDA): a truncated tanh-sinh rule for both integrals on the specialised and
+    the generic kernel, and the undamped Newton step eta = 1 with the analytic derivative."""
+    from oracle import c_oracle as co
+    N = 3000
+    b = wl.c2_batch(N)
+    a = [b[k] for k in ("r", "q", "sigma", "K", "T", "S", "is_put")]
+    rule = "tanh-sinh:2.0"     # nodes stay 2e-5 from +-1: the reference's u = tau - tau (1+y)^2/4 degenerates closer than 2e-8
+    for n, l, m in ((12, 32, 64), (12, 48, 96)):
+        rl, rm = batch.quadrature_rule(rule, l), batch.quadrature_rule(rule, m)
+        ref = co.alo_price_batch("A", *a, n=n, l=l, m=m, iter_tol=1e-5, max_iters=30, rule_l=rl, rule_m=rm)
+        ps = np.isfinite(ref["price"]) & (ref["err"] < 1e-2)
+        assert ps.sum() >= 0.97 * N
+        for kernel in (0, 1):
+            out = _np(batch.price_batch(*a, cfg=AloConfig("A", n, l, m, 1e-5, 30, kernel=kernel, rule_l=rule, rule_m=rule)))
+            tag = (n, l, m, kernel)
+            assert np.max(np.abs(out["price"] - ref["price"])[ps]) <= PRICE_ABS_TOL, tag
+            assert np.nanmax(np.abs(out["B"] / ref["B"] - 1)[ps]) <= BOUNDARY_REL_TOL, tag
+            assert _flips_are_ties(out, ref, ps, 1e-5, tag) <= 2, tag
+    ref = co.alo_price_batch("A", *a, n=12, l=32, m=64, iter_tol=1e-7, max_iters=80, use_derivative=True, eta=1.0)
+    ps = np.isfinite(ref["price"]) & (ref["err"] < 1e-2)
+    assert ps.sum() >= 0.9 * N
+    for kernel in (0, 1):
+        out = _np(batch.price_batch(*a, cfg=AloConfig("A", 12, 32, 64, 1e-7, 80, use_derivative=True, eta=1.0, kernel=kernel)))
+        assert np.max(np.abs(out["price"] - ref["price"])[ps]) <= PRICE_ABS_TOL, kernel
+        assert np.nanmax(np.abs(out["B"] / ref["B"] - 1)[ps]) <= BOUNDARY_REL_TOL, kernel
+        assert _flips_are_ties(out, ref, ps, 1e-7, kernel) <= 3, kernel
+
+
+@pytest.mark.parametrize("kernel", [0, 1])
+def test_domain_knobs_against_live_reference(kernel):
+    """tau_max != T (FastAmericanOptionSolverBase.py:28, consumed at :185, :223) through faop_cfg.tau_max and the drop-in
+    attribute, and tau_min != 0 (upstream: NaN after one sweep), against the live reference (ref_domain.npz)."""
+    from fastamericanoptionpricing_b200.FastAmericanOptionSolverA import FastAmericanOptionSolverA, qd
+    from fastamericanoptionpricing_b200.FastAmericanOptionSolverB import FastAmericanOptionSolverB
+    d = load_golden("ref_domain.npz")
+    sel = d["tau_min"] == 0
+    for key in sorted(set(zip(d["solver"][sel], d["n"][sel], d["l"][sel], d["m"][sel]))):
+        ix = np.nonzero(sel & (d["solver"] == key[0]) & (d["n"] == key[1]) & (d["l"] == key[2]) & (d["m"] == key[3]))[0]
+        cfg = AloConfig(str(key[0]), int(key[1]), int(key[2]), int(key[3]), 1e-5, 60, kernel=kernel)
+        out = _np(batch.price_batch(*_inputs(d, ix), t=d["in_t"][ix], cfg=cfg, tau_max=d["tau_max"][ix]))
+        nn = int(key[1]) + 1
+        assert np.max(np.abs(out["price"] - d["price"][ix])) <= PRICE_ABS_TOL, key
+        assert np.max(np.abs(out["B"] / d["B"][ix][:, :nn] - 1)) <= BOUNDARY_REL_TOL and np.array_equal(out["iters"], d["iters"][ix])
+        assert np.max(np.abs(out["tau"] - d["tau"][ix][:, :nn])) <= 1e-15
+        if kernel == 0:        # host-buffer entry point: cfg.tau_max is a host array there
+            oh = batch.HostContext(0).price_batch(*_inputs(d, ix), t=d["in_t"][ix], cfg=cfg, tau_max=d["tau_max"][ix])
+            assert np.array_equal(oh["price"], out["price"])
+    if kernel == 1:
+        return
+    for i in list(np.nonzero(sel)[0][::7]) + list(np.nonzero(~sel)[0]):
+        cls = FastAmericanOptionSolverA if str(d["solver"][i]) == "A" else FastAmericanOptionSolverB
+        s = cls(float(d["in_r"][i]), float(d["in_q"][i]), float(d["in_sigma"][i]), float(d["in_K"][i]), float(d["in_T"][i]),
+                qd.OptionType.Put if d["in_is_put"][i] else qd.OptionType.Call)
+        s.DEBUG = False
+        s.collocation_num, s.quadrature_num, s.integration_num = int(d["n"][i]), int(d["l"][i]), int(d["m"][i])
+        s.max_iters, s.iter_tol = int(d["max_iters"][i]), float(d["iter_tol"][i])
+        s.tau_max, s.tau_min = float(d["tau_max"][i]), float(d["tau_min"][i])
+        v = s.solve(float(d["in_t"][i]), float(d["in_S"][i]))
+        if d["tau_min"][i] != 0:
+            assert np.isnan(v) and s.num_iters == 1 and np.isnan(s.error) and np.isnan(d["price"][i])
+            assert np.max(np.abs(np.asarray(s.shared_tau) - d["tau"][i][:len(s.shared_tau)])) <= 1e-15
+        else:
+            assert abs(v - d["price"][i]) <= PRICE_ABS_TOL and s.num_iters == d["iters"][i]
+            assert np.max(np.abs(np.asarray(s.shared_tau) - d["tau"][i][:len(s.shared_tau)])) <= 1e-15
+
+
+def test_nan_outcomes_match_generic_kernel():
+    """Where upstream turns to NaN (a boundary node outside (0, inf): diverging iterate, poisoned seed, X = rK/q = 0; a spot
+    outside (0, inf)), the specialised kernels — whose reduced-cost exp / erfcx / sqrt clamp on the integer high word — must
+    report exactly what the libdevice-accurate generic kernel (and numpy) report: NaN price, NaN boundary, the same sweep count.
+    Includes NaNs with the sign bit set (0xFFF8...), the pattern device-generated NaNs carry."""
+    from oracle import c_oracle as co
+    N = 64
+    b = {k: v[:N].copy() for k, v in wl.c2_batch(4096).items()}
+    a = [b[k] for k in ("r", "q", "sigma", "K", "T", "S", "is_put")]
+    neg_nan = np.frombuffer(np.array([0xFFF8000000000000], dtype=np.uint64).tobytes(), dtype=np.float64)[0]
+    for solver, n, l, m in (("A", 12, 32, 64), ("B", 12, 32, 64), ("B", 24, 64, 128), ("A", 16, 40, 50)):
+        base = _np(batch.price_batch(*a, cfg=AloConfig(solver, n, l, m, 1e-5, 40, kernel=1)))
+        B0 = base["B0"].copy()
+        poison = [-1.0, float("nan"), neg_nan, 0.0, float("inf"), -float("inf")]
+        for i, v in enumerate(poison):
+            B0[i, (3 * i) % n] = v
+        S = b["S"].copy()
+        S[10], S[11], S[12] = -5.0, float("nan"), neg_nan
+        ref = co.alo_price_batch(solver, *a[:5], S, a[6], n=n, l=l, m=m, iter_tol=1e-5, max_iters=40, B0=B0)
+        outs = [_np(batch.price_batch(*a[:5], S, a[6], cfg=AloConfig(solver, n, l, m, 1e-5, 40, kernel=k), B0=B0)) for k in (1, 0)]
+        for out in outs:
+            assert np.isnan(out["price"][:6]).all() and np.isnan(out["price"][10:13]).all(), (solver, n)
+            assert np.isfinite(out["price"][13:]).all()
+            assert np.array_equal(np.isnan(out["price"]), np.isnan(ref["price"])), (solver, n)
+            assert np.array_equal(out["iters"][:13], ref["iters"][:13]), (solver, n, out["iters"][:13], ref["iters"][:13])
+            assert np.array_equal(np.isnan(out["B"]), np.isnan(ref["B"])), (solver, n)
+            assert np.array_equal(np.isnan(out["err"]), np.isnan(ref["err"]))
+        assert np.array_equal(outs[0]["iters"], outs[1]["iters"])
+    # a diverging iterate rather than a poisoned seed: Solver A with the derivative at low vol x long T
+    s = {k: v[:2048] for k, v in wl.c3_batch(2048).items()}
+    sa = [s[k] for k in ("r", "q", "sigma", "K", "T", "S", "is_put")]
+    o1, o0 = (_np(batch.price_batch(*sa, cfg=AloConfig("A", 12, 32, 64, 1e-5, 40, use_derivative=True, kernel=k))) for k in (1, 0))
+    nan1 = np.isnan(o1["price"])
+    assert nan1.sum() >= 5 and (np.isnan(o0["price"]) != nan1).mean() <= 0.01
+    agree = nan1 & np.isnan(o0["price"]) & (o1["iters"] <= 6)       # early blow-ups are deterministic; late ones are chaotic
+    assert agree.sum() >= 3 and np.array_equal(o0["iters"][agree], o1["iters"][agree])
+    # dev-math hooks with a negative-sign NaN: every variant must return NaN
+    for kind in (0, 4, 5, 6, 7, 8, 9, 10, 11, 12):
+        got = batch.dev_math_batch(kind, np.array([neg_nan, float("nan")])).cpu().numpy()
+        assert np.isnan(got).all() or kind in (0, 5, 6, 7, 8, 9, 12), kind      # the point-loop variants are guarded upstream of them
+
+
+def test_host_entry_converts_and_validates():
+    """faop_alo_price_batch_host through HostContext: float32 / strided / list inputs are converted, bool flags are viewed, a wrong
+    length or a wrong output buffer raises instead of reading or writing out of bounds (the C call trusts its pointers)."""
+    b = {k: v[:2000] for k, v in wl.c2_batch(4096).items()}
+    a = [b[k] for k in ("r", "q", "sigma", "K", "T", "S", "is_put")]
+    cfg = AloConfig(**wl.C2_CFG)
+    ctx = batch.HostContext(0)
+    ref = ctx.price_batch(*a, cfg=cfg)["price"]
+    wide = np.repeat(b["K"], 2)
+    got = ctx.price_batch(b["r"].tolist(), b["q"], b["sigma"], wide[::2], b["T"], b["S"], b["is_put"].astype(np.int64), cfg=cfg)
+    assert np.array_equal(got["price"], ref)
+    f32 = ctx.price_batch(*[x.astype(np.float32) if x.dtype == np.float64 else x for x in a], cfg=cfg)["price"]
+    assert np.nanmax(np.abs(f32 - ref)) < 1e-3 and np.isfinite(f32).mean() > 0.99
+    with pytest.raises(ValueError):
+        ctx.price_batch(b["r"], b["q"][:-1], *a[2:], cfg=cfg)
+    with pytest.raises(ValueError):
+        ctx.price_batch(*a, cfg=cfg, out=dict(price=np.empty(2000), iters=np.empty(2000, dtype=np.int64)))
+    with pytest.raises(ValueError):
+        ctx.price_batch(*a, cfg=cfg, out=dict(price=np.empty(1999)))
+    with pytest.raises(ValueError):
+        ctx.price_batch(*a, cfg=cfg, out=dict(price=np.empty(4000)[::2]))
 
 
 def test_cn_device_countdown_equals_host_schedule():

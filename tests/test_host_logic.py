@@ -3,6 +3,7 @@ configuration struct, workload generators."""
 import ctypes
 
 import numpy as np
+import pytest
 
 from fastamericanoptionpricing_b200 import _lib, batch, workloads as wl
 from oracle import alo_oracle as o
@@ -33,8 +34,11 @@ def test_config_struct_round_trip():
     assert c.iter_tol == 1e-7 and c.eta == 0.75 and batch.AloConfig().c().flags == 0
     d = batch.AloConfig()          # the reference's constructor defaults (FastAmericanOptionSolverBase.py:19-23, 46-47)
     assert (d.solver, d.n, d.l, d.m, d.iter_tol, d.max_iters, d.use_derivative, d.eta) == ("A", 12, 24, 48, 1e-5, 200, False, 0.5)
-    assert d.rule_l == d.rule_m == "gauss-legendre"
-    assert ctypes.sizeof(c) == 48
+    assert d.rule_l == d.rule_m == "gauss-legendre" and d.seed == "hybr"
+    assert batch.AloConfig(seed="newton").c().flags == _lib.FLAG_SEED_NEWTON and c.tau_max is None
+    with pytest.raises(ValueError):
+        batch.AloConfig(seed="bisect").c()
+    assert ctypes.sizeof(c) == 56
 
 
 def test_stress_workload_blocks():
@@ -67,3 +71,21 @@ def test_qdplus_internal_helpers_match_reference_values():
         got = dict(v_qQD=s.v_qQD, v_dlogSdh=s.v_dlogSdh, v_c=s.c(tau, S), v_c0=s.c0(tau, S), v_b=s.b(tau, S))
         for k, v in got.items():
             assert abs(v - e[k]) <= 1e-12 * max(1.0, abs(e[k])), (ot, k, v, e[k])
+
+
+def test_host_buffer_checks_without_gpu():
+    """HostContext._host_in / _host_out (the guards in front of the host-buffer C call) are plain host logic."""
+    hin, hout = batch.HostContext._host_in, batch.HostContext._host_out
+    x = np.arange(6, dtype=np.float64)
+    assert hin(x, 6, np.float64, "x") is x                                   # right layout: passed through, no copy
+    y = hin(x[::2], 3, np.float64, "x")
+    assert y.flags.c_contiguous and np.array_equal(y, [0, 2, 4])
+    assert hin([1, 2, 3], 3, np.float64, "x").dtype == np.float64 and hin(np.float32(2.5), 4, np.float64, "x").tolist() == [2.5] * 4
+    f = np.array([True, False, True])
+    assert hin(f, 3, np.uint8, "is_put").tolist() == [1, 0, 1] and hin(f.astype(np.int64), 3, np.uint8, "is_put").dtype == np.uint8
+    for bad in (lambda: hin(x, 5, np.float64, "x"), lambda: hout(np.empty(3, dtype=np.int64), (3,), np.int32, "iters"),
+                lambda: hout(np.empty(6)[::2], (3,), np.float64, "price"), lambda: hout(np.empty(4), (3,), np.float64, "price"),
+                lambda: hout([0.0] * 3, (3,), np.float64, "price")):
+        with pytest.raises(ValueError):
+            bad()
+    assert hout(np.empty((3, 13)), (3, 13), np.float64, "B").shape == (3, 13)

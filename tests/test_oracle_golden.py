@@ -45,9 +45,19 @@ def test_c2_golden_prefix(name, fn):
     out = fn("A", *_inputs(g, ix), **kw)
     ps = _check(out, g, ix, tag="c2 " + name)
     assert ps.sum() >= 0.98 * cnt
-    # seeds: Newton vs MINPACK hybr (xtol 1.49e-8) land on the same root
-    relB0 = np.abs(out["B0"] / g["B0"][ix] - 1)[ps]
-    assert np.nanmax(relB0) <= 1e-8
+    # seeds: the hybr restatement.  numpy/scipy arithmetic -> the reference's iterate bit for bit; libm's erfc/exp instead of
+    # scipy's ndtr / numpy's exp -> the same iterate up to the conditioning of hybrd's stopping point (co.seed_conditioning)
+    relB0 = np.abs(out["B0"] / g["B0"][ix] - 1)
+    if name == "numpy":
+        assert np.array_equal(out["B0"], g["B0"][ix], equal_nan=True)
+    else:
+        cond = co.seed_conditioning(*[g["in_" + k][ix] for k in ("T", "r", "q", "sigma", "K", "is_put")], 12)
+        assert np.nanmax(relB0[ps]) <= 2e-9 and np.nanmedian(relB0[ps]) <= 1e-15
+        assert (np.nanmax(relB0, axis=1)[ps] <= 1e-13 + 100 * cond[ps]).all()
+    # the Newton seed (the CUDA path's opt-in fast mode) lands on the same root to hybr's xtol = 1.49e-8
+    outn = fn("A", *_inputs(g, ix), seed="newton", **kw)
+    assert np.nanmax(np.abs(outn["B0"] / g["B0"][ix] - 1)[ps]) <= 1e-8
+    _check(outn, g, ix, tag="c2 newton " + name)
     # borrowed seeds: bit-level agreement of the iteration itself
     out2 = fn("A", *_inputs(g, ix), B0=g["B0"][ix], **kw)
     ps = _check(out2, g, ix, tag="c2 borrowed " + name)
@@ -62,13 +72,16 @@ def test_c3_golden(name, fn):
     out = fn("B", *_inputs(g), B0=g["B0"], **kw)
     ps = _check(out, g, tag="c3 borrowed " + name)
     assert ps.all()
+    # own seeds, every option, no exclusions: the fixture holds an extreme call (q ~ 3e-4, X = rK/q ~ 270 K) on which hybrd
+    # exits on slow progress far from the root — the restatement stops at the same iterate (a Newton seed does not: it costs
+    # one sweep-count mismatch and 9.5e-10 on the boundary there)
     out = fn("B", *_inputs(g), **kw)
-    # own seeds: hybr and Newton disagree on one extreme call (q ~ 3e-4, X = rK/q ~ 270 K); the fixed point is the same
-    seed_ok = np.nanmax(np.abs(out["B0"] / g["B0"] - 1), axis=1) <= 1e-6
-    assert seed_ok.sum() >= len(seed_ok) - 3
-    _check({k: v[seed_ok] for k, v in out.items()}, {k: g[k][seed_ok] for k in ("price", "err", "B", "iters")}, tag="c3 " + name)
-    assert np.max(np.abs(out["price"] - g["price"])) <= PRICE_ABS_TOL
-    assert np.nanmax(np.abs(out["B"] / g["B"] - 1)) <= 1e-8
+    ps = _check(out, g, tag="c3 " + name)
+    assert ps.all()
+    if name == "numpy":
+        assert np.array_equal(out["B0"], g["B0"], equal_nan=True)
+    outn = fn("B", *_inputs(g), seed="newton", **kw)
+    assert (np.nanmax(np.abs(outn["B0"] / g["B0"] - 1), axis=1) > 1e-6).sum() == 1
 
 
 @pytest.mark.parametrize("name,fn", IMPLS)
@@ -103,9 +116,14 @@ def test_qd_boundary():
     for fn in (o.qd_boundary, co.qd_boundary_batch):
         B = fn(q["in_tau"], q["in_r"], q["in_q"], q["in_sigma"], q["in_K"], q["in_is_put"])
         rel = np.abs(B / q["B"] - 1)
-        assert rel.max() <= 1e-8 and np.median(rel) <= 1e-13          # hybr xtol = 1.49e-8
         Bc = fn(q["curve_tau"], q["curve_r"], q["curve_q"], q["curve_sigma"], q["curve_K"], True)
+        if fn is o.qd_boundary:        # hybr1 on numpy/scipy arithmetic: the reference's iterate itself
+            assert np.array_equal(B, q["B"]) and np.array_equal(Bc, q["curve_B"])
+        assert rel.max() <= 2e-9 and np.median(rel) <= 1e-15
         assert np.max(np.abs(Bc / q["curve_B"] - 1)) <= 1e-11       # test_QDplus_curve.py anchors
+        Bn = fn(q["in_tau"], q["in_r"], q["in_q"], q["in_sigma"], q["in_K"], q["in_is_put"], **(
+            dict(method="newton") if fn is o.qd_boundary else dict(seed="newton")))
+        assert np.abs(Bn / q["B"] - 1).max() <= 1e-8                # hybr xtol = 1.49e-8
     assert abs(q["curve_B"][0] - 87.92730686380622) < 1e-12 and abs(q["curve_B"][11] - 104.2155098819196) < 1e-12
     assert q["curve_B"][12] == q["curve_K"]
     # residual on an array of spots, test_QDplus.py:20-21
@@ -115,6 +133,72 @@ def test_qd_boundary():
     rc, qc, sc, Kc = q["resid_call_params"]
     Fc = o.qd_residual(q["resid_S"], float(q["resid_tau"]), rc, qc, sc, Kc, False)
     assert np.max(np.abs(Fc - q["resid_call"])) <= 1e-11
+
+
+def test_hybr1_equals_scipy_root():
+    """The restatement of MINPACK hybrd for one unknown (oracle.alo_oracle.hybr1) against scipy.optimize.root(method="hybr")
+    — the call the reference makes (QDplusAmericanOptionSolver.py:73) — on the QD residual: same iterate bit for bit, same
+    number of residual evaluations (scipy counts two shape-probing calls more), over converged and slow-progress exits."""
+    import scipy.optimize
+    from fastamericanoptionpricing_b200 import workloads as wl
+    g = np.random.default_rng(5)
+    infos = set()
+    for b in (wl.c2_batch(4096), wl.c3_batch(4096), wl.stress_batch(6000)):
+        for i in g.choice(len(b["r"]), 60, replace=False):
+            c = np.cos(np.arange(12) * np.pi / 12)
+            for tau in (b["T"][i] * (1 + c) ** 2 / 4)[[0, 5, 9, 11]]:
+                a = (tau, b["r"][i], b["q"][i], b["sigma"][i], b["K"][i], bool(b["is_put"][i]))
+
+                def f(S):
+                    return float(o.qd_residual(np.float64(S), *a))
+                with np.errstate(all="ignore"):
+                    sol = scipy.optimize.root(lambda S: np.array([f(S[0])]), x0=a[4])
+                    x, nfev, info = o.hybr1(f, a[4])
+                assert (x == sol.x[0] or (np.isnan(x) and np.isnan(sol.x[0]))) and nfev + 2 == sol.nfev and info == sol.status, a
+                infos.add(info)
+    assert 1 in infos and len(infos) >= 2        # converged exits and at least one of hybrd's slow-progress exits
+
+
+def test_domain_knobs_golden():
+    """tau_max != T (FastAmericanOptionSolverBase.py:28, consumed at :185 and :223) against the live reference (ref_domain.npz)."""
+    d = load_golden("ref_domain.npz")
+    sel = d["tau_min"] == 0
+    for name, fn in IMPLS:
+        for key in sorted(set(zip(d["solver"][sel], d["n"][sel], d["l"][sel], d["m"][sel]))):
+            ix = np.nonzero(sel & (d["solver"] == key[0]) & (d["n"] == key[1]) & (d["l"] == key[2]) & (d["m"] == key[3]))[0]
+            out = fn(str(key[0]), *_inputs(d, ix), t=d["in_t"][ix], n=int(key[1]), l=int(key[2]), m=int(key[3]), iter_tol=1e-5,
+                     max_iters=60, tau_max=d["tau_max"][ix])
+            nn = int(key[1]) + 1
+            assert np.max(np.abs(out["price"] - d["price"][ix])) <= 1e-11, (name, key)
+            assert np.max(np.abs(out["B"] / d["B"][ix][:, :nn] - 1)) <= 1e-12 and np.array_equal(out["iters"], d["iters"][ix])
+    # tau_min != 0: upstream returns NaN after one sweep
+    bad = ~sel
+    assert bad.sum() == 6 and np.isnan(d["price"][bad]).all() and (d["iters"][bad] == 1).all() and np.isnan(d["err"][bad]).all()
+
+
+def test_custom_rule_and_eta():
+    """The oracle takes any rule on [-1, 1] and any damping, so the opt-in modes of the CUDA path (tanh-sinh, eta = 1 with the
+    derivative) have an independent checker: Gauss-Legendre passed explicitly reproduces the default bit for bit, and the two
+    oracles agree with each other on a tanh-sinh rule and on the undamped Newton step."""
+    from numpy.polynomial.legendre import leggauss
+    from fastamericanoptionpricing_b200 import batch, workloads as wl
+    b = {k: v[:24] for k, v in wl.c2_batch(4096).items()}
+    a = [b[k] for k in ("r", "q", "sigma", "K", "T", "S", "is_put")]
+    kw = dict(n=12, l=32, m=64, iter_tol=1e-7, max_iters=60)
+    for fn in (o.alo_price_batch, co.alo_price_batch):
+        d0 = fn("A", *a, **kw)
+        d1 = fn("A", *a, rule_l=leggauss(32), rule_m=leggauss(64), **kw)
+        assert np.array_equal(d0["price"], d1["price"]) and np.array_equal(d0["B"], d1["B"])
+    # truncated at t_max = 2.0 (nodes 2e-5 from the ends): the reference forms u = tau - tau (1+y)^2/4 (Base.py:186), which rounds to tau (-> 0/0 in
+    # phi/(sigma sqrt(tau-u))) for nodes within 2e-8 of -1; the CUDA path works with h = (1+y)/2 directly, the oracle follows the reference
+    rl, rm = batch.quadrature_rule("tanh-sinh:2.0", 32), batch.quadrature_rule("tanh-sinh:2.0", 64)
+    p1 = o.alo_price_batch("A", *a, rule_l=rl, rule_m=rm, **kw)
+    p2 = co.alo_price_batch("A", *a, rule_l=rl, rule_m=rm, **kw)
+    assert np.max(np.abs(p1["price"] - p2["price"])) <= 1e-11 and np.array_equal(p1["iters"], p2["iters"])
+    assert 1e-7 < np.max(np.abs(p1["price"] - d0["price"])) < 5e-2          # a different rule IS a different answer
+    e1 = o.alo_price_batch("A", *a, eta=1.0, use_derivative=True, **kw)
+    e2 = co.alo_price_batch("A", *a, eta=1.0, use_derivative=True, **kw)
+    assert np.max(np.abs(e1["price"] - e2["price"])) <= 1e-11 and np.array_equal(e1["iters"], e2["iters"])
 
 
 def test_qd_price():
@@ -255,7 +339,7 @@ def test_c5_surface_sample_golden():
     assert ps.sum() >= 0.95 * len(ps)
 
 
-def _stress_checks(fn_price, tag):
+def _stress_checks(fn_price, tag, exact_seed=False):
     """Shared by the CPU and the GPU suites: hard corners against the live reference (tests/golden/ref_stress_A.npz)."""
     g = load_golden("ref_stress_A.npz")
     a = _inputs(g)
@@ -270,18 +354,24 @@ def _stress_checks(fn_price, tag):
     assert np.abs(out["price"] - g["price"])[ps].max() <= PRICE_ABS_TOL, tag
     assert np.nanmax(np.abs(out["B"] / g["B"] - 1)[ps]) <= BOUNDARY_REL_TOL, tag
     assert (out["iters"][ps] != g["iters"][ps]).sum() == 0, tag
-    # own seeds: where MINPACK hybr and Newton stop at different points of an ill-conditioned QD residual, the boundary may
-    # differ by the seed difference and no more; a seed on another branch altogether (r ~ 0: X = rK/q ~ 0) is left out
+    # own seeds (hybrd restated): every option of the parity set, identical sweep counts.  The bars are the north-star's, widened
+    # only by what the REFERENCE's own seed is worth: `cond` = how far its hybrd iterate moves when the normal cdf inside the QD
+    # residual changes by 1-2 ulp (oracle-side probe, independent of the implementation under test), damped by the 1/2 per sweep
+    # the fixed point contracts with.  That term is below 1e-10 except for a handful of tiny-maturity options with X = rK/q << K
+    # (catastrophic cancellation in K - S - p, ~8 sweeps): there scipy itself on another libm would not reproduce the fixture.
     out = fn_price(a, kw, None)
-    seed = np.nanmax(np.abs(out["B0"] / g["B0"] - 1), axis=1)
-    same_branch = ps & (seed < 1e-3)
-    assert (ps & ~same_branch).sum() <= 2, tag
+    cond = co.seed_conditioning(*[g["in_" + k] for k in ("T", "r", "q", "sigma", "K", "is_put")], 12)
+    allow = 4 * cond * 0.5 ** g["iters"]
+    assert (allow[ps] > 1e-10).sum() <= 6 and (cond[ps] > 1e-7).sum() >= 5     # few get any room; the fixture does contain them
     dB = np.nanmax(np.abs(out["B"] / g["B"] - 1), axis=1)
-    assert (dB[same_branch] <= BOUNDARY_REL_TOL + seed[same_branch]).all(), tag
-    assert (np.abs(out["price"] - g["price"])[same_branch] <= PRICE_ABS_TOL + seed[same_branch] * g["in_K"][same_branch]).all(), tag
-    assert (seed[same_branch] > 1e-10).sum() >= 5        # the fixture does contain the ill-conditioned seeds
+    assert (dB[ps] <= BOUNDARY_REL_TOL + allow[ps]).all(), (tag, np.nanmax(dB[ps] - allow[ps]))
+    assert (np.abs(out["price"] - g["price"])[ps] <= PRICE_ABS_TOL + allow[ps] * g["in_K"][ps]).all(), tag
+    assert (out["iters"][ps] != g["iters"][ps]).sum() == 0, tag
+    if exact_seed:      # numpy/scipy arithmetic: the reference's seeds bit for bit, so the plain bars hold everywhere
+        assert np.array_equal(out["B0"][ps], g["B0"][ps]), tag
+        assert dB[ps].max() <= BOUNDARY_REL_TOL and np.abs(out["price"] - g["price"])[ps].max() <= PRICE_ABS_TOL, tag
 
 
 @pytest.mark.parametrize("name,fn", IMPLS)
 def test_stress_corners_golden(name, fn):
-    _stress_checks(lambda a, kw, B0: fn("A", *a, B0=B0, **kw), "stress " + name)
+    _stress_checks(lambda a, kw, B0: fn("A", *a, B0=B0, **kw), "stress " + name, exact_seed=(name == "numpy"))
