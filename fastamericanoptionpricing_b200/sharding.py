@@ -48,20 +48,45 @@ def gather_slices(local, N, world, group=None, unit=1):
     return full
 
 
+def interleaved_rows(G, world_size, rank):
+    """Rows g = rank, rank + W, rank + 2W, ... of a G-row problem (where cost correlates with the row index — the
+    sweep count and the number of recorded iterates of a (T, sigma) scenario grow with T — deal the rows round-robin instead of
+    cutting contiguous blocks, so every rank sees the same mix)."""
+    return slice(int(rank), int(G), int(world_size))
+
+
+def gather_interleaved(local, G, world, group=None, unit=1):
+    """all_gather of per-rank row sets dealt round-robin (interleaved_rows) back into one G x unit matrix, flattened."""
+    import torch.distributed as dist
+    longest = -(-G // world) * unit
+    pad = torch.zeros(longest, dtype=local.dtype, device=local.device)
+    pad[:local.numel()] = local.reshape(-1)
+    parts = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(parts, pad, group=group)
+    full = torch.empty((G, unit), dtype=local.dtype, device=local.device)
+    for rk in range(world):
+        cnt = len(range(rk, G, world))
+        full[rk::world] = parts[rk][:cnt * unit].reshape(cnt, unit)
+    return full.reshape(-1)
+
+
 def ladder_batch_sharded(r, q, sigma, T, S, is_put, K, cfg=None, gather=False, group=None):
-    """Strike ladders (batch.ladder_batch) with the SCENARIOS cut across ranks: rank g prices rows [lo, hi) of the
-    G x nK result — the boundary solves are split too, nothing is replicated and nothing is exchanged.  With `gather`
-    every rank receives the full G x nK matrix (one all_gather).  Returns (prices, (lo, hi))."""
+    """Strike ladders (batch.ladder_batch) with the SCENARIOS dealt round-robin across ranks: rank g prices rows g, g + W, ...
+    of the G x nK result — the boundary solves are split too, nothing is replicated and nothing is exchanged.  With `gather`
+    every rank receives the full G x nK matrix (one all_gather).  Returns (prices, rows) with rows = the slice of row indices
+    this rank priced."""
     import torch.distributed as dist
     from . import batch
     cfg = cfg or batch.AloConfig()
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     G = len(r)
-    lo, hi = shard_bounds(G, world, rank)
-    sl = slice(lo, hi)
-    local = batch.ladder_batch(r[sl], q[sl], sigma[sl], T[sl], S[sl], is_put[sl], K, cfg=cfg)
+    sl = interleaved_rows(G, world, rank)
+
+    def take(x):
+        return x[sl].contiguous() if isinstance(x, torch.Tensor) else x[sl]
+    local = batch.ladder_batch(take(r), take(q), take(sigma), take(T), take(S), take(is_put), K, cfg=cfg)
     if not gather or world == 1:
-        return local, (lo, hi)
+        return local, sl
     nK = local.shape[1]
-    return gather_slices(local.reshape(-1), G * nK, world, group, unit=nK).reshape(G, nK), (lo, hi)
+    return gather_interleaved(local, G, world, group, unit=nK).reshape(G, nK), sl

@@ -126,3 +126,30 @@ def seed_conditioning(T, r, q, sigma, K, is_put, n, tau_max=None):
     finally:
         lib().oracle_set_seed_probe(ctypes.c_int(0))
     return spread
+
+
+SEED_PROBES = (1, -1, 2, -2, 3, -3, 4, -4, 6, -6, 8, -8)
+
+
+def seed_sensitivity(solver, r, q, sigma, K, T, S, is_put, probes=SEED_PROBES, **kw):
+    """What the reference's own seed noise is worth in its FINAL answer: the whole solve (hybrd seed, damped sweeps, price
+    integral) is repeated with the normal cdf inside the QD residual scaled by (1 + k ulp), k in `probes`; returns per option
+    (max_k |B_k / B_0 - 1| over the nodes, max_k |price_k - price_0|, any sweep-count change).  This is the band inside which two
+    correct implementations of the reference (scipy's ndtr vs libm's or libdevice's erfc — or scipy on another CPU) legitimately
+    differ: zero-ish for well-conditioned options, and up to 1e-8 where hybrd stops on a flat residual after few sweeps or
+    bifurcates between two slow-progress exits.  Meant for the handful of options that exceed the plain bars, not for whole batches."""
+    base = alo_price_batch(solver, r, q, sigma, K, T, S, is_put, **kw)
+    dB = np.zeros(len(base["price"]))
+    dP = np.zeros(len(base["price"]))
+    flip = np.zeros(len(base["price"]), dtype=bool)
+    try:
+        for k in probes:
+            lib().oracle_set_seed_probe(ctypes.c_int(k))
+            o = alo_price_batch(solver, r, q, sigma, K, T, S, is_put, **kw)
+            with np.errstate(all="ignore"):
+                dB = np.fmax(dB, np.nan_to_num(np.nanmax(np.abs(o["B"] / base["B"] - 1), axis=1), nan=np.inf))
+                dP = np.fmax(dP, np.nan_to_num(np.abs(o["price"] - base["price"]), nan=np.inf))
+            flip |= o["iters"] != base["iters"]
+    finally:
+        lib().oracle_set_seed_probe(ctypes.c_int(0))
+    return dB, dP, flip

@@ -354,22 +354,22 @@ def _stress_checks(fn_price, tag, exact_seed=False):
     assert np.abs(out["price"] - g["price"])[ps].max() <= PRICE_ABS_TOL, tag
     assert np.nanmax(np.abs(out["B"] / g["B"] - 1)[ps]) <= BOUNDARY_REL_TOL, tag
     assert (out["iters"][ps] != g["iters"][ps]).sum() == 0, tag
-    # own seeds (hybrd restated): every option of the parity set, identical sweep counts.  The bars are the north-star's, widened
-    # only by what the REFERENCE's own seed is worth: `cond` = how far its hybrd iterate moves when the normal cdf inside the QD
-    # residual changes by 1-2 ulp (oracle-side probe, independent of the implementation under test), damped by the 1/2 per sweep
-    # the fixed point contracts with.  That term is below 1e-10 except for a handful of tiny-maturity options with X = rK/q << K
-    # (catastrophic cancellation in K - S - p, ~8 sweeps): there scipy itself on another libm would not reproduce the fixture.
+    # own seeds (hybrd restated): every option of the parity set, identical sweep counts, the north-star's bars.  The few options
+    # over the plain bars must be explained by the REFERENCE's own seed noise: co.seed_sensitivity repeats the oracle's whole solve
+    # with the normal cdf inside the QD residual off by a few ulp; an option may differ from the fixture by no more than 4x what
+    # that moves the oracle's own final answer.  (Tiny maturities with X = rK/q << K: catastrophic cancellation in K - S - p and
+    # only ~8 sweeps — scipy itself on another libm would not reproduce the fixture there.)
     out = fn_price(a, kw, None)
-    cond = co.seed_conditioning(*[g["in_" + k] for k in ("T", "r", "q", "sigma", "K", "is_put")], 12)
-    allow = 4 * cond * 0.5 ** g["iters"]
-    assert (allow[ps] > 1e-10).sum() <= 6 and (cond[ps] > 1e-7).sum() >= 5     # few get any room; the fixture does contain them
     dB = np.nanmax(np.abs(out["B"] / g["B"] - 1), axis=1)
-    assert (dB[ps] <= BOUNDARY_REL_TOL + allow[ps]).all(), (tag, np.nanmax(dB[ps] - allow[ps]))
-    assert (np.abs(out["price"] - g["price"])[ps] <= PRICE_ABS_TOL + allow[ps] * g["in_K"][ps]).all(), tag
+    dP = np.abs(out["price"] - g["price"])
+    over = np.nonzero(ps & ((dB > BOUNDARY_REL_TOL) | (dP > PRICE_ABS_TOL)))[0]
+    assert len(over) <= 0.03 * ps.sum(), (tag, len(over))
+    if len(over):
+        sB, sP, _ = co.seed_sensitivity("A", *[x[over] for x in a], **kw)
+        assert (dB[over] <= BOUNDARY_REL_TOL + 4 * sB).all() and (dP[over] <= PRICE_ABS_TOL + 4 * sP).all(), (tag, dB[over], sB)
     assert (out["iters"][ps] != g["iters"][ps]).sum() == 0, tag
     if exact_seed:      # numpy/scipy arithmetic: the reference's seeds bit for bit, so the plain bars hold everywhere
-        assert np.array_equal(out["B0"][ps], g["B0"][ps]), tag
-        assert dB[ps].max() <= BOUNDARY_REL_TOL and np.abs(out["price"] - g["price"])[ps].max() <= PRICE_ABS_TOL, tag
+        assert np.array_equal(out["B0"][ps], g["B0"][ps]) and len(over) == 0, tag
 
 
 @pytest.mark.parametrize("name,fn", IMPLS)

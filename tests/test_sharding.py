@@ -9,7 +9,7 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from fastamericanoptionpricing_b200 import workloads as wl
-from fastamericanoptionpricing_b200.sharding import gather_slices, shard_bounds
+from fastamericanoptionpricing_b200.sharding import gather_interleaved, gather_slices, interleaved_rows, shard_bounds
 
 
 def test_shard_bounds_cover_and_balance():
@@ -19,6 +19,15 @@ def test_shard_bounds_cover_and_balance():
             assert cuts[0][0] == 0 and cuts[-1][1] == N
             assert all(cuts[i][1] == cuts[i + 1][0] for i in range(W - 1))
             sizes = [hi - lo for lo, hi in cuts]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_interleaved_rows_cover():
+    for G in (0, 1, 7, 1000, 100_003):
+        for W in (1, 2, 3, 8):
+            rows = sorted(i for r in range(W) for i in range(G)[interleaved_rows(G, W, r)])
+            assert rows == list(range(G))
+            sizes = [len(range(G)[interleaved_rows(G, W, r)]) for r in range(W)]
             assert max(sizes) - min(sizes) <= 1
 
 
@@ -42,6 +51,13 @@ def _worker(rank, world, port, N, out):
     # row-wise cut (ladder_batch_sharded: scenarios x strikes): N rows of 3
     mat = torch.arange(3 * N, dtype=torch.float64).reshape(N, 3)
     ok = ok and torch.equal(gather_slices(mat[lo:hi].reshape(-1).clone(), 3 * N, world, unit=3).reshape(N, 3), mat)
+    # round-robin deal (ladder_batch_sharded / bench.py's C5: scenario g -> rank g mod W)
+    sl = interleaved_rows(N, world, rank)
+    ok = ok and torch.equal(gather_interleaved(mat[sl].clone(), N, world, unit=3).reshape(N, 3), mat)
+    # an exact, order-independent checksum (integer micro-units), equal for every world size, as bench.py's C5 line reports
+    chk = torch.round(mat[sl] * 1e6).to(torch.int64).sum().reshape(1)
+    dist.all_reduce(chk)
+    ok = ok and chk.item() == int(torch.round(mat * 1e6).to(torch.int64).sum())
     # every rank reduces its step time with MAX, as bench.py does
     t = torch.tensor([10.0 + rank])
     dist.all_reduce(t, op=dist.ReduceOp.MAX)

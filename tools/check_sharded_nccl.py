@@ -17,7 +17,7 @@ ref = batch.price_batch(*a, cfg=cfg, want_boundary=False)["price"]
 ok1 = torch.equal(full, ref)
 G, Kl = 1001, np.linspace(60, 140, 33)
 g = [x[:G] for x in a]
-lad, (glo, ghi) = ladder_batch_sharded(g[0], g[1], g[2], g[4], g[5], g[6], Kl, cfg=cfg, gather=True)
+lad, rows = ladder_batch_sharded(g[0], g[1], g[2], g[4], g[5], g[6], Kl, cfg=cfg, gather=True)
 lref = batch.ladder_batch(g[0], g[1], g[2], g[4], g[5], g[6], Kl, cfg=cfg)
 ok2 = torch.equal(lad, lref)
 flag = torch.tensor([int(ok1 and ok2)], device="cuda")
