@@ -5,12 +5,18 @@ Contract:  python bench.py --gpus N --steps K --wa
   step      one pass of the hot path (QD seed kernel + boundary/price kernel) over one batch of synthetic options:
             BASELINE.json configs[1] = 1M random puts/calls, FastAmericanOptionSolverA n=12 l=32 (m=64), tol 1e-5,
             max_iters 20 — per GPU (weak scaling: every rank prices its own 1M-option slice, no collective).
+            Default configuration of the library: the QD seed is found with the reference's own root finder (hybrd).
   value     options/s over all ranks, inputs resident in HBM, CUDA-event time per step, max over ranks
   e2e       the same through the host-buffer C-ABI call (faop_alo_price_batch_host) with pinned host arrays:
             H2D of the inputs and D2H of prices inside the timed region
   roofline  nominal FP64 FLOPs (SURVEY §8d model) / time of the dominant kernel alone, over the DFMA-pipe peak
-            measured live by faop_measure_fp64_peak (MEASURED_PEAKS.json carries no FP64 figure)
+            measured live by faop_measure_fp64_peak (MEASURED_PEAKS.json carries no FP64 figure); the ncu-side counters
+            come from profiles/kernel_profile.json (written by tools/round_profile.sh with the hash of the kernel sources;
+            "stale": true when the sources have changed since)
   cpu_baseline  the plain-C oracle port (oracle/alo_oracle.c) on all host cores over a bounded prefix of the batch
+  configs   the other BASELINE.json configs measured in the same run: c3 (Solver B n=24 l=64, stress thirds), c4 (Crank-Nicolson
+            2000 x 2000 cross-checked against spectral prices), c5 (100M-option surface through the shared-boundary ladder path —
+            under torchrun the (T, sigma) scenarios are dealt round-robin across the ranks: fixed total work, strong scaling)
 --impl reference  times that CPU port alone (rank 0 only) and prints the same line with "impl": "reference".
 """
 import argparse
@@ -32,6 +38,10 @@ METRIC = "American options priced/sec (FP64)"
 UNIT = "options/s"
 N_PER_GPU = 1_000_000
 kSMSP = 148 * 4          # SM sub-partitions (issue ports) of one B200
+KEYS = ("r", "q", "sigma", "K", "T", "S", "is_put")
+# the unmodified Python reference, SURVEY.md §6 (measured in the dev container: Pool(8), 64 options of the C2 generator)
+SURVEY_PYTHON = {"value": 1.96, "unit": UNIT, "cores": 8, "per_core": 0.245, "from_survey": True,
+                 "sample": "64 random C2 options, FastAmericanOptionSolverA.solve under multiprocessing.Pool(8), SURVEY.md section 6"}
 
 
 def flops_per_option(solver, n, l, m, J):
@@ -45,16 +55,62 @@ def cpu_port_rate(cfg, b, target_seconds, threads):
     from oracle import c_oracle as co          # cpu_baseline leg: the one place bench.py may execute oracle/
     kw = dict(n=cfg["n"], l=cfg["l"], m=cfg["m"], iter_tol=cfg["iter_tol"], max_iters=cfg["max_iters"],
               use_derivative=cfg["use_derivative"], nthreads=threads)
-    keys = ("r", "q", "sigma", "K", "T", "S", "is_put")
     probe = 64 * threads
     t0 = time.perf_counter()
-    co.alo_price_batch(cfg["solver"], *[b[k][:probe] for k in keys], **kw)
+    co.alo_price_batch(cfg["solver"], *[b[k][:probe] for k in KEYS], **kw)
     rate = probe / (time.perf_counter() - t0)
     count = int(min(len(b["r"]), max(probe, rate * target_seconds)))
     t0 = time.perf_counter()
-    out = co.alo_price_batch(cfg["solver"], *[b[k][:count] for k in keys], **kw)
+    out = co.alo_price_batch(cfg["solver"], *[b[k][:count] for k in KEYS], **kw)
     dt = time.perf_counter() - t0
     return count / dt, count, dt, out
+
+
+def python_reference_rate():
+    """The UNMODIFIED Python reference under multiprocessing.Pool(P) on 2P options of the C2 generator — only where the
+    reference tree is at hand (the dev container: /root/reference does not travel to the GPU box); otherwise the survey figure."""
+    ref = os.environ.get("FAOP_REFERENCE", "/root/reference")
+    if not os.path.isdir(ref):
+        return SURVEY_PYTHON
+    try:
+        import importlib.util
+        spec = importlib.util.spec_from_file_location("faop_gen_golden", os.path.join(REPO, "oracle", "gen_golden.py"))
+        gg = importlib.util.module_from_spec(spec)
+        sys.modules["faop_gen_golden"] = gg    # Pool pickles solve_one by module name
+        spec.loader.exec_module(gg)            # puts the reference (behind its no-op matplotlib stub) on sys.path
+        import multiprocessing as mp
+        P = len(os.sched_getaffinity(0))
+        b = wl.c2_batch(64)
+        c = wl.C2_CFG
+        jobs = [("A", b["r"][i], b["q"][i], b["sigma"][i], b["K"][i], b["T"][i], b["S"][i], 0.0, bool(b["is_put"][i]), c["n"], c["l"],
+                 c["m"], c["iter_tol"], c["max_iters"], False) for i in range(min(64, 2 * P))]
+        with mp.Pool(P) as pool:
+            t0 = time.perf_counter()
+            pool.map(gg.solve_one, jobs, chunksize=1)
+            dt = time.perf_counter() - t0
+        cpu = ""
+        try:
+            cpu = [ln.split(":", 1)[1].strip() for ln in open("/proc/cpuinfo") if ln.startswith("model name")][0]
+        except Exception:
+            pass
+        return {"value": len(jobs) / dt, "unit": UNIT, "cores": P, "per_core": len(jobs) / dt / P, "from_survey": False, "cpu": cpu,
+                "sample": "%d random C2 options, unmodified FastAmericanOptionSolverA.solve (DEBUG=False) under Pool(%d), %.1f s" % (
+                    len(jobs), P, dt)}
+    except Exception as e:      # pragma: no cover
+        return dict(SURVEY_PYTHON, error=repr(e))
+
+
+def kernel_profile(name):
+    """ncu-side counters of a kernel from profiles/kernel_profile.json (never literals in this file)."""
+    from fastamericanoptionpricing_b200 import _lib
+    try:
+        prof = json.load(open(os.path.join(REPO, "profiles", "kernel_profile.json")))
+        k = dict(prof["kernels"][name])
+        k["source_hash"] = prof.get("source_hash")
+        k["stale"] = prof.get("source_hash") != _lib.kernel_source_hash()
+        return k
+    except Exception:
+        return None
 
 
 class ClockSampler(threading.Thread):
@@ -102,12 +158,11 @@ def run_reference(args):
     rate0, count, _, _ = cpu_port_rate(cfg, b, 2.0, threads)
     per_step = int(max(64 * threads, min(N_PER_GPU, rate0 * 8.0)))     # ~8 s of CPU work per step
     from oracle import c_oracle as co
-    keys = ("r", "q", "sigma", "K", "T", "S", "is_put")
     kw = dict(n=cfg["n"], l=cfg["l"], m=cfg["m"], iter_tol=cfg["iter_tol"], max_iters=cfg["max_iters"], nthreads=threads)
     times = []
     for s in range(args.warmup + args.steps):
         t0 = time.perf_counter()
-        co.alo_price_batch(cfg["solver"], *[b[k][:per_step] for k in keys], **kw)
+        co.alo_price_batch(cfg["solver"], *[b[k][:per_step] for k in KEYS], **kw)
         if s >= args.warmup:
             times.append(time.perf_counter() - t0)
     ms = 1e3 * float(np.mean(times))
@@ -119,83 +174,189 @@ def run_reference(args):
                        "options_per_step": per_step, "seed": wl.C2_SEED},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
                              "sample": "first %d options of the 1M C2 batch per step, plain-C port of the reference "
-                                       "algorithm (oracle/alo_oracle.c) on %d pthreads" % (per_step, threads)},
+                                       "algorithm (oracle/alo_oracle.c, hybrd seed) on %d pthreads" % (per_step, threads)},
+            "cpu_baseline_python": python_reference_rate(),
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 
 
-def run_c5(args):
-    """BASELINE.json configs[4]: 100M puts = 1000 strikes x 1000 maturities x 100 vols (S=100, r=.04, q=.01), Solver A n=12
-    l=32 m=64.  The (T, sigma) scenarios are cut across the ranks; each rank solves its scenarios' boundaries once (K = 1)
-    and prices all 1000 strikes of each (faop_alo_ladder_batch).  Total work is fixed: strong scaling."""
+class Ctx:
+    """rank / device / collective helpers shared by the legs"""
+
+    def __init__(self):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=self.dev)
+        self.flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=self.dev)      # > 126 MB L2
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def flush(self):
+        self.flush_buf.zero_()
+
+    def timed(self, fn, steps, flush=True):
+        """mean CUDA-event ms of `steps` calls of fn on the current stream, L2 flushed (outside the event pair) before each"""
+        torch = self.torch
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        for a, b in ev:
+            if flush:
+                self.flush()
+            a.record()
+            fn()
+            b.record()
+        torch.cuda.synchronize()
+        return float(np.mean([a.elapsed_time(b) for a, b in ev]))
+
+    def reduce(self, vals, op="max"):
+        t = self.torch.tensor(vals, dtype=self.torch.float64, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op={"max": self.dist.ReduceOp.MAX, "min": self.dist.ReduceOp.MIN, "sum": self.dist.ReduceOp.SUM}[op])
+        return t.tolist()
+
+    def close(self):
+        if self.world > 1:
+            self.dist.destroy_process_group()
+
+
+def leg_c3(cx, steps, threads):
+    """BASELINE configs[2]: Solver B n=24 l=64 m=128, max_iters 200, the stress thirds (low vol, long T, q > r); rank 0's GPU."""
     import torch
-    import torch.distributed as dist
     from fastamericanoptionpricing_b200 import batch
-    from fastamericanoptionpricing_b200.sharding import shard_bounds
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    W = max(args.warmup, 3)
+    from oracle import c_oracle as co
+    N = 262144
+    b = wl.c3_batch(N)
+    cfgd = dict(wl.C3_CFG)
+    cfg = batch.AloConfig(**cfgd)
+    d = [torch.as_tensor(np.ascontiguousarray(b[k])).to(cx.dev) for k in KEYS[:6]] + [torch.as_tensor(b["is_put"].astype(np.uint8)).to(cx.dev)]
+    for _ in range(2):
+        out = batch.price_batch(*d, cfg=cfg, want_boundary=False)
+    ms = cx.timed(lambda: batch.price_batch(*d, cfg=cfg, want_boundary=False), steps)
+    seeds = batch.price_batch(*d, cfg=cfg, want_boundary=True)
+    B0, J = seeds["B0"], float(seeds["iters"].double().mean().item())
+    ms_k = cx.timed(lambda: batch.price_batch(*d, cfg=cfg, B0=B0, want_boundary=False), steps)
+    fl = flops_per_option("B", cfgd["n"], cfgd["l"], cfgd["m"], J)
+    cnt = 256 * threads // 8 if threads >= 8 else 256
+    ref = co.alo_price_batch("B", *[b[k][:cnt] for k in KEYS], n=cfgd["n"], l=cfgd["l"], m=cfgd["m"], iter_tol=cfgd["iter_tol"],
+                             max_iters=cfgd["max_iters"], nthreads=threads)
+    ok = np.isfinite(ref["price"]) & (ref["err"] < 1e-2)
+    p = out["price"].cpu().numpy()[:cnt]
+    tf_peak, _ = batch.measure_fp64_peak(10)
+    return {"workload": "C3: %d options (prefix of the 1M stress batch: low vol / long T / q > r thirds), FastAmericanOptionSolverB n=24 l=64 "
+                        "m=128 tol=1e-5 max_iters=200 (BASELINE.json configs[2])" % N,
+            "value": N / (ms / 1e3), "unit": UNIT, "ms_per_step": ms, "kernel_ms": ms_k, "mean_iterations": J,
+            "max_abs_err_vs_cpu_port": float(np.max(np.abs(p - ref["price"])[ok])), "parity_sample": int(ok.sum()),
+            "sweep_count_mismatches": int((out["iters"].cpu().numpy()[:cnt] != ref["iters"])[ok].sum()),
+            "roofline": {"bound": "fp64", "achieved": fl * N / (ms_k / 1e3) / 1e12, "peak": tf_peak, "unit": "TFLOP/s",
+                         "frac": fl * N / (ms_k / 1e3) / 1e12 / tf_peak, "kernel": "alo_clen_kernel<1,2,true>", "flops_per_option": fl,
+                         "executed": kernel_profile("alo_clen_kernel")}}
+
+
+def leg_c4(cx, steps):
+    """BASELINE configs[3]: Crank-Nicolson American puts on the 2000 x 2000 grid (projected tridiagonal sweep), Smax per option by
+    workloads.c4_smax, cross-checked against the spectral prices of the same options; rank 0's GPU."""
+    import torch
+    from fastamericanoptionpricing_b200 import batch
+    from oracle import c_oracle as co
+    N = 8192
+    b = {k: v[:N] for k, v in wl.c4_batch().items()}
+    sm = wl.c4_smax(b)
+    a = [torch.as_tensor(np.ascontiguousarray(b[k])).to(cx.dev) for k in KEYS[:6]]
+    mdt = torch.as_tensor(b["T"] / 2000).to(cx.dev)
+    smd = torch.as_tensor(sm).to(cx.dev)
+
+    def run():
+        return batch.cn_put_batch(*a, n_space=2000, max_dt=mdt, mode=2, Smax=smd)
+    cn = run()
+    ms = cx.timed(run, max(2, min(steps, 3)), flush=False)      # state lives in registers / shared memory; inputs are 450 KB
+    cn = cn.cpu().numpy()
+    sp = batch.price_batch(b["r"], b["q"], b["sigma"], b["K"], b["T"], b["S"], b["is_put"],
+                           cfg=batch.AloConfig(**{**wl.C2_CFG, "iter_tol": 1e-8, "max_iters": 40}), want_boundary=False)["price"].cpu().numpy()
+    ref = co.cn_put_batch(*[b[k][:8] for k in KEYS[:6]], n_space=2000, max_dt=b["T"][:8] / 2000, mode=2, Smax=sm[:8])
+    tf_peak, _ = batch.measure_fp64_peak(10)
+    node_steps = 2000.0 * 2000.0
+    return {"workload": "C4: %d of the 100k Crank-Nicolson puts, 2000 nodes x 2000 steps, projected tridiagonal sweep, Smax = K max(3, "
+                        "exp(3 sigma sqrt T)) (BASELINE.json configs[3])" % N,
+            "value": N / (ms / 1e3), "unit": UNIT, "ms_per_step": ms, "kernel_ms": ms,
+            "projected_seconds_for_100k": 100000.0 / (N / (ms / 1e3)),
+            "max_abs_cn_minus_spectral": float(np.max(np.abs(cn - sp))), "cross_check_bar": 5e-3,
+            "max_abs_err_vs_cpu_port": float(np.max(np.abs(cn[:8] - ref))), "parity_sample": 8,
+            "roofline": {"bound": "fp64", "achieved": 11.0 * node_steps * N / (ms / 1e3) / 1e12, "peak": tf_peak, "unit": "TFLOP/s",
+                         "frac": 11.0 * node_steps * N / (ms / 1e3) / 1e12 / tf_peak, "kernel": "cn_scan_kernel<8,true>",
+                         "flops_per_option": 11.0 * node_steps,
+                         "flop_model": "SURVEY 8d: 11 flops per node-step; the state never leaves the SM, so the HBM-streaming bound "
+                                       "(16 B per node-step -> 1.0e5 options/s) does not apply",
+                         "executed": kernel_profile("cn_scan_kernel")}}
+
+
+def leg_c5(cx, steps):
+    """BASELINE configs[4]: 100M puts = 1000 strikes x 1000 maturities x 100 vols (S=100, r=.04, q=.01), Solver A n=12 l=32 m=64.
+    The 100k (T, sigma) scenarios are dealt round-robin across the ranks (scenario g -> rank g mod W: sweep counts grow with T, a
+    contiguous cut would give rank 0 the cheap end); each rank solves its scenarios' boundaries once (K = 1) and prices all 1000
+    strikes of each (faop_alo_ladder_batch).  Total work is fixed: strong scaling.  No collective on the data path."""
+    import torch
+    from fastamericanoptionpricing_b200 import batch
+    from fastamericanoptionpricing_b200.sharding import interleaved_rows
+    from oracle import c_oracle as co
     cfg = batch.AloConfig(**wl.C5_CFG)
     nK, nT, nV = 1000, 1000, 100
     Kl = np.linspace(50.0, 150.0, nK)
     Tg, Vg = np.meshgrid(np.linspace(1.0 / 52, 3.0, nT), np.linspace(0.10, 0.60, nV), indexing="ij")
     G = nT * nV
-    lo, hi = shard_bounds(G, world, rank)
-    g = hi - lo
-    T = torch.from_numpy(Tg.reshape(-1)[lo:hi].copy()).to(dev)
-    V = torch.from_numpy(Vg.reshape(-1)[lo:hi].copy()).to(dev)
-    r = torch.full((g,), 0.04, dtype=torch.float64, device=dev)
-    q = torch.full((g,), 0.01, dtype=torch.float64, device=dev)
-    S = torch.full((g,), 100.0, dtype=torch.float64, device=dev)
-    put = torch.ones(g, dtype=torch.uint8, device=dev)
-    Kd = torch.from_numpy(Kl).to(dev)
-    out = torch.empty((g, nK), dtype=torch.float64, device=dev)
+    rows = interleaved_rows(G, cx.world, cx.rank)
+    Th, Vh = Tg.reshape(-1)[rows].copy(), Vg.reshape(-1)[rows].copy()
+    g = len(Th)
+    T, V = torch.from_numpy(Th).to(cx.dev), torch.from_numpy(Vh).to(cx.dev)
+    r = torch.full((g,), 0.04, dtype=torch.float64, device=cx.dev)
+    q = torch.full((g,), 0.01, dtype=torch.float64, device=cx.dev)
+    S = torch.full((g,), 100.0, dtype=torch.float64, device=cx.dev)
+    put = torch.ones(g, dtype=torch.uint8, device=cx.dev)
+    Kd = torch.from_numpy(Kl).to(cx.dev)
+    out = torch.empty((g, nK), dtype=torch.float64, device=cx.dev)
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for _ in range(W):
+    def run():
         batch.ladder_batch(r, q, V, T, S, put, Kd, cfg=cfg, out=out)
-    barrier()
-    sampler = ClockSampler(local)
-    sampler.start()
+    for _ in range(3):
+        run()
+    cx.barrier()
     l0 = batch.launch_count()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    barrier()
-    for s in range(args.steps):       # the 800 MB/world output per step is itself larger than L2: nothing survives between steps
-        ev[s][0].record()
-        batch.ladder_batch(r, q, V, T, S, put, Kd, cfg=cfg, out=out)
-        ev[s][1].record()
-    barrier()
+    ms_own = cx.timed(run, steps, flush=False)      # the 800 MB / world output per step is itself larger than L2
     launches = batch.launch_count() - l0
-    clocks = sampler.stop()
-    ms = float(np.mean([a.elapsed_time(b_) for a, b_ in ev]))
-    red = torch.tensor([ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(red, op=dist.ReduceOp.MAX)
-    ms = red.item()
-    if rank == 0:
-        line = {"metric": METRIC, "value": G * nK / (ms / 1e3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": W,
-                "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
-                "data": "synthetic",
-                "config": {"workload": "C5: 100M-put surface (1000 strikes x 1000 maturities x 100 vols), FastAmericanOptionSolverA "
-                                       "n=12 l=32 m=64 tol=1e-5 max_iters=20; boundary solves shared per (T, sigma) scenario "
-                                       "(BASELINE.json configs[4], SURVEY 8f row 1)",
-                           "scenarios": G, "strikes": nK, "parallelism": "scenarios cut across %d ranks, no collective" % world,
-                           "l2": "output (%d MB per rank) exceeds L2" % (g * nK * 8 >> 20)},
-                "gpu_launches": int(launches), "clocks": clocks,
-                "checksum": float(out.sum().item())}
-        print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    cx.barrier()
+    ms = cx.reduce([ms_own], "max")[0]
+    ms_min = cx.reduce([ms_own], "min")[0]
+    # exact, order-independent checksum over ALL 100M prices (integer micro-units), equal for every world size
+    chk = torch.round(out * 1e6).to(torch.int64).sum().reshape(1)
+    if cx.world > 1:
+        cx.dist.all_reduce(chk)
+    # live parity on a seeded sample of this rank's scenarios x strikes against the plain-C port (option by option)
+    gsel = np.random.default_rng(5 + cx.rank).integers(0, g, 32)
+    ksel = np.random.default_rng(7).integers(0, nK, 32)
+    ref = co.alo_price_batch("A", np.full(32, 0.04), np.full(32, 0.01), Vh[gsel], Kl[ksel], Th[gsel], np.full(32, 100.0),
+                             np.ones(32, dtype=bool), n=cfg.n, l=cfg.l, m=cfg.m, iter_tol=cfg.iter_tol, max_iters=cfg.max_iters, nthreads=4)
+    got = out[torch.as_tensor(gsel, device=cx.dev), torch.as_tensor(ksel, device=cx.dev)].cpu().numpy()
+    ok = np.isfinite(ref["price"]) & (ref["err"] < 1e-2)
+    err = cx.reduce([float(np.max(np.abs(got - ref["price"])[ok]))], "max")[0]
+    return {"workload": "C5: 100M-put surface (1000 strikes x 1000 maturities x 100 vols), FastAmericanOptionSolverA n=12 l=32 m=64 tol=1e-5 "
+                        "max_iters=20; one boundary solve per (T, sigma) scenario shared by its 1000 strikes, each strike stopping at its "
+                        "own sweep as upstream's absolute rule does (BASELINE.json configs[4], SURVEY 8f row 1)",
+            "value": G * nK / (ms / 1e3), "unit": UNIT, "ms_per_step": ms, "scaling": "strong", "n_gpus": cx.world,
+            "rank_ms_max": ms, "rank_ms_min": ms_min, "rank_imbalance": ms / ms_min - 1.0,
+            "parallelism": "scenario g -> rank g mod %d (round-robin deal), no collective on the data path" % cx.world,
+            "scenarios": G, "strikes": nK, "checksum_micro_units": int(chk.item()),
+            "max_abs_err_vs_cpu_port": err, "parity_sample": int(32 * cx.world),
+            "gpu_launches_per_step": launches / max(steps, 1),
+            "l2": "output (%d MB per rank) exceeds L2" % (g * nK * 8 >> 20)}
 
 
 def main():
@@ -207,97 +368,96 @@ def main():
     ap.add_argument("--options", type=int, default=N_PER_GPU, help="options per GPU per step (default: the 1M of configs[1])")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--kernel", type=int, default=0)
+    ap.add_argument("--seed-mode", default="hybr", choices=["hybr", "newton"],
+                    help="root finder of the QD seed for the headline line: hybr = the library default (the reference's), newton = opt-in")
+    ap.add_argument("--skip-configs", action="store_true", help="headline C2 line only (no c3 / c4 / c5 legs)")
     ap.add_argument("--workload", default="c2", choices=["c2", "c5"],
-                    help="c2 (default, the headline line) or c5: the 100M-option surface as 100k (T, sigma) scenarios x "
-                         "1000 strikes through the deduplicated ladder path, scenarios cut across the ranks (strong scaling)")
+                    help="c2 (default: the headline line, carrying c3 / c4 / c5 under `configs`) or c5 alone as its own line")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
-    if args.workload == "c5":
-        return run_c5(args)
 
     import torch
-    import torch.distributed as dist
     from fastamericanoptionpricing_b200 import batch
-
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+    cx = Ctx()
+    rank, world, dev = cx.rank, cx.world, cx.dev
     W = max(args.warmup, 3)
+    if args.workload == "c5":
+        sampler = ClockSampler(cx.local)
+        sampler.start()
+        c5 = leg_c5(cx, args.steps)
+        clocks = sampler.stop()
+        if rank == 0:
+            line = {"metric": METRIC, "value": c5["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": 3,
+                    "ms_per_step": c5["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+                    "data": "synthetic", "config": {k: c5[k] for k in ("workload", "scenarios", "strikes", "parallelism", "l2")},
+                    "gpu_launches": int(c5["gpu_launches_per_step"] * args.steps), "clocks": clocks,
+                    "checksum_micro_units": c5["checksum_micro_units"], "rank_ms_max": c5["rank_ms_max"], "rank_ms_min": c5["rank_ms_min"],
+                    "max_abs_err_vs_cpu_port": c5["max_abs_err_vs_cpu_port"]}
+            print(json.dumps(line), flush=True)
+        return cx.close()
+
     Nopt = args.options
     cfgd = dict(wl.C2_CFG)
-    cfg = batch.AloConfig(kernel=args.kernel, **cfgd)
+    cfg = batch.AloConfig(kernel=args.kernel, seed=args.seed_mode, **cfgd)
+    cfg_alt = batch.AloConfig(kernel=args.kernel, seed="newton" if args.seed_mode == "hybr" else "hybr", **cfgd)
 
     # every rank prices its own slice of a world*Nopt batch: rank r gets the r-th independent 1M draw
     b = wl.c2_batch(Nopt, seed=wl.C2_SEED + 7919 * rank)
-    keys = ("r", "q", "sigma", "K", "T", "S")
-    host = {k: torch.from_numpy(np.ascontiguousarray(b[k])).pin_memory() for k in keys}
+    host = {k: torch.from_numpy(np.ascontiguousarray(b[k])).pin_memory() for k in KEYS[:6]}
     host["is_put"] = torch.from_numpy(b["is_put"].astype(np.uint8)).pin_memory()
     d = {k: v.to(dev) for k, v in host.items()}
-    args_dev = [d[k] for k in keys] + [d["is_put"]]
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    args_dev = [d[k] for k in KEYS]
 
     def step():
         return batch.price_batch(*args_dev, cfg=cfg, want_boundary=False)
 
     for _ in range(W):
         out = step()
-    barrier()
-    sampler = ClockSampler(local)
+    cx.barrier()
+    sampler = ClockSampler(cx.local)
     sampler.start()
     l0 = batch.launch_count()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    barrier()
+    cx.barrier()
     for s in range(args.steps):
-        flush.zero_()                       # L2 flush between timed iterations (outside the event pair)
+        cx.flush()                          # L2 flush between timed iterations (outside the event pair)
         ev[s][0].record()
         out = step()
         ev[s][1].record()
-    barrier()
+    cx.barrier()
     launches = batch.launch_count() - l0
-    ms_steps = [a.elapsed_time(b_) for a, b_ in ev]
-    ms_step = float(np.mean(ms_steps))
+    ms_step = float(np.mean([a.elapsed_time(b_) for a, b_ in ev]))
+
+    # the same step with the other seed mode (hybr = the reference's root finder, newton = the cheaper opt-in)
+    for _ in range(2):
+        batch.price_batch(*args_dev, cfg=cfg_alt, want_boundary=False)
+    ms_alt = cx.timed(lambda: batch.price_batch(*args_dev, cfg=cfg_alt, want_boundary=False), args.steps)
 
     # dominant kernel alone: borrowed seeds -> only the boundary/price kernel is launched
     seeds = batch.price_batch(*args_dev, cfg=cfg, want_boundary=True)
     B0 = seeds["B0"]
     iters_mean = float(seeds["iters"].double().mean().item())
     del seeds
-    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    for s in range(args.steps):
-        flush.zero_()
-        kev[s][0].record()
-        batch.price_batch(*args_dev, cfg=cfg, B0=B0, want_boundary=False)
-        kev[s][1].record()
-    torch.cuda.synchronize()
-    ms_kernel = float(np.mean([a.elapsed_time(b_) for a, b_ in kev]))
+    ms_kernel = cx.timed(lambda: batch.price_batch(*args_dev, cfg=cfg, B0=B0, want_boundary=False), args.steps)
     del B0
 
     # end to end through the host-buffer C-ABI entry point (pinned host arrays in, host arrays out)
-    ctx = batch.HostContext(local)
+    hctx = batch.HostContext(cx.local)
     hout = {"price": torch.empty(Nopt, dtype=torch.float64).pin_memory().numpy()}
-    hargs = [host[k].numpy() for k in keys] + [host["is_put"].numpy()]
+    hargs = [host[k].numpy() for k in KEYS]
     for _ in range(2):
-        ctx.price_batch(*hargs, cfg=cfg, out=hout)
-    barrier()
+        hctx.price_batch(*hargs, cfg=cfg, out=hout)
+    cx.barrier()
     e2e_t = []
     l1 = batch.launch_count()
     for s in range(args.steps):
-        flush.zero_()
+        cx.flush()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        ctx.price_batch(*hargs, cfg=cfg, out=hout)          # returns after the D2H copy has completed
+        hctx.price_batch(*hargs, cfg=cfg, out=hout)          # returns after the D2H copy has completed
         e2e_t.append(time.perf_counter() - t0)
-    barrier()
+    cx.barrier()
     clocks = sampler.stop()
     ms_e2e = 1e3 * float(np.mean(e2e_t))
     e2e_launches = batch.launch_count() - l1
@@ -306,24 +466,47 @@ def main():
     tf_peak, _ = batch.measure_fp64_peak(20)
     mix_pps, _ = batch.measure_point_mix_peak(10)
 
-    red = torch.tensor([ms_step, ms_e2e, ms_kernel], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(red, op=dist.ReduceOp.MAX)
-    ms_step, ms_e2e, ms_kernel = red.tolist()
+    ms_step, ms_e2e, ms_kernel, ms_alt = cx.reduce([ms_step, ms_e2e, ms_kernel, ms_alt], "max")
     value = world * Nopt / (ms_step / 1e3)
     e2e_value = world * Nopt / (ms_e2e / 1e3)
+
+    threads = len(os.sched_getaffinity(0))
+    configs = {}
+    if not args.skip_configs:
+        cx.barrier()
+        configs["c5"] = leg_c5(cx, max(3, min(args.steps, 10)))       # all ranks
+        if rank == 0:
+            configs["c3"] = leg_c3(cx, max(2, min(args.steps, 5)), threads)
+            configs["c4"] = leg_c4(cx, args.steps)
+        cx.barrier()
 
     if rank == 0:
         fl = flops_per_option(cfgd["solver"], cfgd["n"], cfgd["l"], cfgd["m"], iters_mean)
         achieved = fl * Nopt / (ms_kernel / 1e3) / 1e12
-        threads = len(os.sched_getaffinity(0))
         cpu_rate, cpu_count, cpu_dt, cpu_out = cpu_port_rate(cfgd, b, args.cpu_seconds, threads)
         # the CPU leg doubles as a live parity check of this very run
         p = out["price"].cpu().numpy()[:cpu_count]
         ok = np.isfinite(cpu_out["price"]) & (cpu_out["err"] < 1e-2)
         max_abs = float(np.max(np.abs(p - cpu_out["price"])[ok]))
+        nan_equal = bool(np.array_equal(np.isnan(p), np.isnan(cpu_out["price"])))
         h2d = Nopt * (6 * 8 + 1)
         d2h = Nopt * 8
+        prof = kernel_profile("alo_fast_A12_kernel") if args.kernel == 0 else None
+        executed = None
+        if prof:
+            sc = iters_mean / prof["mean_iterations"]          # the counters were taken at the profile run's own mean sweep count
+            fpo = prof["flops_executed_per_option"] * sc
+            executed = {"flops_per_option": fpo, "tflops": fpo * Nopt / (ms_kernel / 1e3) / 1e12,
+                        "frac": fpo * Nopt / (ms_kernel / 1e3) / 1e12 / tf_peak,
+                        "fp64_pipe_active_pct_ncu": prof["fp64_pipe_active_pct"],
+                        # what bounds the kernel: an FP64 warp instruction holds the SMSP issue port for two cycles,
+                        # any other for one; counts per option from the ncu source page, scaled to this run's sweep count
+                        "issue_port_frac": (2 * prof["fp64_warp_inst_per_option"] + prof["other_warp_inst_per_option"]) * sc /
+                                           (ms_kernel * 1e-3 * (clocks["sm_mhz"] or 1965.0) * 1e6 * kSMSP / Nopt),
+                        "points_per_s": Nopt * iters_mean * cfgd["n"] * cfgd["l"] / (ms_kernel / 1e3),
+                        "point_math_peak_points_per_s": mix_pps,
+                        "point_math_frac": Nopt * iters_mean * cfgd["n"] * cfgd["l"] / (ms_kernel / 1e3) / mix_pps,
+                        "source": "profiles/kernel_profile.json", "source_hash": prof["source_hash"], "stale": prof["stale"]}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": W,
                 "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic",
@@ -331,48 +514,34 @@ def main():
                                        "max_iters=20 (BASELINE.json configs[1])",
                            "options_per_gpu": Nopt, "seed": wl.C2_SEED, "parallelism": "dp%d independent slices, no collective" % world,
                            "l2": "flushed (256 MB write) between timed iterations; inputs 49 MB/GPU",
-                           "mean_iterations": iters_mean, "kernel": "auto" if args.kernel == 0 else "generic"},
-                "max_abs_err_vs_cpu_port": max_abs, "parity_sample": int(ok.sum()),
+                           "mean_iterations": iters_mean, "kernel": "auto" if args.kernel == 0 else "generic",
+                           "qd_seed": "%s (%s)" % (cfg.seed, "the reference's root finder, MINPACK hybrd restated: library default"
+                                                    if cfg.seed == "hybr" else "safeguarded Newton, opt-in")},
+                "max_abs_err_vs_cpu_port": max_abs, "parity_sample": int(ok.sum()), "nan_pattern_equal_to_cpu_port": nan_equal,
+                "other_seed_mode": {"qd_seed": cfg_alt.seed, "value": world * Nopt / (ms_alt / 1e3), "ms_per_step": ms_alt},
                 "roofline": {"bound": "fp64", "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s",
                              "frac": achieved / tf_peak,
-                             # dram__bytes_read+write of the dominant kernel, per launch: 153.5 B/option measured by
-                             # ncu --set full (profiles/r1_alo_fast_A12_ncu_full.csv) == the algorithmic 49 B in + 104 B seeds
-                             "traffic": 153.5 * Nopt if args.kernel == 0 else None,
+                             # dram__bytes_read+write of the dominant kernel per launch, from the committed ncu capture
+                             "traffic": (prof["dram_bytes_per_option"] * Nopt) if prof else None,
+                             "traffic_algorithmic": (49 + 8 * (cfgd["n"] + 1) + 8) * Nopt,
                              "kernel": "alo_fast_A12_kernel" if args.kernel == 0 else "alo_generic_kernel",
-                             "kernel_ms": ms_kernel, "flops_per_option": fl,
+                             "kernel_ms": ms_kernel, "kernel_share_of_step": ms_kernel / ms_step, "flops_per_option": fl,
                              "flop_model": "SURVEY 8d nominal: add/mul 1, FMA 2, div/sqrt 16, exp 40, log 56, Phi 120, phi 42 "
-                                           "at the realised mean iteration count",
-                             # hardware-side view of the same launch: DFMA x2 + DMUL + DADD thread instructions per option
-                             # counted by ncu (profiles/r1_alo_fast_A12_ncu_full.csv, 1.131 MFLOP at 19.32 sweeps), scaled
-                             # to this run's sweep count; the nominal model prices exp/Phi/sqrt as 40/120/16 flops where
-                             # the kernel spends 24/50/12, which is why `frac` can exceed 1
-                             "executed": None if args.kernel != 0 else {
-                                 "flops_per_option": 1.131e6 * iters_mean / 19.316,
-                                 "tflops": 1.131e6 * iters_mean / 19.316 * Nopt / (ms_kernel / 1e3) / 1e12,
-                                 "frac": 1.131e6 * iters_mean / 19.316 * Nopt / (ms_kernel / 1e3) / 1e12 / tf_peak,
-                                 "fp64_pipe_active_pct_ncu": 70.7,
-                                 # what actually bounds the kernel: an FP64 warp instruction holds the SMSP issue
-                                 # port for two cycles, any other for one.  21.34 k FP64 + 15.12 k other warp instructions per
-                                 # option at 19.32 sweeps (ncu source page) over this run's cycles per option and SMSP
-                                 "issue_port_frac": (2 * 21335.4 + 15116.2) * iters_mean / 19.316 /
-                                                    (ms_kernel * 1e-3 * (clocks["sm_mhz"] or 1965.0) * 1e6 * kSMSP / Nopt),
-                                 # quadrature points/s of this launch (options * sweeps * n * l) over the rate of the same
-                                 # per-point math on register operands alone, measured in this run (faop_measure_point_mix_peak):
-                                 # what the loads, reductions, node closures, seeds and the price integral cost on top
-                                 "points_per_s": Nopt * iters_mean * cfgd["n"] * cfgd["l"] / (ms_kernel / 1e3),
-                                 "point_math_peak_points_per_s": mix_pps,
-                                 "point_math_frac": Nopt * iters_mean * cfgd["n"] * cfgd["l"] / (ms_kernel / 1e3) / mix_pps},
+                                           "at the realised mean iteration count; the kernel spends 24/50/12 instructions on "
+                                           "exp/Phi/sqrt, which is why `frac` can exceed 1 — `executed` is the hardware-side view",
+                             "executed": executed,
                              "peak_source": "register-operand DFMA chains measured in this run (faop_measure_fp64_peak); "
                                             "MEASURED_PEAKS.json has no FP64 figure"},
                 "cpu_baseline": {"value": cpu_rate, "unit": UNIT, "cores": threads, "kind": "port",
                                  "sample": "first %d options of rank 0's batch, %.1f s, plain-C port of the reference "
-                                           "algorithm on %d pthreads" % (cpu_count, cpu_dt, threads)},
+                                           "algorithm (hybrd seed) on %d pthreads" % (cpu_count, cpu_dt, threads)},
+                "cpu_baseline_python": SURVEY_PYTHON,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": ms_e2e, "bitwise_equal_to_device_path": same},
-                "gpu_launches": int(launches), "gpu_launches_e2e": e2e_launches, "clocks": clocks}
+                "gpu_launches": int(launches), "gpu_launches_e2e": e2e_launches, "clocks": clocks,
+                "configs": configs}
         print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    cx.close()
 
 
 if __name__ == "__main__":

@@ -111,6 +111,19 @@ def load():
     return lib
 
 
+def kernel_source_hash():
+    """sha256 (first 16 hex digits) of the CUDA sources.  profiles/kernel_profile.json records the hash of the build its ncu counters
+    were taken from; bench.py marks the counters `stale` when the sources have changed since."""
+    import hashlib
+    h = hashlib.sha256()
+    d = os.path.join(_HERE, "csrc")
+    for f in sorted(os.listdir(d)):
+        if f.endswith((".cu", ".cuh", ".h")):
+            h.update(f.encode())
+            h.update(open(os.path.join(d, f), "rb").read())
+    return h.hexdigest()[:16]
+
+
 def declared_symbols():
     """Every entry point include/faop.h declares (kept in step by tests/test_abi.py)."""
     return sorted(_SIGNATURES)

@@ -74,8 +74,65 @@ def full(rep, dst, options):
         f.write("TOTAL,%d,100,%.1f\n" % (tot, tot / options))
 
 
+def kernel_json(rep, dst, name, options, mean_iters):
+    """Merge the counters bench.py quotes for kernel `name` into profiles/kernel_profile.json, stamped with the hash of the
+    CUDA sources the capture was taken from (bench.py prints "stale": true once they differ)."""
+    import json
+    import os
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from fastamericanoptionpricing_b200 import _lib
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv", "--print-units", "base"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    d = dict(zip(rows[0], rows[2]))
+    units = dict(zip(rows[0], rows[1]))
+
+    def num(k):
+        return float(d[k].replace(",", ""))
+    src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+    srows = list(csv.reader(src.splitlines()))
+    shdr, sdata = srows[1], srows[2:]
+    ci, si, ti = shdr.index("Instructions Executed"), shdr.index("Source"), shdr.index("Predicated-On Thread Instructions Executed")
+    fp64 = other = 0
+    flops = 0
+    for r in sdata:
+        if len(r) <= ci or not r[ci].isdigit():
+            continue
+        m = re.match(r"(@!?U?P\d+\s+)?([A-Z0-9_]+)", r[si].strip())
+        op = m.group(2) if m else ""
+        if op in ("DFMA", "DMUL", "DADD", "DSETP", "DMNMX"):
+            fp64 += int(r[ci])
+        else:
+            other += int(r[ci])
+        if op in ("DFMA", "DMUL", "DADD"):
+            flops += int(r[ti]) * (2 if op == "DFMA" else 1)
+    assert units["gpu__time_duration.sum"] in ("ns", "nsecond"), units["gpu__time_duration.sum"]
+    entry = {"kernel": d.get("Kernel Name", name), "options": options, "mean_iterations": mean_iters,
+             "duration_ms": num("gpu__time_duration.sum") / 1e6,
+             "registers": int(num("launch__registers_per_thread")),
+             "fp64_pipe_active_pct": num("sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active"),
+             "issue_active_pct": num("smsp__issue_active.avg.pct_of_peak_sustained_active"),
+             "flops_executed_per_option": flops / options,
+             "fp64_warp_inst_per_option": fp64 / options, "other_warp_inst_per_option": other / options,
+             "dram_bytes_per_option": (num("dram__bytes_read.sum") + num("dram__bytes_write.sum")) / options,
+             "local_loads": num("sass__inst_executed_local_loads") if "sass__inst_executed_local_loads" in d else None,
+             "capture": os.path.basename(rep)}
+    try:
+        prof = json.load(open(dst))
+    except Exception:
+        prof = {"kernels": {}}
+    h = _lib.kernel_source_hash()
+    if prof.get("source_hash") != h:        # a new build: counters of the old one do not carry over
+        prof = {"kernels": {}}
+    prof["source_hash"] = h
+    prof["kernels"][name] = entry
+    json.dump(prof, open(dst, "w"), indent=1, sort_keys=True)
+    print(json.dumps(entry))
+
+
 if __name__ == "__main__":
     if sys.argv[1] == "launches":
         launches(sys.argv[2], sys.argv[3])
+    elif sys.argv[1] == "json":        # json <rep> <dst.json> <kernel key> <options> <mean sweeps>
+        kernel_json(sys.argv[2], sys.argv[3], sys.argv[4], int(sys.argv[5]), float(sys.argv[6]))
     else:
         full(sys.argv[2], sys.argv[3], int(sys.argv[4]))
