@@ -123,6 +123,7 @@ __global__ void __launch_bounds__(kCnThreads, (NPT <= 8 ? 2 : 1)) cn_scan_kernel
     double* s_fwC = s_clo + 4;           // [warp][w]: d' entering `warp` = sum_w s_fwC[warp][w] * (forward total B of warp w); per dt
     double* s_bwK = s_fwC + kCnWarps * kCnWarps;   // unprojected: [warp][w] coefficients of the backward totals, [warp][kCnWarps] of X_{N-1}
     double* s_misc = s_bwK + kCnWarps * (kCnWarps + 1);          // [0] flag: some R_i < 0 outside the thread of node 0, [1] payoff at the last node
+    double* s_dl = s_misc + 8;           // [warp] D of the warp's last slot (the neighbour above rebuilds that slot's X from it: no halo barrier)
 
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const int n = a.n_space;
@@ -145,6 +146,10 @@ __global__ void __launch_bounds__(kCnThreads, (NPT <= 8 ? 2 : 1)) cn_scan_kernel
             xlast = xin ? xin[n - 1] : fmax(K - grid_point(n - 1, n, Sm), 0.0);
         }
         double Af[5], Ab[5], excA = 0.0, nxtA = 0.0, cR3 = 0.0, cR4 = 0.0, cinv = 0.0;
+        // halo without a barrier of its own: hr (used by lane 31) = X of the first slot of the warp above = the value `v` that
+        // entered this warp in the last back-substitution; hl (used by lane 0) = X of the last slot of the warp below, rebuilt
+        // from that slot's D (published before the back-substitution barrier) and its per-dt constants Rl, Gl
+        double hl = 0.0, hr = 0.0, Rl = 0.0, Gl = 0.0;
         // time stepping: either the caller's schedule, or solvePDE's countdown `while t > 0: dt = min(t, max_dt); ...; t -= dt`
         // (CrankNicolsonOptionSolver.py:36-45) in the same IEEE arithmetic, including its last ~1e-16-long step
         const bool sched = a.dts != nullptr;
@@ -158,6 +163,9 @@ __global__ void __launch_bounds__(kCnThreads, (NPT <= 8 ? 2 : 1)) cn_scan_kernel
         __syncthreads();                          // the previous option's output pass is done with s_seq
         if (lane == 0) s_eL[warp] = X[0];
         if (lane == 31) s_eR[warp] = X[NPT - 1];
+        __syncthreads();
+        hl = (warp > 0) ? s_eR[warp - 1] : 0.0;
+        hr = (warp < kCnWarps - 1) ? s_eL[warp + 1] : xlast;   // node N-2 sees X_{N-1}
         for (int st = 0; sched ? st < nsteps : trem > 0; ++st) {
             const double dt = sched ? a.dts[opt * a.max_steps + st] : fmin(trem, mdt);
             if (!sched) {
@@ -240,6 +248,10 @@ __global__ void __launch_bounds__(kCnThreads, (NPT <= 8 ? 2 : 1)) cn_scan_kernel
                     const double m3 = cR3 * m2, m4 = cR4 * m3;
                     cinv = 1.0 / (2.0 - m4 + 4.0 * m3 - 5.0 * m2);
                 }
+                if (warp > 0) {    // constants of the last slot of the warp below
+                    Rl = s_R[(NPT - 1) * kCnThreads + warp * 32 - 1];
+                    Gl = s_G[(NPT - 1) * kCnThreads + warp * 32 - 1];
+                }
                 __syncthreads();   // warp totals A visible
                 if (t < kCnWarps * kCnWarps) {
                     // d' entering warp `wr` = sum over w < wr of (prod_{w < v < wr} A_v) B_w: the products are per dt
@@ -266,13 +278,13 @@ __global__ void __launch_bounds__(kCnThreads, (NPT <= 8 ? 2 : 1)) cn_scan_kernel
                     }
                 }
                 dt_prev = dt;
+                __syncthreads();   // the warp-level coefficients are visible
             }
-            __syncthreads();   // halo values (and, after a dt change, the warp-level coefficients) are visible
             // ---- right-hand side, already scaled by 1/den: P_i = Q_i X_{i-1} + O_i X_i + R_i X_{i+1}
             double xl = __shfl_up_sync(kFullMask, X[NPT - 1], 1);
             double xr = __shfl_down_sync(kFullMask, X[0], 1);
-            if (lane == 0) xl = (warp > 0) ? s_eR[warp - 1] : 0.0;
-            if (lane == 31) xr = (warp < kCnWarps - 1) ? s_eL[warp + 1] : xlast;   // node N-2 sees X_{N-1}
+            if (lane == 0) xl = hl;
+            if (lane == 31) xr = hr;
             double D[NPT];
 #pragma unroll
             for (int j = 0; j < NPT; ++j) {
@@ -330,6 +342,7 @@ __global__ void __launch_bounds__(kCnThreads, (NPT <= 8 ? 2 : 1)) cn_scan_kernel
                     s_bwB[warp] = B;
                     if (PROJ) s_bwC[warp] = C;
                 }
+                if (lane == 31) s_dl[warp] = D[NPT - 1];
                 __syncthreads();
                 // last row: x = X_{N-1} from D_{N-4..N-2}
                 const double p2 = s_clo[2];
@@ -339,12 +352,8 @@ __global__ void __launch_bounds__(kCnThreads, (NPT <= 8 ? 2 : 1)) cn_scan_kernel
                 if (PROJ) xlast = dmax(xlast, s_misc[1]);
                 double v = xlast;
                 if (PROJ) {
-#pragma unroll
-                    for (int w = kCnWarps - 1; w > 0; --w) {
-                        const double Aw = s_bwA[w], Bw = s_bwB[w], Cw = s_bwC[w];
-                        const double y = fma(Aw, v, Bw);
-                        if (w > warp) v = dmax(y, Cw);
-                    }
+                    for (int w = kCnWarps - 1; w > warp; --w)       // warp-uniform trip count: only the warps above this one
+                        v = dmax(fma(s_bwA[w], v, s_bwB[w]), s_bwC[w]);
                 } else {    // affine maps superpose: a dot product with per-dt coefficients
                     const double* ck = s_bwK + warp * (kCnWarps + 1);
                     v = ck[kCnWarps] * xlast;
@@ -365,6 +374,11 @@ __global__ void __launch_bounds__(kCnThreads, (NPT <= 8 ? 2 : 1)) cn_scan_kernel
                     if (PROJ) xn = dmax(xn, s_G[j * kCnThreads + t]);
                     X[j] = xn;
                     xin = xn;
+                }
+                hr = (warp < kCnWarps - 1) ? v : xlast;
+                if (warp > 0) {     // X of the last slot of the warp below: the same arithmetic its owner performs (lane 0's X[0] enters it)
+                    hl = fma(Rl, X[0], s_dl[warp - 1]);
+                    if (PROJ) hl = dmax(hl, Gl);
                 }
             } else {
                 // some R_i < 0 away from S = 0 (q >> r with tiny sigma): the max-affine maps are not monotone there,
@@ -394,9 +408,13 @@ __global__ void __launch_bounds__(kCnThreads, (NPT <= 8 ? 2 : 1)) cn_scan_kernel
                     X[j] = (i >= 0) ? s_seq[i] : 0.0;
                 }
                 xlast = s_seq[n - 1];
+                {   // halos from the sequential result
+                    const int il = warp * 32 * NPT - 1 - off, ir = (warp + 1) * 32 * NPT - off;
+                    hl = (warp > 0 && il >= 0) ? s_seq[il] : 0.0;
+                    hr = (warp < kCnWarps - 1) ? s_seq[ir] : xlast;
+                }
+                __syncthreads();   // before the next step's forward totals / the next fallback overwrite s_seq
             }
-            if (lane == 0) s_eL[warp] = X[0];
-            if (lane == 31) s_eR[warp] = X[NPT - 1];
         }
         // ---- output: X (optional) and np.interp(S0, S, X) (:32-34)
         __syncthreads();
@@ -532,7 +550,7 @@ __global__ void cn_rows_kernel(int64_t N, int n, const double* r, const double* 
 template <int NPT, bool PROJ>
 static int launch_scan(const CnArgs& a, cudaStream_t st) {
     constexpr int NS = kCnThreads * NPT;
-    size_t sm = sizeof(double) * (size_t)(5 * NS + 2 + 7 * kCnWarps + kCnWarps * (2 * kCnWarps + 1) + 8);
+    size_t sm = sizeof(double) * (size_t)(5 * NS + 2 + 7 * kCnWarps + kCnWarps * (2 * kCnWarps + 1) + 8 + kCnWarps);
     FAOP_CUDA_OK(cudaFuncSetAttribute(cn_scan_kernel<NPT, PROJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     int64_t grid = a.N < (int64_t)kSMs * 8 ? a.N : (int64_t)kSMs * 8;
     cn_scan_kernel<NPT, PROJ><<<(unsigned)grid, kCnThreads, sm, st>>>(a);
