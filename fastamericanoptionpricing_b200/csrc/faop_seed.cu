@@ -24,17 +24,18 @@ struct SeedC {      // per (option, tau) invariants, formed exactly as the refer
 
 __device__ __forceinline__ double seed_Phi(double x) { return 0.5 * erfc(-x * kInvSqrt2); }
 
+// One expression for puts and calls, so that a warp holding both does not split: with om = +1 (put) / -1 (call),
+// P1 = Phi(-om d1), P2 = Phi(-om d2) and v = K e^{-r tau} P2 - S e^{-q tau} P1, the put's residual (:124) is
+// (1 - e^{-q tau} P1) S + qQD ((K - S) - v) with p = v, and the call's (:122), (1 - e^{-q tau} P1) S - qQD ((S - K) - c) with
+// c = -v, is the same number bit for bit: negation is exact, so (S - K) - c = -((K - S) - v) and -qQD (-X) = qQD X.
 __device__ __forceinline__ double seed_F(const SeedC& c, double S) {
     const double d1 = log(S * c.Ed / c.K) / c.vs + c.hv;          // EuropeanOptionSolver.py:35-36
     const double d2 = d1 - c.vs;                                   // :39-40
-    if (c.put) {
-        const double P1 = seed_Phi(-d1);
-        const double p = c.Ker * seed_Phi(-d2) - S * c.eq * P1;    // :13
-        return (1 - c.eq * P1) * S + c.qQD * (c.K - S - p);        // QDplusAmericanOptionSolver.py:124
-    }
-    const double P1 = seed_Phi(d1);
-    const double cv = S * c.eq * P1 - c.Ker * seed_Phi(d2);        // :22
-    return (1 - c.eq * P1) * S - c.qQD * (S - c.K - cv);           // :122
+    const double om = c.put ? 1.0 : -1.0;
+    const double P1 = 0.5 * erfc((om * d1) * kInvSqrt2);           // Phi(-om d1) = erfc(om d1 / sqrt2) / 2
+    const double P2 = 0.5 * erfc((om * d2) * kInvSqrt2);
+    const double v = c.Ker * P2 - S * c.eq * P1;                   // :13 (put value; the call value :22 is -v)
+    return (1 - c.eq * P1) * S + c.qQD * (c.K - S - v);
 }
 
 // hybrd for one unknown as a state machine around ONE residual evaluation per trip: `phase` says what the value just computed
@@ -181,31 +182,76 @@ __device__ __forceinline__ SeedC seed_consts(double tau, double r, double q, dou
     return c;
 }
 
-// one thread per (option, node), NODE-MAJOR: thread g handles node j = g / N of option g % N, so a warp holds the same node of
-// 32 consecutive options.  hybrd's evaluation count depends mostly on tau_j (9-12 at the long nodes, 18-30 at the shortest),
-// so lanes of a warp finish closer together; the option parameters load coalesced; the 8-byte stores are strided by n+1 (104 MB
-// per 1M options in all, the L2 merges them).  Writes seeds_out[opt * (n+1) + j].
-// Measured alternatives (B200, 1M C2 options, seed kernel alone): the textbook nesting with the residual inlined at three sites
-// 17.2 ms; this state machine 11.3 ms; the same with a warp vote per trip so that finished lanes wait (all lanes re-evaluate) 13.2 ms;
-// persistent warps dealing items to lanes as they finish 13.9 ms — the lane-private bookkeeping and the per-item setup then run
-// under divergence on almost every trip and cost what the refill saves.
-__global__ void __launch_bounds__(128) qd_seed_hybr_kernel(AloArgs a) {
-    const int nn = a.tl.n + 1;
-    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= a.N * nn) return;
-    const int j = (int)(g / a.N);
-    const int64_t opt = g - (int64_t)j * a.N;
-    const double r = a.r[opt], q = a.q[opt], sg = a.sigma[opt], K = a.K[opt];
-    const double T = a.tau_max ? a.tau_max[opt] : a.T[opt];      // collocation domain [0, tau_max], Base.py:28,223
-    const bool put = a.is_put[opt] != 0;
-    double* out = a.seeds_out + opt * nn + j;
-    if (q == 0 && !put) {     // European shortcut (Base.py:50-53): no boundary is solved
-        *out = nan("");
-        return;
+// Persistent warps with LANE-LEVEL REFILL.  hybrd needs 9-12 evaluations at the long nodes, 18-30 at the shortest and now and then
+// 50; with one thread per root and the lanes of a warp left to themselves only a third of the lanes is active on average (ncu:
+// 4.4 k FP64 warp instructions per option against 1.4 k if all 32 lanes worked; 11.3 ms per 1M C2 options).  Measured steps to
+// this form: a vote per trip so that finished lanes wait, 13.2 ms (the slowest lane of 32 sets the pace); dealing items to lanes as
+// they finish from NODE-major ranges, 13.9 ms (the warps that own the short nodes finish last); OPTION-major ranges, 10.2 ms; one
+// residual expression for puts and calls (seed_F), so that a warp holding both does not split, and refills batched by the
+// quarter-warp, 6.7 ms with 23 of 32 lanes active on average and the residual itself at 31-32.  So every warp owns a contiguous range of the
+// N n root problems — OPTION-major (item g = node g % n of option g / n), so that every range holds the same mix of cheap and
+// expensive nodes — and deals them to its lanes one at a time: a lane that has finished takes the next item of the range at the
+// top of the next trip.  One residual evaluation per trip for all 32 lanes side by side; the lane-private parts (taking an item,
+// hybrd's bookkeeping) are what diverges.
+constexpr int kSeedThreads = 128;
+constexpr int kSeedRefill = 8;
+__global__ void __launch_bounds__(kSeedThreads) qd_seed_hybr_kernel(AloArgs a, int refill) {
+    const int n = a.tl.n, nn = n + 1;
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * kSeedThreads + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * kSeedThreads) >> 5;
+    const int64_t total = a.N * n;
+    // the pinned node tau_n = 0 (B_at_zero) and the European shortcut rows, grid-stride
+    for (int64_t o = (int64_t)blockIdx.x * kSeedThreads + threadIdx.x; o < a.N; o += (int64_t)gridDim.x * kSeedThreads) {
+        const bool put = a.is_put[o] != 0;
+        a.seeds_out[o * nn + n] = (a.q[o] == 0 && !put) ? nan("") : b_at_zero(a.r[o], a.q[o], a.K[o], put);
     }
-    const double cj = a.tables[a.tl.off_c + j];
-    const double tau = (cj + 1) * (cj + 1) * (T - 0.0) / 4 + 0.0;      // to_orig_point, Base.py:239-240
-    *out = (tau == 0) ? b_at_zero(r, q, K, put) : hybr1_seed(seed_consts(tau, r, q, sg, K, put));
+    const int64_t per = (total + nwarps - 1) / nwarps;
+    int64_t next = warp * per;                    // warp-uniform cursor into this warp's range
+    const int64_t end = (next + per < total) ? next + per : total;
+    Hybr s;
+    SeedC c;
+    c.K = 1.0; c.qQD = -1.0; c.Ed = 1.0; c.vs = 1.0; c.hv = 0.5; c.Ker = 1.0; c.eq = 1.0; c.put = true;    // harmless idle problem
+    s.start(1.0);
+    bool have = false;
+    double* dst = nullptr;
+    for (;;) {
+        const unsigned need = __ballot_sync(0xffffffffu, !have);
+        // deal new items only once a quarter of the lanes is idle (or nothing is running): the per-item setup (four exponentials,
+        // two square roots, a handful of divisions) then runs with >= 8 lanes instead of one or two at a time
+        if (next < end && (__popc(need) >= refill || need == 0xffffffffu)) {                 // warp-uniform
+            if (!have) {
+                const int64_t g = next + __popc(need & ((1u << lane) - 1));
+                if (g < end) {
+                    const int64_t opt = g / n;
+                    const int j = (int)(g - opt * n);
+                    const double r = a.r[opt], q = a.q[opt], sg = a.sigma[opt], K = a.K[opt];
+                    const double T = a.tau_max ? a.tau_max[opt] : a.T[opt];      // collocation domain [0, tau_max], Base.py:28,223
+                    const bool put = a.is_put[opt] != 0;
+                    const double cj = a.tables[a.tl.off_c + j];
+                    const double tau = (cj + 1) * (cj + 1) * (T - 0.0) / 4 + 0.0;      // to_orig_point, Base.py:239-240
+                    dst = a.seeds_out + opt * nn + j;
+                    if (q == 0 && !put) *dst = nan("");            // European shortcut (Base.py:50-53): no boundary is solved
+                    else if (tau == 0) *dst = b_at_zero(r, q, K, put);
+                    else {
+                        c = seed_consts(tau, r, q, sg, K, put);
+                        s.start(K);
+                        have = true;
+                    }
+                }
+            }
+            next += __popc(need);
+        }
+        if (!__any_sync(0xffffffffu, have)) {
+            if (next >= end) break;
+            continue;                             // a trip that only dealt trivial items
+        }
+        const double fe = seed_F(c, s.xe);        // all 32 lanes side by side (idle lanes evaluate their last problem again)
+        if (have && s.advance(fe)) {
+            *dst = s.x;
+            have = false;
+        }
+    }
 }
 
 // QDplus.compute_exercise_boundary per element (QDplusAmericanOptionSolver.py:69-76), the reference's root finder
@@ -280,7 +326,10 @@ static inline unsigned blocks_for(int64_t n, int threads) { return (unsigned)((n
 
 int launch_qd_seed_hybr(const AloArgs& a, cudaStream_t st) {
     if (a.N == 0) return 0;
-    qd_seed_hybr_kernel<<<blocks_for(a.N * (a.tl.n + 1), 128), 128, 0, st>>>(a);
+    // persistent: enough warps to fill the machine (5 CTAs of 4 warps per SM at ~96 registers), never more warps than 64-item ranges
+    const int64_t want = (a.N * a.tl.n + 64 * 4 - 1) / (64 * 4);
+    const int64_t cap = (int64_t)kSMs * 5;      // 4 or 5 CTAs per SM and a refill threshold of 4..12 lanes measure the same (60.5-61.5 ms per C2 step)
+    qd_seed_hybr_kernel<<<(unsigned)(want < cap ? (want > 0 ? want : 1) : cap), kSeedThreads, 0, st>>>(a, kSeedRefill);
     count_launch();
     return launch_status();
 }
