@@ -119,26 +119,26 @@ class FastAmericanOptionSolver(ABC):
         self.debug("collocation point = {0}".format(self.shared_tau))
         self.debug("step 3. checking numerical integration ...")
         self.test_numerical_integration()
-        out = _batch.price_batch(self.r, self.q, self.sigma, self.K, self.T, s0, self._is_put(), t=t, cfg=self._cfg(),
-                                 want_iter_errs=True, tau_max=self._tau_max())
+        out = _batch.price_one(self.r, self.q, self.sigma, self.K, self.T, s0, self._is_put(), t=t, cfg=self._cfg(),
+                               tau_max=self._tau_max())
         self._store(out)
         self.debug("step 6. checking exercise boundary ...")
         self.debug("exercise boundary = {0}".format(self.shared_B))
         if self.DEBUG:
             self.debug("match condition err = {0}".format(self.check_value_match_condition2()))
-        return np.float64(out["price"].item())
+        return out["price"]
 
     def _store(self, out):
-        self.shared_B0 = list(out["B0"].cpu().numpy()[0])
-        self.shared_B = list(out["B"].cpu().numpy()[0])
-        self.num_iters = int(out["iters"].item())
-        self.error = float(out["err"].item())
-        errs = out["iter_errs"].cpu().numpy()[0]
+        """results of batch.price_one (one packed device-to-host copy) into the reference's attributes"""
+        self.shared_B0 = list(out["B0"])
+        self.shared_B = list(out["B"])
+        self.num_iters = out["iters"]
+        self.error = out["err"]
+        errs = out["iter_errs"]
         for k in range(self.num_iters):
             self.debug("  iter = {0}, err = {1}".format(k + 1, errs[k]))
             self.iter_records.append((k + 1, float(errs[k])))
-        if "european" in out:
-            self.european_price = np.float64(out["european"].item())
+        self.european_price = out["european"]
 
     def compute_exercise_boundary(self):
         """reference :105-133 (seed + damped Jacobi loop); fills shared_B0, shared_B, error, num_iters, iter_records"""
@@ -148,8 +148,8 @@ class FastAmericanOptionSolver(ABC):
         if len(self.shared_tau) != self.collocation_num + 1:
             self.set_collocation_points()
         self.debug("step 5. starting iteration ...")
-        out = _batch.price_batch(self.r, self.q, self.sigma, self.K, self.T, self.K, self._is_put(), cfg=self._cfg(),
-                                 want_iter_errs=True, tau_max=self._tau_max())
+        out = _batch.price_one(self.r, self.q, self.sigma, self.K, self.T, self.K, self._is_put(), cfg=self._cfg(),
+                               tau_max=self._tau_max())
         eur = self.european_price
         self._store(out)
         self.european_price = eur

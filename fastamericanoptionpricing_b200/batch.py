@@ -198,6 +198,50 @@ def price_batch(r, q, sigma, K, T, S, is_put, t=None, cfg: AloConfig = AloConfig
         return out
 
 
+_ONE = {}
+
+
+def price_one(r, q, sigma, K, T, S, is_put, t=0.0, cfg: AloConfig = AloConfig(), tau_max=None, device=None):
+    """solve(t, s0) of ONE option (the drop-in classes' scalar path) with one host-to-device copy, the two kernel launches and
+    one device-to-host copy: the seven scalars travel as one pinned 80-byte block, every output (price, european, err, iters,
+    B, B0, the per-sweep errors) comes back as one block.  Buffers are cached per (device, n, max_iters).
+    Returns a dict of numpy values / arrays."""
+    lib = _lib.load()
+    dev = _device(device)
+    nn, mi = cfg.n + 1, int(cfg.max_iters)
+    key = (str(dev), nn, mi)
+    st = _ONE.get(key)
+    with torch.cuda.device(dev):
+        if st is None:
+            nout = 4 + 2 * nn + mi                  # price, european, err, iters(int32 in an 8-byte slot), B, B0, iter_errs
+            st = dict(hin=torch.empty(10, dtype=torch.float64).pin_memory(), din=torch.empty(10, dtype=torch.float64, device=dev),
+                      hout=torch.empty(nout, dtype=torch.float64).pin_memory(), dout=torch.empty(nout, dtype=torch.float64, device=dev))
+            _ONE[key] = st
+        h = st["hin"].numpy()
+        h[:8] = (r, q, sigma, K, T, t, S, T if tau_max is None else tau_max)
+        h[8:9].view(np.uint8)[0] = 1 if is_put else 0
+        din, dout = st["din"], st["dout"]
+        din.copy_(st["hin"], non_blocking=True)
+        base, ob = din.data_ptr(), dout.data_ptr()
+
+        def ip(i):
+            return ctypes.c_void_p(base + 8 * i)
+
+        def op(i):
+            return ctypes.c_void_p(ob + 8 * i)
+        c = cfg.c()
+        if tau_max is not None:
+            c.tau_max = base + 8 * 7
+        check(lib.faop_alo_price_batch(ctypes.byref(c), 1, ip(0), ip(1), ip(2), ip(3), ip(4), ip(5), ip(6), ip(8),
+                                       _ptr(tables_for(cfg, dev)), None, op(0), op(1), op(4), op(4 + nn), op(3), op(2),
+                                       op(4 + 2 * nn) if mi > 0 else None, None, _stream(dev)), "faop_alo_price_batch")
+        st["hout"].copy_(dout, non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()
+        o = st["hout"].numpy()
+        return dict(price=np.float64(o[0]), european=np.float64(o[1]), err=float(o[2]), iters=int(o[3:4].view(np.int32)[0]),
+                    B=o[4:4 + nn].copy(), B0=o[4 + nn:4 + 2 * nn].copy(), iter_errs=o[4 + 2 * nn:4 + 2 * nn + mi].copy())
+
+
 def collocation_tau(T, n):
     """set_collocation_points (FastAmericanOptionSolverBase.py:221-223): tau_i = (cos(i pi/n) + 1)^2 T / 4."""
     c = torch.as_tensor(np.cos(np.arange(n + 1) * np.pi / n), dtype=torch.float64, device=T.device)
