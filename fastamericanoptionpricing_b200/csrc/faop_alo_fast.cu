@@ -4,14 +4,24 @@
 // instantiation, FastAmericanOptionSolverB at the same sizes (the reference's testB case: per point two Phi instead of
 // one Phi and two phi, FastAmericanOptionSolverB.py:25-39, with both invariant tables w e^{qu}, w e^{ru} in shared memory).
 //
-// One option per warp, lane = quadrature index k.  What makes it fast (all FP64-pipe instruction savings):
-//   * H(u_ik) comes from the option-independent interpolation matrix M[i][j][k] staged once per CTA in shared
-//     memory (13 DFMA per point instead of a Clenshaw recurrence); the iterate H_j lives in registers;
-//   * e^{q u_ik} (iteration invariant) is computed once per option into shared memory;
-//   * per point: 2 fast_exp + 1 mills_half + 1 fast_sqrt, ~95 FP64 instructions (faop_fastmath.cuh);
-//   * the 24 per-node sums of one sweep are reduced by a transposing butterfly (10 shuffles per 4 nodes
-//     instead of 40) and closed by lanes 0..11 in one pass.
-// 16 warps per CTA, one CTA per SM, grid = min(#SM, ceil(N/16)) persistent CTAs striding over the batch.
+// One option per warp, lane = quadrature index k.  What makes it fast (all FP64-issue savings; the kernel sits at 95 % of the
+// issue bound `2 x FP64 + other` warp instructions per scheduler):
+//   * H(u_ik) comes from the option-independent interpolation matrix staged once per CTA in shared memory as
+//     M2[i][j/2][k][2] (one 16-byte load feeds two DFMAs, 12 DFMA per point instead of a Clenshaw recurrence; the j = n column
+//     multiplies H_n = 0 and is dropped); the iterate H_j lives in registers;
+//   * e^{q u_ik} (iteration invariant) is computed once per option into shared memory, with the quadrature weight folded in;
+//   * per point ~78 FP64 instructions: sqrt by rsqrt.approx + one third-order step, d+- as x = d/sqrt2 from packed per-node
+//     constants (four 16-byte broadcast loads), two exponentials with merged arguments exp(ln w + qu - d+^2/2) (degree-8 fits),
+//     Phi through erfcx(x)/2 = Q(t)/(x + c) (degree 16, one reciprocal), integer-ALU clamps and sign tests; two nodes advance in
+//     lock step (6 independent polynomial chains per lane), coefficients are constant-bank operands;
+//   * the 24 per-node sums of one sweep are reduced 4 nodes at a time through a shared-memory transpose (8 STS + 8 LDS +
+//     9 DADD + 2 shuffles, row pitch 36) and closed by lanes 0..12 in one pass; the stopping test is warp-uniform and uses the
+//     squared norm;
+//   * NaN outcomes (a node outside (0, inf)) are decided once per sweep on the full-accuracy log instead of being carried
+//     through the clamped fast paths.
+// 16 warps per CTA, one CTA per SM, grid = min(#SM, ceil(N/16)) persistent CTAs striding over the batch.  Static striding: a
+// warp prices ~420 options of a 1M batch, its total sweep count has a relative spread of 1.5 sqrt(420) / (19.3 x 420) = 0.4 %, so
+// a work counter would buy nothing at these sizes (the snapshot mode's tail is equally averaged).
 #include "faop_alo.cuh"
 #include "faop_fastmath.cuh"
 #include "faop_alo_fast.cuh"
