@@ -583,8 +583,39 @@ def gen_stress(pool):
     print("stress: %d options, nan %d, err>=1e-2 %d" % (len(idx), np.isnan(out["price"]).sum(), (out["err"] >= 1e-2).sum()))
 
 
+def gen_seedcases(pool):
+    """Where the seed's root finder matters (round 2): options picked by the ORACLE's own measures, run through the live reference.
+    (a) C2 options whose hybrd iterate is far from the Newton root at some node (hybrd exits on slow progress; upstream then turns to
+    NaN in the second sweep or converges from a different seed), (b) the worst-conditioned seeds of the stress batch, (c) a random
+    slice of the stress batch.  Solver A, n=12, l=32, m=64, tol 1e-5, 40 sweeps."""
+    from oracle import c_oracle as co
+    n = 12
+    c = np.cos(np.arange(n + 1) * np.pi / n)
+    picks = []
+    b2 = wl.c2_batch(200_000)
+    tau = np.square(c + 1)[None, :] * b2["T"][:, None] / 4
+    a2 = (tau, b2["r"][:, None], b2["q"][:, None], b2["sigma"][:, None], b2["K"][:, None], b2["is_put"][:, None])
+    with np.errstate(all="ignore"):
+        far = np.nanmax(np.abs(co.qd_boundary_batch(*a2, seed="hybr") / co.qd_boundary_batch(*a2, seed="newton") - 1), axis=1)
+    ia = np.argsort(-np.nan_to_num(far))[:48]
+    bs = wl.stress_batch(6000)
+    cond = co.seed_conditioning(bs["T"], bs["r"], bs["q"], bs["sigma"], bs["K"], bs["is_put"], n)
+    ib = np.argsort(-np.nan_to_num(cond))[:72]
+    ic = np.random.default_rng(99).choice(6000, 120, replace=False)
+    keys = ("r", "q", "sigma", "K", "T", "S", "is_put")
+    b = {k: np.concatenate([b2[k][ia], bs[k][ib], bs[k][ic]]) for k in keys}
+    b["t"] = np.zeros(len(b["r"]))
+    cfg = dict(wl.C2_CFG, max_iters=40)
+    out = run_batch(pool, "A", b, cfg, list(range(len(b["r"]))))
+    out["group"] = np.concatenate([np.zeros(len(ia), dtype=int), np.ones(len(ib), dtype=int), np.full(len(ic), 2)])
+    out["source_index"] = np.concatenate([ia, ib, ic])
+    np.savez(os.path.join(OUT, "ref_seedcases_A.npz"), **out)
+    print("seedcases: %d options, nan %d, err>=1e-2 %d, hybr-vs-newton seed distance of group a: min %.1e" % (
+        len(b["r"]), np.isnan(out["price"]).sum(), (out["err"] >= 1e-2).sum(), far[ia].min()))
+
+
 GENS = dict(c1=gen_c1, european=gen_european, cheb=gen_cheb, qd=gen_qd, stage=gen_stage, misc=gen_misc, cn=gen_cn, cn_state=gen_cn_state, domain=gen_domain,
-            c3=gen_c3, c2=gen_c2, bs=gen_bs, c5=gen_c5, stress=gen_stress)
+            c3=gen_c3, c2=gen_c2, bs=gen_bs, c5=gen_c5, stress=gen_stress, seedcases=gen_seedcases)
 
 
 def main():

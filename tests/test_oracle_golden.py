@@ -375,3 +375,43 @@ def _stress_checks(fn_price, tag, exact_seed=False):
 @pytest.mark.parametrize("name,fn", IMPLS)
 def test_stress_corners_golden(name, fn):
     _stress_checks(lambda a, kw, B0: fn("A", *a, B0=B0, **kw), "stress " + name, exact_seed=(name == "numpy"))
+
+
+def _seedcases_checks(fn_price, tag, numpy_impl=False):
+    """Shared by the CPU and the GPU suites: options chosen because the seed's root finder matters (ref_seedcases_A.npz, live
+    reference): 48 C2 options whose hybrd iterate is far from the root at some node (upstream turns to NaN in its second sweep on 45
+    of them), the 72 worst-conditioned seeds of the stress batch (none converges upstream) and 120 random stress options."""
+    g = load_golden("ref_seedcases_A.npz")
+    a = _inputs(g)
+    kw = dict(n=12, l=32, m=64, iter_tol=1e-5, max_iters=40)
+    out = fn_price(a, kw)
+    short = (g["in_q"] == 0) & ~g["in_is_put"]
+    # NaN for NaN with the same sweep count, on every option: a Newton seed misses 44 of the 45 upstream NaNs of the first group
+    assert np.array_equal(np.isnan(out["price"]), np.isnan(g["price"])), tag
+    isn = np.isnan(g["price"])
+    assert isn.sum() >= 40 and np.array_equal(out["iters"][isn], g["iters"][isn]), tag
+    ps = parity_set({k: g[k] for k in ("price", "err")}) & ~short & (g["B"] > 1e-3 * g["in_K"][:, None]).all(axis=1)
+    assert ps.sum() >= 100
+    dB = np.nanmax(np.abs(out["B"] / g["B"] - 1), axis=1)
+    dP = np.abs(out["price"] - g["price"])
+    over = np.nonzero(ps & ((dB > BOUNDARY_REL_TOL) | (dP > PRICE_ABS_TOL)))[0]
+    assert len(over) <= 0.05 * ps.sum(), (tag, len(over))
+    if numpy_impl:          # numpy/scipy arithmetic: the reference's seeds and answers themselves
+        assert len(over) == 0 and np.array_equal(out["B0"], g["B0"][:len(out["B0"])], equal_nan=True), tag
+    elif len(over):         # explained by the checker's own seed noise, as in _stress_checks
+        sB, sP, _ = co.seed_sensitivity("A", *[x[over] for x in a], **kw)
+        assert (dB[over] <= BOUNDARY_REL_TOL + 4 * sB).all() and (dP[over] <= PRICE_ABS_TOL + 4 * sP).all(), (tag, dB[over], sB)
+    assert (out["iters"][ps] != g["iters"][ps]).sum() == 0, tag
+
+
+def test_seedcases_golden():
+    _seedcases_checks(lambda a, kw: co.alo_price_batch("A", *a, **kw), "seedcases c")
+    # the numpy restatement (slow): the first 12 options of the first two groups, bit for bit
+    g = load_golden("ref_seedcases_A.npz")
+    sub = np.r_[0:12, 48:60]
+    out = o.alo_price_batch("A", *[x[sub] for x in _inputs(g)], n=12, l=32, m=64, iter_tol=1e-5, max_iters=40)
+    assert np.array_equal(out["B0"], g["B0"][sub], equal_nan=True) and np.array_equal(out["price"], g["price"][sub], equal_nan=True)
+    assert np.array_equal(out["iters"], g["iters"][sub])
+    # and the Newton seed does NOT reproduce upstream there (which is why hybrd is the default)
+    outn = co.alo_price_batch("A", *_inputs(g), seed="newton", n=12, l=32, m=64, iter_tol=1e-5, max_iters=40)
+    assert (np.isnan(outn["price"]) != np.isnan(g["price"])).sum() >= 30
