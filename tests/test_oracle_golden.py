@@ -386,10 +386,17 @@ def _seedcases_checks(fn_price, tag, numpy_impl=False):
     kw = dict(n=12, l=32, m=64, iter_tol=1e-5, max_iters=40)
     out = fn_price(a, kw)
     short = (g["in_q"] == 0) & ~g["in_is_put"]
-    # NaN for NaN with the same sweep count, on every option: a Newton seed misses 44 of the 45 upstream NaNs of the first group
-    assert np.array_equal(np.isnan(out["price"]), np.isnan(g["price"])), tag
+    # NaN for NaN with the same sweep count (a Newton seed misses 44 of the 45 upstream NaNs of the first group).  hybrd's exit can
+    # sit on a knife edge — on two of these options the ORACLE's own outcome flips between NaN-after-2-sweeps and a converged price
+    # when the normal cdf in the seed residual moves by one ulp — so an option may differ only if the checker itself flips there
     isn = np.isnan(g["price"])
-    assert isn.sum() >= 40 and np.array_equal(out["iters"][isn], g["iters"][isn]), tag
+    bad = np.nonzero((np.isnan(out["price"]) != isn) | (isn & (out["iters"] != g["iters"])))[0]
+    assert isn.sum() >= 40 and len(bad) <= 3, (tag, bad)
+    if numpy_impl:
+        assert len(bad) == 0, tag
+    elif len(bad):
+        sB, _, sflip = co.seed_sensitivity("A", *[x[bad] for x in a], **kw)
+        assert (np.isinf(sB) | sflip).all(), (tag, bad, sB, sflip)
     ps = parity_set({k: g[k] for k in ("price", "err")}) & ~short & (g["B"] > 1e-3 * g["in_K"][:, None]).all(axis=1)
     assert ps.sum() >= 100
     dB = np.nanmax(np.abs(out["B"] / g["B"] - 1), axis=1)
