@@ -336,8 +336,13 @@ def test_full_size_properties():
     isn = np.nonzero(np.isnan(p))[0]
     assert len(isn) <= 500      # ~2e-4 of C2: calls with q ~ 1e-4, X = rK/q ~ 600 K, where hybrd leaves one node's seed at ~K
     if len(isn):
-        refn = co.alo_price_batch("A", *[x[isn] for x in a], **{k: wl.C2_CFG[k] for k in ("n", "l", "m", "iter_tol", "max_iters")})
-        assert np.isnan(refn["price"]).all() and np.array_equal(refn["iters"], o1["iters"].cpu().numpy()[isn])
+        kwc = {k: wl.C2_CFG[k] for k in ("n", "l", "m", "iter_tol", "max_iters")}
+        refn = co.alo_price_batch("A", *[x[isn] for x in a], **kwc)
+        off = np.nonzero(~np.isnan(refn["price"]) | (refn["iters"] != o1["iters"].cpu().numpy()[isn]))[0]
+        assert len(off) <= 0.05 * len(isn), (len(off), len(isn))
+        if len(off):     # knife-edge hybrd exits: the checker's own outcome flips under a one-ulp probe of its seed residual
+            sB, _, sflip = co.seed_sensitivity("A", *[x[isn][off] for x in a], **kwc)
+            assert (np.isinf(sB) | sflip).all(), (isn[off], sB, sflip)
     ok = np.isfinite(p) & (o1["err"].cpu().numpy() < 1e-2)
     assert ok.mean() > 0.99
     assert np.all(p[ok] >= o1["european"].cpu().numpy()[ok] - 1e-7)                               # early exercise premium >= 0
