@@ -1,5 +1,5 @@
 // faop_alo_clen.cu — specialised boundary + price kernel for the configurations whose interpolation matrix does not fit
-// in shared memory: Solver A or B without derivative, n <= 28 collocation nodes (n a multiple of 4), l <= 64 quadrature
+// in shared memory: Solver A or B without derivative, any n <= 31 collocation nodes, l <= 64 quadrature
 // points.  BASELINE.json configs[2] (C3: FastAmericanOptionSolverB, n = 24, l = 64, m = 128) runs here.
 //
 // Same structure as faop_alo_fast.cu (one option per warp, lane = quadrature index, 4 nodes per shared-memory transpose
@@ -164,7 +164,7 @@ __global__ void __launch_bounds__(kClenWarps * 32, 1) alo_clen_kernel(AloArgs a)
 
             if (!degenerate) {
 #pragma unroll 1
-                for (int grp = 0; grp < n / 4; ++grp) {
+                for (int grp = 0; grp < (n + 3) / 4; ++grp) {      // the last group of an n that is no multiple of 4 repeats node n-1
                     double acc[8];
 #pragma unroll
                     for (int k8 = 0; k8 < 8; ++k8) acc[k8] = 0.0;
@@ -175,7 +175,7 @@ __global__ void __launch_bounds__(kClenWarps * 32, 1) alo_clen_kernel(AloArgs a)
                         double hh[2], rhh[2], gg[2], whh[2], z[2];
 #pragma unroll
                         for (int c = 0; c < 2; ++c) {
-                            nd_i[c] = (PPL == 2) ? grp * 4 + pr : grp * 4 + 2 * pr + c;
+                            nd_i[c] = min((PPL == 2) ? grp * 4 + pr : grp * 4 + 2 * pr + c, n - 1);
                             const int p = (PPL == 2) ? c : 0;
                             hh[c] = h[p]; rhh[c] = rh[p]; gg[c] = g[p]; whh[c] = wh[p];
                             z[c] = fma(ws.opc[nd_i[c]], sgk[p], -1.0);   // to_cheby_point(u_ik) = (1+c_i) sqrt(g_k) - 1
@@ -261,7 +261,9 @@ __global__ void __launch_bounds__(kClenWarps * 32, 1) alo_clen_kernel(AloArgs a)
                     const double tot = transpose_reduce8(acc, ws.red, lane);
                     if ((lane & 3) == 0) {
                         const int node = grp * 4 + (lane >> 3);
-                        if (lane & 4) ws.sD[node] = tot; else ws.sN[node] = tot;
+                        if (node < n) {
+                            if (lane & 4) ws.sD[node] = tot; else ws.sN[node] = tot;
+                        }
                     }
                 }
             }
@@ -325,7 +327,7 @@ static int launch_clen_t(const AloArgs& a, cudaStream_t st) {
 static bool clen_match(const faop_cfg& cfg) {
     const int n = cfg.n_colloc, LP = 32 * ((cfg.n_quad + 31) / 32);
     // n = 12, l <= 32 Solver A runs in the matrix kernel (faop_alo_fast.cu)
-    return !cfg.use_derivative && n % 4 == 0 && n + 1 <= kClenMaxNodes && LP <= 64;
+    return !cfg.use_derivative && n >= 2 && n + 1 <= kClenMaxNodes && LP <= 64;
 }
 
 // Scratch for the invariant tables: one region per resident warp of the persistent grid.  Used for Solver B (two of four
@@ -338,7 +340,7 @@ size_t alo_clen_scratch_bytes(const faop_cfg& cfg) {
 
 int launch_alo_clen(const AloArgs& a, cudaStream_t st) {
     const int n = a.tl.n;
-    const bool match = !a.cfg.use_derivative && n % 4 == 0 && n + 1 <= kClenMaxNodes && a.tl.LP <= 64 && a.iter_errs == nullptr && a.snap == nullptr;
+    const bool match = !a.cfg.use_derivative && n >= 2 && n + 1 <= kClenMaxNodes && a.tl.LP <= 64 && a.iter_errs == nullptr && a.snap == nullptr;
     if (!match) return -1000;
     if (a.N == 0) return 0;
     if (a.cfg.solver == 0) return a.tl.LP == 64 ? launch_clen_t<0, 2, false>(a, st) : launch_clen_t<0, 1, false>(a, st);

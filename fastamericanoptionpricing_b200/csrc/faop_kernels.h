@@ -48,7 +48,7 @@ int launch_iv_update(int64_t N, const double* target, const double* price, doubl
 int launch_alo_interp(const AloArgs& a, double* Bu, cudaStream_t st);
 // specialised kernels (faop_alo_fast.cu); returns -1000 when no specialisation matches the config
 int launch_alo_fast(const AloArgs& a, cudaStream_t st);
-// Clenshaw-based specialised kernels (faop_alo_clen.cu): Solver A/B, no derivative, n % 4 == 0, n <= 28, l <= 64
+// Clenshaw-based specialised kernels (faop_alo_clen.cu): Solver A/B, no derivative, 2 <= n <= 31, l <= 64
 int launch_alo_clen(const AloArgs& a, cudaStream_t st);
 size_t alo_clen_scratch_bytes(const faop_cfg& cfg);   // 0 when the config does not run there
 

@@ -300,6 +300,32 @@ def test_solver_b_vs_c_oracle():
             assert np.array_equal(np.isnan(out["price"]), np.isnan(ref["price"])), tag
 
 
+def test_specialised_kernels_cover_odd_sizes():
+    """Every (n, l) without the derivative runs on a specialised kernel up to n = 31, l = 64 — including n that are no multiple of
+    the 4-node reduction group and ragged l: same prices, boundaries and sweep counts as the libdevice-accurate generic kernel, and
+    the C oracle on a prefix."""
+    from oracle import c_oracle as co
+    N = 1500
+    b = wl.c2_batch(N)
+    a = [b[k] for k in ("r", "q", "sigma", "K", "T", "S", "is_put")]
+    for solver, n, l, m in (("A", 5, 7, 9), ("A", 6, 10, 30), ("B", 7, 24, 48), ("A", 9, 33, 40), ("B", 10, 40, 64), ("A", 13, 32, 64),
+                            ("B", 15, 64, 64), ("A", 18, 48, 96), ("B", 22, 50, 100), ("A", 27, 64, 128), ("A", 31, 64, 128), ("B", 2, 8, 16)):
+        mi = 40 if solver == "A" else 80
+        spec = _np(batch.price_batch(*a, cfg=AloConfig(solver, n, l, m, 1e-5, mi, kernel=0)))
+        gen = _np(batch.price_batch(*a, cfg=AloConfig(solver, n, l, m, 1e-5, mi, kernel=1)))
+        ok = np.isfinite(gen["price"]) & (gen["err"] < 1e-2)
+        tag = (solver, n, l, m)
+        assert ok.sum() >= 0.9 * N, tag
+        assert np.max(np.abs(spec["price"] - gen["price"])[ok]) <= PRICE_ABS_TOL, tag
+        assert np.nanmax(np.abs(spec["B"] / gen["B"] - 1)[ok]) <= BOUNDARY_REL_TOL, tag
+        assert _flips_are_ties(spec, gen, ok, 1e-5, tag) <= 2, tag
+        assert np.array_equal(np.isnan(spec["price"]), np.isnan(gen["price"])), tag
+        ref = co.alo_price_batch(solver, *[x[:200] for x in a], n=n, l=l, m=m, iter_tol=1e-5, max_iters=mi)
+        okr = np.isfinite(ref["price"]) & (ref["err"] < 1e-2)
+        assert np.max(np.abs(spec["price"][:200] - ref["price"])[okr]) <= PRICE_ABS_TOL, tag
+        assert np.nanmax(np.abs(spec["B"][:200] / ref["B"] - 1)[okr]) <= BOUNDARY_REL_TOL, tag
+
+
 def test_solver_a_derivative_vs_c_oracle():
     """use_derivative=True (the diagonal-Newton step with the analytic f', FastAmericanOptionSolverA.py:46-83, Base.py:276-278)
     through the specialised kernel and the generic one against the plain-C oracle."""
