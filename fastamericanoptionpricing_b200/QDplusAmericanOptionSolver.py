@@ -1,7 +1,7 @@
 """Drop-in for the reference's QDplusAmericanOptionSolver.py: OptionType and QDplus with the same constructor and
 methods; roots, residuals and the QD+ price come from the CUDA leaf kernels (faop_qd_boundary_batch,
-faop_qd_residual_batch, faop_qd_price_batch).  The boundary root uses a safeguarded Newton iteration from x0 = K
-on the device instead of MINPACK hybr (reference :73)."""
+faop_qd_residual_batch, faop_qd_price_batch).  The boundary root is found on the device by the reference's own root finder —
+MINPACK hybrd as scipy.optimize.root(hybr, x0=K) drives it (reference :73), restated for one unknown in csrc/faop_seed.cu."""
 from enum import Enum
 
 import numpy as np
