@@ -156,7 +156,8 @@ def run_reference(args):
     cfg = dict(wl.C2_CFG)
     b = wl.c2_batch(N_PER_GPU)
     rate0, count, _, _ = cpu_port_rate(cfg, b, 2.0, threads)
-    per_step = int(max(64 * threads, min(N_PER_GPU, rate0 * 8.0)))     # ~8 s of CPU work per step
+    step_seconds = float(os.environ.get("FAOP_REF_STEP_SECONDS", "8"))   # ~8 s of CPU work per step (tests shorten it)
+    per_step = int(max(64 * threads, min(N_PER_GPU, rate0 * step_seconds)))
     from oracle import c_oracle as co
     kw = dict(n=cfg["n"], l=cfg["l"], m=cfg["m"], iter_tol=cfg["iter_tol"], max_iters=cfg["max_iters"], nthreads=threads)
     times = []

@@ -89,3 +89,25 @@ def test_host_buffer_checks_without_gpu():
         with pytest.raises(ValueError):
             bad()
     assert hout(np.empty((3, 13)), (3, 13), np.float64, "B").shape == (3, 13)
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside ours): one JSON line with the contract's keys, timed on the
+    plain-C port; needs no GPU and no /root/reference (the Python cross-reference leg reports itself absent)."""
+    import json, os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, FAOP_REF_STEP_SECONDS="0.5", FAOP_REFERENCE="/nonexistent")
+    out = subprocess.run([sys.executable, "bench.py", "--impl", "reference", "--steps", "2", "--warmup", "1"], cwd=root, env=env,
+                         capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    line = json.loads(lines[0])
+    assert line["impl"] == "reference" and line["metric"] == "American options priced/sec (FP64)" and line["unit"] == "options/s"
+    for key in ("value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "dtype", "config",
+                "cpu_baseline", "e2e"):
+        assert key in line, key
+    assert line["steps"] == 2 and line["warmup"] == 1 and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["value"] == line["value"]
+    assert line["e2e"] == {"value": line["value"], "unit": line["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert line["config"]["workload"].startswith("C2")
